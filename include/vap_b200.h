@@ -1,0 +1,109 @@
+/* vap_b200.h — C ABI of libvap_b200.so: the B200 (sm_100a) kernels of the Video-As-Prompt MoT denoise hot path.
+ *
+ * The reference (bytedance/Video-As-Prompt) is pure Python/PyTorch and has no FFI of its own; every entry
+ * point below replaces one PyTorch library call site (or a fused group of them) inside the reference's MoT
+ * block forward.  "Ref:" cites the replaced interface, paths relative to
+ * /root/reference/diffusers/src/diffusers.  INTEGRATION.md shows the ctypes binding a maintainer of the
+ * reference would add.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers owned by the caller (PyTorch allocates every buffer incl. outputs);
+ *     the library never allocates, frees, synchronises a stream or keeps state between calls;
+ *   - bf16 tensors are `uint16_t`-sized elements (torch.bfloat16); vectors of per-channel parameters
+ *     (norm weights, modulation, gates, RoPE tables) are fp32;
+ *   - sizes/strides are in ELEMENTS; the innermost dimension is contiguous;
+ *   - `stream` is a `cudaStream_t` passed as `void*` (torch.cuda.current_stream().cuda_stream);
+ *   - return 0 on success, <0 on error (-1 invalid argument, -2 CUDA runtime error, -3 TMA descriptor
+ *     error); `vap_last_error()` returns the thread-local message.  Nothing is ever computed on the CPU.
+ */
+#ifndef VAP_B200_H
+#define VAP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VAP_B200_VERSION 100 /* major*10000 + minor*100 + patch */
+
+/* Library version (VAP_B200_VERSION of the build). */
+int vap_version(void);
+/* Thread-local message of the last failing call on this thread ("" if none). */
+const char* vap_last_error(void);
+/* Number of SMs of the current device (148 on B200); <0 on error. */
+int vap_sm_count(void);
+
+/* (1) adaLN-modulated LayerNorm over the last dim, one pass (read x once, write out once).
+ *   y = LayerNorm(x, eps)  [* ln_w + ln_b]  [* scale1p[b] + shift[b]]     b = row / rows_per_batch
+ * rounding = 0 (Wan): everything in fp32, one bf16 rounding at the end.
+ *     Ref: transformer_wan_mot.py:620-623, 680-689 (FP32LayerNorm no-affine + (1+scale)/shift modulation),
+ *          :668-669 (norm2: FP32LayerNorm affine, no modulation), normalization.py:85-94.
+ * rounding = 1 (CogVideoX): bf16 roundings after the affine LayerNorm, after the scale multiply and after
+ *     the shift add, like the reference's bf16 tensor ops.
+ *     Ref: CogVideoXLayerNormZero.forward, normalization.py:464-471; nn.LayerNorm norm_final :1045.
+ * scale1p is (1 + scale), precomputed by the caller in the reference's dtype. */
+int vap_adaln_layernorm(const void* x, void* out, int64_t rows, int d, int64_t x_row_stride, int64_t out_row_stride,
+                        const float* ln_w, const float* ln_b, const float* scale1p, const float* shift, int64_t mod_stride,
+                        int64_t rows_per_batch, float eps, int rounding, void* stream);
+
+/* (2) q/k normalisation + rotary embedding, in place on q and k (rows = B * rows_per_batch tokens, each row
+ *     heads*head_dim contiguous channels, consecutive rows row_stride apart — q and k may be column slices
+ *     of the fused QKV projection output).
+ * mode = 0 (Wan): RMSNorm over ALL heads*head_dim channels with weight wq/wk [heads*head_dim] (bq/bk NULL);
+ *     Ref: WanAttnMOTProcessor2_0 transformer_wan_mot.py:218-236, RMSNorm normalization.py:554-568.
+ * mode = 1 (CogVideoX): per-head LayerNorm(head_dim) with weight/bias [head_dim];
+ *     Ref: CogVideoXAttnMOTProcessor2_0 attention_processor.py:2934-2945, apply_rotary_emb embeddings.py:1229-1248.
+ * RoPE: pairs (x[2i], x[2i+1]) of every head are rotated by (cos[t, i], sin[t, i]), tables [rope_rows, head_dim/2]
+ *     fp32, t = (row % rows_per_batch) - rope_row0; tokens with t < 0 (CogVideoX text tokens) are not
+ *     rotated.  cos = sin = NULL disables RoPE; k = NULL normalises q only (cross-attention queries / keys). */
+int vap_qk_norm_rope(void* q, void* k, int64_t rows, int heads, int head_dim, int64_t row_stride, const float* wq,
+                     const float* bq, const float* wk, const float* bk, const float* cos, const float* sin,
+                     int64_t rows_per_batch, int64_t rope_row0, int64_t rope_rows, float eps, int mode, void* stream);
+
+/* (3) Joint attention forward: O = softmax(Q K^T * scale) V, no mask, no dropout, non-causal.
+ *     q [B,H,Lq,D], k/v [B,H,Lkv,D], o [B,H,Lq,D] addressed by element strides (batch, head, token), D
+ *     contiguous, D in {64, 128}; lse (optional, may be NULL) [B,H,Lq] fp32 = log-sum-exp of the scaled scores.
+ *     Ref: F.scaled_dot_product_attention at transformer_wan_mot.py:637-644 (joint [target|ref]),
+ *          cogvideox_transformer_3d_mot.py:424-431 (joint [text|target|text_ref|ref]),
+ *          transformer_wan_mot.py:163-179 (cross-attention); finetrainers attention_dispatch.py:416-458. */
+int vap_attention_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int Lq, int Lkv, int D,
+                      int64_t q_sb, int64_t q_sh, int64_t q_sl, int64_t k_sb, int64_t k_sh, int64_t k_sl, int64_t v_sb,
+                      int64_t v_sh, int64_t v_sl, int64_t o_sb, int64_t o_sh, int64_t o_sl, float scale, void* stream);
+
+/* (4) Linear layer  C[M,N] = epilogue(A[M,K] @ W[N,K]^T + bias[N])  (bf16 in/out, fp32 accumulate).
+ *     Ref: nn.Linear call sites transformer_wan_mot.py:214-216, 241-243; attention.py:1245-1251 (FeedForward);
+ *          attention_processor.py:2923-2925, 2952.
+ * epilogue: 0 bias only;
+ *           1 bias + GELU(tanh)                                                   (activations.py:65-91)
+ *           2 C = bf16(R + bf16(AW+b) * gate)   fp32 gate, fp32 math            (transformer_wan_mot.py:658-663, 684, 693-697)
+ *           3 C = bf16(R + bf16(AW+b))                                            (transformer_wan_mot.py:675-676)
+ *           4 C = bf16(R + bf16(gate * bf16(AW+b)))  bf16-valued gate             (cogvideox_transformer_3d_mot.py:445-446, 457-458)
+ * gate [nbatch, N] fp32 with gate_stride elements between batches, batch = row / rows_per_batch. */
+int vap_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int M, int N, int K,
+                  const void* bias, int epilogue, const void* R, int64_t ldr, const float* gate, int64_t gate_stride,
+                  int64_t rows_per_batch, void* stream);
+
+/* (5) Ulysses sequence-parallel re-layout helpers (head <-> sequence exchange around the joint attention;
+ *     replaces the reference's ring attention, finetrainers attention_dispatch.py:686-773, parallel/ptd.py:515-679).
+ *   pack  : dst[s][l][0:chunk] = src[l][s*chunk : (s+1)*chunk]      s < nsplit, l < L
+ *           src rows are src_row_stride apart; dst rows dst_row_stride apart, dst splits dst_split_stride apart
+ *           (builds the all-to-all #1 send buffer [P, L_loc, 3, H/P*D] from q, k, v column slices of the QKV output)
+ *   unpack: dst[l][s*chunk : (s+1)*chunk] = src[s][l][0:chunk]      (after all-to-all #2: [P, L_loc, H/P*D] -> [L_loc, H*D])
+ *   chunk and all strides are in bf16 elements and must be multiples of 8. */
+int vap_ulysses_pack(const void* src, void* dst, int64_t L, int nsplit, int64_t chunk, int64_t src_row_stride,
+                     int64_t dst_row_stride, int64_t dst_split_stride, void* stream);
+int vap_ulysses_unpack(const void* src, void* dst, int64_t L, int nsplit, int64_t chunk, int64_t src_row_stride,
+                       int64_t src_split_stride, int64_t dst_row_stride, void* stream);
+
+/* (6) Bring-up probe for the tcgen05 descriptors: one CTA computes D[128,N] = A[128,K] * B, fp32 out.
+ *     a_in_tmem: 0 = A from shared memory (K-major, SWIZZLE_128B), 1 = A staged to TMEM as packed bf16.
+ *     b_mn_major: 0 = B is [N,K] (K contiguous), 1 = B is [K,N] (N contiguous; the V operand of P*V).
+ *     Descriptor fields are runtime arguments so alternative encodings can be swept from the test-suite. */
+int vap_probe_umma(const void* A, const void* B, float* Dout, int N, int K, int a_in_tmem, int b_mn_major, int lbo_b, int sbo_b,
+                   int kstep_b, int layout_type, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VAP_B200_H */

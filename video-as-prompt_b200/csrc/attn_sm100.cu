@@ -1,0 +1,333 @@
+// attn_sm100.cu — flash-style joint attention forward on tcgen05 / TMEM / TMA (sm_100a).
+//
+// Replaces F.scaled_dot_product_attention(attn_mask=None, dropout_p=0, is_causal=False) at the MoT joint
+// attention call sites (transformer_wan_mot.py:637-644, cogvideox_transformer_3d_mot.py:424-431) and the
+// per-stream cross-attention (transformer_wan_mot.py:163-179).  q/k/v/o are addressed through explicit
+// (batch, head, token) element strides, so the kernel reads Q, K and V straight out of the fused QKV GEMM
+// output [tokens, 3, H, D] of BOTH streams (no torch.cat, no head-major transpose) and writes O token-major
+// [tokens, H*D], which is the A operand of the output projection.
+//
+// One CTA = one (batch, head, 256 query rows) work item = two 128-row Q tiles that ping-pong on the tensor
+// core (while the softmax warps of tile 0 work, the MMAs of tile 1 run).  12 warps:
+//   warp 0    : TMA producer — Q once, then K_j / V_j tiles into a ring of 128xD bf16 stages (SWIZZLE_128B)
+//   warp 1    : MMA issuer   — S_i = Q_i K_j^T (SS, both K-major), O_i += P_i V_j (A = P from TMEM, B = V MN-major)
+//   warp 2    : TMEM allocator (S0 | S1 | O0 | O1, fp32 columns; P_i is written as packed bf16 over S_i)
+//   warps 4-7 : softmax of Q tile 0 — one thread per query row: tcgen05.ld S row, online softmax in the
+//               exp2 domain, lazy rescale of the O row (only when the running max grew by > 2^8), P -> TMEM
+//   warps 8-11: softmax of Q tile 1
+// The last KV tile is masked against Lkv (TMA zero-fills out-of-range K/V rows).
+#include "vap_kernels.cuh"
+
+namespace vap {
+
+
+constexpr int kAttnThreads = 384;
+constexpr int kBlockM = 128;  // rows per Q tile
+constexpr int kBlockN = 128;  // kv rows per tile
+constexpr float kRescaleThreshold = 8.0f;
+
+template <int D>
+struct AttnCfg {
+    static constexpr int kTileBytes = 128 * D * 2;  // one Q / K / V tile
+    static constexpr int kHalfBytes = 128 * 64 * 2;  // one 64-column (128-byte) swizzle slab
+    static constexpr int kHalves = D / 64;
+    static constexpr int kKvStages = (D == 128) ? 5 : 8;
+    static constexpr int kSmemBytes = 2 * kTileBytes + kKvStages * kTileBytes + 1024 + 256;
+    static constexpr int kTmemCols = 512;
+    static constexpr int kColS0 = 0, kColS1 = 128, kColO0 = 256, kColO1 = 256 + D;
+};
+
+template <int D>
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+    using Cfg = AttnCfg<D>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t q_smem = smem_base;
+    const uint32_t kv_smem = smem_base + 2 * Cfg::kTileBytes;
+    const uint32_t bar_base = kv_smem + Cfg::kKvStages * Cfg::kTileBytes;
+    auto kv_full = [&](int s) { return bar_base + 8u * s; };
+    auto kv_empty = [&](int s) { return bar_base + 8u * (Cfg::kKvStages + s); };
+    const uint32_t q_full = bar_base + 8u * (2 * Cfg::kKvStages);
+    auto s_full = [&](int i) { return bar_base + 8u * (2 * Cfg::kKvStages + 1 + i); };
+    auto p_full = [&](int i) { return bar_base + 8u * (2 * Cfg::kKvStages + 3 + i); };
+    auto o_done = [&](int i) { return bar_base + 8u * (2 * Cfg::kKvStages + 5 + i); };
+    const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * Cfg::kKvStages + 7);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * (2 * kBlockM);
+    const int head = blockIdx.y;
+    const int batch = blockIdx.z;
+    const int n_kv = (p.Lkv + kBlockN - 1) / kBlockN;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmK);
+        tma_prefetch_desc(&tmV);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < Cfg::kKvStages; ++s) {
+            mbar_init(kv_full(s), 1);
+            mbar_init(kv_empty(s), 1);
+        }
+        mbar_init(q_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(s_full(i), 1);
+            mbar_init(p_full(i), 128);
+            mbar_init(o_done(i), 1);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_ptr_addr, Cfg::kTmemCols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            mbar_arrive_expect_tx(q_full, 2 * Cfg::kTileBytes);
+            for (int t = 0; t < 2; ++t)
+                for (int h = 0; h < Cfg::kHalves; ++h)
+                    tma_load_4d(q_smem + t * Cfg::kTileBytes + h * Cfg::kHalfBytes, &tmQ, q_full, h * 64, q0 + t * kBlockM, head, batch);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int j = 0; j < n_kv; ++j) {
+                for (int kv = 0; kv < 2; ++kv) {  // K_j then V_j
+                    mbar_wait(kv_empty(stage), phase ^ 1);
+                    mbar_arrive_expect_tx(kv_full(stage), Cfg::kTileBytes);
+                    const uint32_t dst = kv_smem + stage * Cfg::kTileBytes;
+                    for (int h = 0; h < Cfg::kHalves; ++h)
+                        tma_load_4d(dst + h * Cfg::kHalfBytes, kv == 0 ? &tmK : &tmV, kv_full(stage), h * 64, j * kBlockN, head, batch);
+                    if (++stage == Cfg::kKvStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            constexpr uint32_t idesc_qk = make_idesc_bf16(kBlockM, kBlockN, 0, 0);  // S = Q K^T : A, B K-major
+            constexpr uint32_t idesc_pv = make_idesc_bf16(kBlockM, D, 0, 1);        // O = P V   : A (TMEM) K-major, B MN-major
+            const uint32_t col_s[2] = {tmem_base + Cfg::kColS0, tmem_base + Cfg::kColS1};
+            const uint32_t col_o[2] = {tmem_base + Cfg::kColO0, tmem_base + Cfg::kColO1};
+
+            auto issue_qk = [&](int i, uint32_t k_addr) {
+                const uint32_t q_addr = q_smem + i * Cfg::kTileBytes;
+#pragma unroll
+                for (int k = 0; k < D / 16; ++k) {
+                    const uint32_t off = (k >> 2) * Cfg::kHalfBytes + (k & 3) * 32;
+                    umma_ss(col_s[i], make_smem_desc(q_addr + off, 0, 1024, kLayoutSw128),
+                            make_smem_desc(k_addr + off, 0, 1024, kLayoutSw128), idesc_qk, k != 0 ? 1u : 0u);
+                }
+            };
+            auto issue_pv = [&](int i, uint32_t v_addr, bool accumulate) {
+#pragma unroll
+                for (int k = 0; k < kBlockN / 16; ++k) {
+                    // A: P_i, packed bf16 pairs, 8 TMEM columns per 16 kv;  B: V rows [16k, 16k+16) (2048 B apart),
+                    // MN-major: 64-column slabs kHalfBytes apart (LBO), 8-row groups 1024 B apart (SBO)
+                    umma_ts(col_o[i], col_s[i] + 8 * k, make_smem_desc(v_addr + k * 2048, Cfg::kHalfBytes, 1024, kLayoutSw128),
+                            idesc_pv, (accumulate || k != 0) ? 1u : 0u);
+                }
+            };
+
+            int stage = 0;
+            uint32_t phase = 0;
+            auto advance = [&]() {
+                if (++stage == Cfg::kKvStages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            };
+            mbar_wait(q_full, 0);
+            mbar_wait(kv_full(stage), phase);  // K_0
+            tc_fence_after();
+            issue_qk(0, kv_smem + stage * Cfg::kTileBytes);
+            umma_commit(s_full(0));
+            issue_qk(1, kv_smem + stage * Cfg::kTileBytes);
+            umma_commit(s_full(1));
+            umma_commit(kv_empty(stage));
+            advance();
+            for (int j = 0; j < n_kv; ++j) {
+                const int v_stage = stage;
+                mbar_wait(kv_full(stage), phase);  // V_j
+                advance();
+                const int k_stage = stage;
+                const bool has_next = (j + 1 < n_kv);
+                if (has_next) {
+                    mbar_wait(kv_full(stage), phase);  // K_{j+1}
+                    advance();
+                }
+                for (int i = 0; i < 2; ++i) {
+                    mbar_wait(p_full(i), j & 1);
+                    tc_fence_after();
+                    issue_pv(i, kv_smem + v_stage * Cfg::kTileBytes, j > 0);
+                    umma_commit(o_done(i));
+                    if (has_next) {
+                        issue_qk(i, kv_smem + k_stage * Cfg::kTileBytes);
+                        umma_commit(s_full(i));
+                    }
+                }
+                umma_commit(kv_empty(v_stage));
+                if (has_next) umma_commit(kv_empty(k_stage));
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== softmax + epilogue warps =====
+        const int i = (warp - 4) >> 2;  // Q tile
+        const int q = warp & 3;         // TMEM lane quarter
+        const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+        const uint32_t s_col = tmem_base + lane_addr + (i == 0 ? Cfg::kColS0 : Cfg::kColS1);
+        const uint32_t o_col = tmem_base + lane_addr + (i == 0 ? Cfg::kColO0 : Cfg::kColO1);
+        const int row = q0 + i * kBlockM + q * 32 + lane;
+        const float c = p.scale_log2;
+        float m_used = -INFINITY;
+        float l = 0.f;
+        for (int j = 0; j < n_kv; ++j) {
+            mbar_wait(s_full(i), j & 1);
+            tc_fence_after();
+            uint32_t sr[4][32];
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) tmem_ld_x32(s_col + 32 * ch, sr[ch]);
+            tmem_ld_wait();
+            const int valid = p.Lkv - j * kBlockN;  // >= 1
+            if (valid < kBlockN) {
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+                    for (int e = 0; e < 32; ++e)
+                        if (32 * ch + e >= valid) sr[ch][e] = __float_as_uint(-INFINITY);
+            }
+            float m_t = -INFINITY;
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+                for (int e = 0; e < 32; ++e) m_t = fmaxf(m_t, __uint_as_float(sr[ch][e]));
+            const float m_new = fmaxf(m_used, m_t);
+            if (j == 0) {
+                m_used = m_new;
+            } else {
+                const bool need = (m_new - m_used) * c > kRescaleThreshold;
+                if (__any_sync(0xffffffffu, need)) {
+                    // O_i must be quiescent: PV_{j-1} complete (PV_j cannot start before our p_full arrive)
+                    mbar_wait(o_done(i), (j - 1) & 1);
+                    tc_fence_after();
+                    const float f = exp2f((m_used - m_new) * c);
+                    l *= f;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < D; c0 += 32) {
+                        uint32_t ov[32];
+                        tmem_ld_x32(o_col + c0, ov);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * f);
+                        tmem_st_x32(o_col + c0, ov);
+                    }
+                    tmem_st_wait();
+                    m_used = m_new;
+                }
+            }
+            const float mc = m_used * c;
+            float lsum = 0.f;
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+                uint32_t pk[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const float p0 = exp2f(fmaf(__uint_as_float(sr[ch][2 * e]), c, -mc));
+                    const float p1 = exp2f(fmaf(__uint_as_float(sr[ch][2 * e + 1]), c, -mc));
+                    lsum += p0 + p1;
+                    pk[e] = pack_bf16x2(p0, p1);
+                }
+                tmem_st_x16(s_col + 16 * ch, pk);
+            }
+            l += lsum;
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(p_full(i));
+        }
+        // ===== epilogue: O / l -> bf16 -> global =====
+        mbar_wait(o_done(i), (n_kv - 1) & 1);
+        tc_fence_after();
+        const float inv_l = 1.f / l;
+        const bool row_ok = row < p.Lq;
+        __nv_bfloat16* orow = p.o + batch * p.o_sb + head * p.o_sh + static_cast<int64_t>(row) * p.o_sl;
+#pragma unroll 1
+        for (int c0 = 0; c0 < D; c0 += 32) {
+            uint32_t ov[32];
+            tmem_ld_x32(o_col + c0, ov);
+            tmem_ld_wait();
+            if (row_ok) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    uint4 o;
+                    o.x = pack_bf16x2(__uint_as_float(ov[8 * g + 0]) * inv_l, __uint_as_float(ov[8 * g + 1]) * inv_l);
+                    o.y = pack_bf16x2(__uint_as_float(ov[8 * g + 2]) * inv_l, __uint_as_float(ov[8 * g + 3]) * inv_l);
+                    o.z = pack_bf16x2(__uint_as_float(ov[8 * g + 4]) * inv_l, __uint_as_float(ov[8 * g + 5]) * inv_l);
+                    o.w = pack_bf16x2(__uint_as_float(ov[8 * g + 6]) * inv_l, __uint_as_float(ov[8 * g + 7]) * inv_l);
+                    *reinterpret_cast<uint4*>(orow + c0 + 8 * g) = o;
+                }
+            }
+        }
+        if (p.lse && row_ok)
+            p.lse[(static_cast<int64_t>(batch) * p.H + head) * p.Lq + row] = m_used * p.scale + logf(l);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    }
+}
+
+
+static int make_attn_tmap(CUtensorMap* tm, const AttnTensor& t, int B, int H, int L, int D, const char* name) {
+    VAP_REQUIRE((reinterpret_cast<uintptr_t>(t.ptr) & 15) == 0, "attention: %s must be 16-byte aligned", name);
+    VAP_REQUIRE(t.sl % 8 == 0 && t.sh % 8 == 0 && t.sb % 8 == 0, "attention: %s strides must be multiples of 8 elements", name);
+    const uint64_t dims[4] = {static_cast<uint64_t>(D), static_cast<uint64_t>(L), static_cast<uint64_t>(H), static_cast<uint64_t>(B)};
+    // a size-1 dim may come with stride 0 from the caller; TMA wants a positive multiple of 16 bytes
+    const uint64_t strides[3] = {static_cast<uint64_t>(t.sl > 0 ? t.sl : D), static_cast<uint64_t>(t.sh > 0 ? t.sh : D),
+                                 static_cast<uint64_t>(t.sb > 0 ? t.sb : D)};
+    const uint32_t box[4] = {64, 128, 1, 1};
+    return make_tmap_bf16(tm, t.ptr, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+template <int D>
+static int launch_attn_d(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const AttnParams& p, cudaStream_t stream) {
+    using Cfg = AttnCfg<D>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        VAP_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        attr_set = true;
+    }
+    const dim3 grid((p.Lq + 2 * kBlockM - 1) / (2 * kBlockM), p.H, p.B);
+    attn_fwd_kernel<D><<<grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(tmQ, tmK, tmV, p);
+    VAP_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_attention_fwd(const AttnTensor& q, const AttnTensor& k, const AttnTensor& v, AttnParams p, int D, cudaStream_t stream) {
+    VAP_REQUIRE(D == 64 || D == 128, "attention: head_dim=%d must be 64 or 128", D);
+    VAP_REQUIRE(p.B > 0 && p.H > 0 && p.Lq >= 0 && p.Lkv > 0, "attention: bad shape B=%d H=%d Lq=%d Lkv=%d", p.B, p.H, p.Lq, p.Lkv);
+    VAP_REQUIRE(p.H <= 65535 && p.B <= 65535, "attention: H and B must be <= 65535");
+    VAP_REQUIRE((reinterpret_cast<uintptr_t>(p.o) & 15) == 0 && p.o_sl % 8 == 0 && p.o_sh % 8 == 0 && p.o_sb % 8 == 0,
+                "attention: output must be 16-byte aligned with strides that are multiples of 8 elements");
+    if (p.Lq == 0) return 0;
+    CUtensorMap tmQ, tmK, tmV;
+    if (make_attn_tmap(&tmQ, q, p.B, p.H, p.Lq, D, "q")) return -3;
+    if (make_attn_tmap(&tmK, k, p.B, p.H, p.Lkv, D, "k")) return -3;
+    if (make_attn_tmap(&tmV, v, p.B, p.H, p.Lkv, D, "v")) return -3;
+    return D == 128 ? launch_attn_d<128>(tmQ, tmK, tmV, p, stream) : launch_attn_d<64>(tmQ, tmK, tmV, p, stream);
+}
+
+}  // namespace vap

@@ -1,0 +1,314 @@
+// gemm_sm100.cu — bf16 GEMM  C[M,N] = epilogue(A[M,K] * W[N,K]^T + bias)  on tcgen05 / TMEM / TMA (sm_100a).
+//
+// The MoT projections (fused QKV, O, FFN-in, FFN-out; reference call sites transformer_wan_mot.py:214-216,
+// 241-243, attention.py:1245-1251, attention_processor.py:2923-2925, 2952) are nn.Linear layers:
+// activations [M,K] row-major and weights [N,K] row-major, i.e. both operands K-major — exactly the
+// layout UMMA wants, so neither side is transposed or repacked.
+//
+// Persistent, warp-specialised kernel, one CTA per SM:
+//   warp 0   : TMA producer  (A tile 128x64, W tile BNx64 per stage, SWIZZLE_128B, kStages-deep mbarrier ring)
+//   warp 1   : MMA issuer    (one elected thread, tcgen05.mma cta_group::1 kind::f16, M=128 N=BN K=16)
+//   warp 2   : TMEM allocator (2 accumulator stages x BN fp32 columns)
+//   warps 4-7: epilogue      (tcgen05.ld -> bias / GELU / gated residual with the reference's bf16 rounding
+//                             points -> 16-byte global stores), overlapped with the next tile's main loop.
+#include "vap_kernels.cuh"
+
+namespace vap {
+
+enum GemmEpilogue : int {
+    kEpiBias = 0,         // C = bf16(acc + bias)
+    kEpiBiasGelu = 1,     // C = bf16(gelu_tanh(bf16(acc + bias)))                          activations.py:65-91
+    kEpiGateResF32 = 2,   // C = bf16(float(R) + bf16(acc + bias) * gate[n])   gate fp32      transformer_wan_mot.py:658-663, 684-697
+    kEpiResAdd = 3,       // C = bf16(float(R) + bf16(acc + bias))                            transformer_wan_mot.py:675-676
+    kEpiGateResBf16 = 4,  // C = bf16(float(R) + bf16(gate[n] * bf16(acc + bias)))  gate bf16  cogvideox_transformer_3d_mot.py:445-446
+};
+
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kGemmThreads = 256;
+constexpr int kGroupM = 16;
+
+template <int BN>
+struct GemmCfg {
+    static constexpr int kStages = (BN == 256) ? 4 : 6;
+    static constexpr int kABytes = kBM * kBK * 2;
+    static constexpr int kBBytes = BN * kBK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int kTmemCols = 2 * BN;  // 512 (BN=256) or 256 (BN=128): powers of two
+};
+
+__device__ __forceinline__ void tile_coords(int tile, int m_blocks, int n_blocks, int& mb, int& nb) {
+    // grouped rasterisation: kGroupM M-blocks share the same sweep over N so A and W tiles are reused from L2
+    const int per_group = kGroupM * n_blocks;
+    const int g = tile / per_group;
+    const int r = tile - g * per_group;
+    const int m0 = g * kGroupM;
+    const int gm = min(kGroupM, m_blocks - m0);
+    mb = m0 + r % gm;
+    nb = r / gm;
+}
+
+__device__ __forceinline__ float gelu_tanh_f(float x) {
+    const float kBeta = 0.7978845608028654f;  // sqrt(2/pi)
+    const float kKappa = 0.044715f;
+    const float inner = kBeta * (x + kKappa * x * x * x);
+    return 0.5f * x * (1.f + tanhf(inner));
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+    using Cfg = GemmCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+    // barrier layout (8 B each): full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], tmem_ptr
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + 2 + s); };
+    const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * Cfg::kStages + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_tiles = p.m_blocks * p.n_blocks;
+    const int k_blocks = (p.K + kBK - 1) / kBK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < Cfg::kStages; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(tfull_bar(s), 1);
+            mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_ptr_addr, Cfg::kTmemCols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                int mb, nb;
+                tile_coords(tile, p.m_blocks, p.n_blocks, mb, nb);
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    const uint32_t a_dst = smem_base + stage * Cfg::kStageBytes;
+                    const uint32_t b_dst = a_dst + Cfg::kABytes;
+                    mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+                    tma_load_2d(a_dst, &tmA, full_bar(stage), kb * kBK, mb * kBM);
+                    tma_load_2d(b_dst, &tmB, full_bar(stage), kb * kBK, nb * BN);
+                    if (++stage == Cfg::kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 0, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_base + stage * Cfg::kStageBytes;
+                    const uint32_t b_addr = a_addr + Cfg::kABytes;
+#pragma unroll
+                    for (int k = 0; k < kBK / 16; ++k) {
+                        const uint64_t da = make_smem_desc(a_addr + k * 32, 0, 1024, kLayoutSw128);
+                        const uint64_t db = make_smem_desc(b_addr + k * 32, 0, 1024, kLayoutSw128);
+                        umma_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs have read it
+                    if (++stage == Cfg::kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue warps =====
+        const int q = warp & 3;  // TMEM lane quarter owned by this warp
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            int mb, nb;
+            tile_coords(tile, p.m_blocks, p.n_blocks, mb, nb);
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const int row = mb * kBM + q * 32 + lane;
+            const bool row_ok = row < p.M;
+            const float* gate = nullptr;
+            if (p.gate) gate = p.gate + (p.rows_per_batch > 0 ? (row_ok ? row / p.rows_per_batch : 0) : 0) * p.gate_stride;
+            __nv_bfloat16* crow = p.C + static_cast<int64_t>(row) * p.ldc;
+            const __nv_bfloat16* rrow = p.R ? p.R + static_cast<int64_t>(row) * p.ldr : nullptr;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c0, v);
+                tmem_ld_wait();
+                const int n0 = nb * BN + c0;
+                if (row_ok && n0 < p.N) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {  // 4 groups of 8 columns = 16-byte stores
+                        const int n = n0 + 8 * g;
+                        if (n < p.N) {
+                            float y[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) y[j] = __uint_as_float(v[8 * g + j]);
+                            if (p.bias) {
+                                const uint4 bb = *reinterpret_cast<const uint4*>(p.bias + n);
+                                const uint32_t* bu = reinterpret_cast<const uint32_t*>(&bb);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float2 f = bf16x2_to_float2(bu[j]);
+                                    y[2 * j] += f.x;
+                                    y[2 * j + 1] += f.y;
+                                }
+                            }
+                            if (p.epilogue != kEpiBias) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) y[j] = bf16_round(y[j]);
+                                if (p.epilogue == kEpiBiasGelu) {
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) y[j] = gelu_tanh_f(y[j]);
+                                } else {
+                                    const uint4 rr = *reinterpret_cast<const uint4*>(rrow + n);
+                                    const uint32_t* ru = reinterpret_cast<const uint32_t*>(&rr);
+                                    float r[8];
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        const float2 f = bf16x2_to_float2(ru[j]);
+                                        r[2 * j] = f.x;
+                                        r[2 * j + 1] = f.y;
+                                    }
+                                    if (p.epilogue == kEpiResAdd) {
+#pragma unroll
+                                        for (int j = 0; j < 8; ++j) y[j] = r[j] + y[j];
+                                    } else {
+                                        const float4 g0 = *reinterpret_cast<const float4*>(gate + n);
+                                        const float4 g1 = *reinterpret_cast<const float4*>(gate + n + 4);
+                                        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                                        if (p.epilogue == kEpiGateResF32) {
+#pragma unroll
+                                            for (int j = 0; j < 8; ++j) y[j] = r[j] + y[j] * gg[j];
+                                        } else {
+#pragma unroll
+                                            for (int j = 0; j < 8; ++j) y[j] = r[j] + bf16_round(gg[j] * y[j]);
+                                        }
+                                    }
+                                }
+                            }
+                            uint4 o;
+                            o.x = pack_bf16x2(y[0], y[1]);
+                            o.y = pack_bf16x2(y[2], y[3]);
+                            o.z = pack_bf16x2(y[4], y[5]);
+                            o.w = pack_bf16x2(y[6], y[7]);
+                            *reinterpret_cast<uint4*>(crow + n) = o;
+                        }
+                    }
+                }
+            }
+            // all TMEM reads of this accumulator stage are complete (tmem_ld_wait) -> release it
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    }
+}
+
+template <int BN>
+static int launch_gemm_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams p, cudaStream_t stream) {
+    using Cfg = GemmCfg<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        VAP_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        attr_set = true;
+    }
+    p.m_blocks = (p.M + kBM - 1) / kBM;
+    p.n_blocks = (p.N + BN - 1) / BN;
+    const int tiles = p.m_blocks * p.n_blocks;
+    const int grid = tiles < sm_count() ? tiles : sm_count();
+    gemm_bf16_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+    VAP_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_gemm_bf16(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, GemmParams p, cudaStream_t stream) {
+    VAP_REQUIRE(p.M >= 0 && p.N > 0 && p.K > 0, "gemm_bf16: bad shape M=%d N=%d K=%d", p.M, p.N, p.K);
+    VAP_REQUIRE(p.N % 8 == 0 && p.K % 8 == 0, "gemm_bf16: N=%d and K=%d must be multiples of 8", p.N, p.K);
+    VAP_REQUIRE(lda % 8 == 0 && ldw % 8 == 0 && p.ldc % 8 == 0, "gemm_bf16: leading dimensions must be multiples of 8 elements");
+    VAP_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(p.C) & 15) == 0,
+                "gemm_bf16: A, W and C must be 16-byte aligned");
+    VAP_REQUIRE(p.epilogue >= kEpiBias && p.epilogue <= kEpiGateResBf16, "gemm_bf16: unknown epilogue %d", p.epilogue);
+    if (p.epilogue >= kEpiGateResF32) {
+        VAP_REQUIRE(p.R != nullptr && p.ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(p.R) & 15) == 0,
+                    "gemm_bf16: residual epilogue needs a 16-byte aligned residual with ldr %% 8 == 0");
+        if (p.epilogue != kEpiResAdd) VAP_REQUIRE(p.gate != nullptr, "gemm_bf16: gated epilogue needs a gate vector");
+    }
+    if (p.bias) VAP_REQUIRE((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0, "gemm_bf16: bias must be 16-byte aligned");
+    if (p.M == 0) return 0;
+    const bool wide = p.N >= 256;
+    const int BN = wide ? 256 : 128;
+    CUtensorMap tmA, tmB;
+    {
+        const uint64_t dims[2] = {static_cast<uint64_t>(p.K), static_cast<uint64_t>(p.M)};
+        const uint64_t strides[1] = {static_cast<uint64_t>(lda)};
+        const uint32_t box[2] = {kBK, kBM};
+        if (make_tmap_bf16(&tmA, A, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return -3;
+    }
+    {
+        const uint64_t dims[2] = {static_cast<uint64_t>(p.K), static_cast<uint64_t>(p.N)};
+        const uint64_t strides[1] = {static_cast<uint64_t>(ldw)};
+        const uint32_t box[2] = {kBK, static_cast<uint32_t>(BN)};
+        if (make_tmap_bf16(&tmB, W, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return -3;
+    }
+    return wide ? launch_gemm_bn<256>(tmA, tmB, p, stream) : launch_gemm_bn<128>(tmA, tmB, p, stream);
+}
+
+}  // namespace vap

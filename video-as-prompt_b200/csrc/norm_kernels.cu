@@ -1,0 +1,301 @@
+// norm_kernels.cu — HBM-bound kernels of the MoT block (sm_100a).
+//
+//  * adaln_layernorm_kernel : (adaLN-modulated) LayerNorm, one warp per token row, the row lives in
+//    registers (16-byte vector loads, read once / written once: 4 B per element of algorithmic traffic).
+//      Wan : (LN_fp32(x) [*w+b]) * (1+scale) + shift -> bf16            transformer_wan_mot.py:620-623, 668-669, 680-689
+//      Cog : bf16(bf16(bf16(LN_affine(x)) * bf16(1+scale)) + shift)     normalization.py:464-471
+//  * qk_norm_rope_kernel    : q/k normalisation + temporally-biased RoPE, in place on the joint q|k|v buffer.
+//      Wan : RMSNorm across all H*D channels (fp32 variance, bf16 rounding before the weight multiply,
+//            normalization.py:554-568) + complex RoPE on interleaved pairs (transformer_wan_mot.py:229-236)
+//      Cog : per-head LayerNorm(D, eps 1e-6, affine) (attention_processor.py:2934-2937) + real cos/sin RoPE
+//            on video tokens only (attention_processor.py:2943-2945, embeddings.py:1229-1248)
+#include "vap_kernels.cuh"
+
+namespace vap {
+
+constexpr int kWarpsPerBlock = 8;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// (adaLN) LayerNorm
+// ------------------------------------------------------------------------------------------
+
+template <int MAXV>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) adaln_layernorm_kernel(LnParams p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (row >= p.rows) return;
+    const int nvec = p.d >> 3;  // 8 bf16 per 16-byte vector
+    const __nv_bfloat16* xr = p.x + row * p.x_stride;
+
+    uint4 raw[MAXV];
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int v = lane + 32 * i;
+        if (v < nvec) raw[i] = ld_nc_v4(xr + 8 * v);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        if (lane + 32 * i < nvec) {
+            const uint32_t* u = reinterpret_cast<const uint32_t*>(&raw[i]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float2 f = bf16x2_to_float2(u[j]);
+                sum += f.x + f.y;
+            }
+        }
+    }
+    const float mean = warp_sum(sum) / static_cast<float>(p.d);
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        if (lane + 32 * i < nvec) {
+            const uint32_t* u = reinterpret_cast<const uint32_t*>(&raw[i]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float2 f = bf16x2_to_float2(u[j]);
+                const float a = f.x - mean, b = f.y - mean;
+                sq += a * a + b * b;
+            }
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(p.d) + p.eps);
+
+    const int64_t batch = p.rows_per_batch > 0 ? row / p.rows_per_batch : 0;
+    const float* s1p = p.scale1p ? p.scale1p + batch * p.mod_stride : nullptr;
+    const float* shf = p.shift ? p.shift + batch * p.mod_stride : nullptr;
+    __nv_bfloat16* orow = p.out + row * p.out_stride;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int v = lane + 32 * i;
+        if (v < nvec) {
+            const uint32_t* u = reinterpret_cast<const uint32_t*>(&raw[i]);
+            float y[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float2 f = bf16x2_to_float2(u[j]);
+                y[2 * j] = (f.x - mean) * rstd;
+                y[2 * j + 1] = (f.y - mean) * rstd;
+            }
+            const int c = 8 * v;
+            if (p.ln_w) {
+                const float4 w0 = *reinterpret_cast<const float4*>(p.ln_w + c), w1 = *reinterpret_cast<const float4*>(p.ln_w + c + 4);
+                const float4 b0 = *reinterpret_cast<const float4*>(p.ln_b + c), b1 = *reinterpret_cast<const float4*>(p.ln_b + c + 4);
+                const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) y[j] = y[j] * w[j] + b[j];
+            }
+            if (p.cog_rounding) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) y[j] = bf16_round(y[j]);
+            }
+            if (s1p) {
+                const float4 s0 = *reinterpret_cast<const float4*>(s1p + c), s1 = *reinterpret_cast<const float4*>(s1p + c + 4);
+                const float4 h0 = *reinterpret_cast<const float4*>(shf + c), h1 = *reinterpret_cast<const float4*>(shf + c + 4);
+                const float s[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                const float h[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+                if (p.cog_rounding) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) y[j] = bf16_round(y[j] * s[j]) + h[j];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) y[j] = y[j] * s[j] + h[j];
+                }
+            }
+            uint4 o;
+            o.x = pack_bf16x2(y[0], y[1]);
+            o.y = pack_bf16x2(y[2], y[3]);
+            o.z = pack_bf16x2(y[4], y[5]);
+            o.w = pack_bf16x2(y[6], y[7]);
+            st_v4(orow + c, o);
+        }
+    }
+}
+
+int launch_adaln_layernorm(const LnParams& p, cudaStream_t stream) {
+    VAP_REQUIRE(p.d % 8 == 0 && p.d >= 8 && p.d <= 8192, "adaln_layernorm: d=%d must be a multiple of 8 and <= 8192", p.d);
+    VAP_REQUIRE(p.x_stride % 8 == 0 && p.out_stride % 8 == 0, "adaln_layernorm: row strides must be multiples of 8 elements");
+    VAP_REQUIRE((p.ln_w == nullptr) == (p.ln_b == nullptr), "adaln_layernorm: ln_w and ln_b must both be given or both null");
+    VAP_REQUIRE((p.scale1p == nullptr) == (p.shift == nullptr), "adaln_layernorm: scale1p and shift must both be given or both null");
+    if (p.rows == 0) return 0;
+    const int nvec = p.d / 8;
+    const unsigned grid = static_cast<unsigned>((p.rows + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    const dim3 block(kWarpsPerBlock * 32);
+    if (nvec <= 32 * 4)
+        adaln_layernorm_kernel<4><<<grid, block, 0, stream>>>(p);
+    else if (nvec <= 32 * 12)
+        adaln_layernorm_kernel<12><<<grid, block, 0, stream>>>(p);
+    else if (nvec <= 32 * 20)
+        adaln_layernorm_kernel<20><<<grid, block, 0, stream>>>(p);
+    else
+        adaln_layernorm_kernel<32><<<grid, block, 0, stream>>>(p);
+    VAP_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// q/k norm + RoPE (in place)
+// ------------------------------------------------------------------------------------------
+
+// One warp per token row; processes q then k.  Every lane always owns the same 8 channels of a head
+// (vector v = lane + 32*i  ->  channel-in-head 8*(v % (D/8)) = 8*(lane % (D/8)) because 32 % (D/8) == 0),
+// so its 4 RoPE (cos,sin) pairs and (Cog) its per-head LN affine values are loaded once.
+template <int MAXV, bool COG>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) qk_norm_rope_kernel(QkParams p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (row >= p.rows) return;
+    const int d = p.heads * p.head_dim;
+    const int nvec = d >> 3;
+    const int vec_per_head = p.head_dim >> 3;
+    const int ch = 8 * (lane % vec_per_head);  // channel offset inside the head
+
+    const int64_t pos = p.rows_per_batch > 0 ? row % p.rows_per_batch : row;
+    const bool rotate = (p.cos != nullptr) && pos >= p.rope_row0 && (pos - p.rope_row0) < p.rope_rows;
+    float cs[4] = {1.f, 1.f, 1.f, 1.f}, sn[4] = {0.f, 0.f, 0.f, 0.f};
+    if (rotate) {
+        const int64_t t = (pos - p.rope_row0) * (p.head_dim >> 1) + (ch >> 1);
+        const float4 c4 = *reinterpret_cast<const float4*>(p.cos + t);
+        const float4 s4 = *reinterpret_cast<const float4*>(p.sin + t);
+        cs[0] = c4.x, cs[1] = c4.y, cs[2] = c4.z, cs[3] = c4.w;
+        sn[0] = s4.x, sn[1] = s4.y, sn[2] = s4.z, sn[3] = s4.w;
+    }
+
+    const int n_which = p.k ? 2 : 1;  // k == null: normalise q only (cross-attention queries)
+#pragma unroll 1
+    for (int which = 0; which < n_which; ++which) {
+        __nv_bfloat16* xr = (which == 0 ? p.q : p.k) + row * p.row_stride;
+        const float* w = which == 0 ? p.wq : p.wk;
+        const float* b = which == 0 ? p.bq : p.bk;
+        uint4 raw[MAXV];
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int v = lane + 32 * i;
+            if (v < nvec) raw[i] = *reinterpret_cast<const uint4*>(xr + 8 * v);
+        }
+        float rs = 0.f;  // Wan: rsqrt(mean(x^2) + eps) over the whole row
+        if (!COG) {
+            float sq = 0.f;
+#pragma unroll
+            for (int i = 0; i < MAXV; ++i) {
+                if (lane + 32 * i < nvec) {
+                    const uint32_t* u = reinterpret_cast<const uint32_t*>(&raw[i]);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float2 f = bf16x2_to_float2(u[j]);
+                        sq += f.x * f.x + f.y * f.y;
+                    }
+                }
+            }
+            rs = rsqrtf(warp_sum(sq) / static_cast<float>(d) + p.eps);
+        }
+        float wl[8], bl[8];
+        if (COG) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                wl[j] = w[ch + j];
+                bl[j] = b[ch + j];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int v = lane + 32 * i;
+            // NOTE: the shuffles below need all lanes of a head group; nvec is a multiple of vec_per_head and
+            // vec_per_head divides 32, so a head is never split between an active and an inactive lane.
+            const bool active = v < nvec;
+            float y[8];
+            {
+                const uint32_t* u = reinterpret_cast<const uint32_t*>(&raw[i]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float2 f = active ? bf16x2_to_float2(u[j]) : make_float2(0.f, 0.f);
+                    y[2 * j] = f.x;
+                    y[2 * j + 1] = f.y;
+                }
+            }
+            if (COG) {
+                // per-head LayerNorm: reduce over the vec_per_head lanes holding this head
+                float s = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s += y[j];
+                for (int o = vec_per_head >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                const float mean = s / static_cast<float>(p.head_dim);
+                float q2 = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float a = y[j] - mean;
+                    q2 += a * a;
+                }
+                for (int o = vec_per_head >> 1; o > 0; o >>= 1) q2 += __shfl_xor_sync(0xffffffffu, q2, o);
+                const float rstd = rsqrtf(q2 / static_cast<float>(p.head_dim) + p.eps);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) y[j] = bf16_round((y[j] - mean) * rstd * wl[j] + bl[j]);
+            } else {
+                if (active) {
+                    const float4 w0 = *reinterpret_cast<const float4*>(w + 8 * v), w1 = *reinterpret_cast<const float4*>(w + 8 * v + 4);
+                    const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) y[j] = bf16_round(bf16_round(y[j] * rs) * ww[j]);
+                }
+            }
+            if (active) {
+                if (rotate) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float xr_ = y[2 * j], xi_ = y[2 * j + 1];
+                        y[2 * j] = xr_ * cs[j] - xi_ * sn[j];
+                        y[2 * j + 1] = xi_ * cs[j] + xr_ * sn[j];
+                    }
+                }
+                uint4 o;
+                o.x = pack_bf16x2(y[0], y[1]);
+                o.y = pack_bf16x2(y[2], y[3]);
+                o.z = pack_bf16x2(y[4], y[5]);
+                o.w = pack_bf16x2(y[6], y[7]);
+                *reinterpret_cast<uint4*>(xr + 8 * v) = o;
+            }
+        }
+    }
+}
+
+int launch_qk_norm_rope(const QkParams& p, int cog_mode, cudaStream_t stream) {
+    const int d = p.heads * p.head_dim;
+    VAP_REQUIRE(p.head_dim == 64 || p.head_dim == 128 || p.head_dim == 32 || p.head_dim == 256,
+                "qk_norm_rope: head_dim=%d must be 32, 64, 128 or 256", p.head_dim);
+    VAP_REQUIRE(d <= 8192, "qk_norm_rope: heads*head_dim=%d must be <= 8192", d);
+    VAP_REQUIRE(p.row_stride % 8 == 0, "qk_norm_rope: row stride must be a multiple of 8 elements");
+    VAP_REQUIRE((p.cos == nullptr) == (p.sin == nullptr), "qk_norm_rope: cos and sin must both be given or both null");
+    VAP_REQUIRE(p.wq && (p.wk || !p.k), "qk_norm_rope: norm weights are required");
+    if (cog_mode) VAP_REQUIRE(p.bq && (p.bk || !p.k), "qk_norm_rope: per-head LayerNorm needs biases");
+    if (p.rows == 0) return 0;
+    const int nvec = d / 8;
+    const unsigned grid = static_cast<unsigned>((p.rows + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    const dim3 block(kWarpsPerBlock * 32);
+#define VAP_QK_LAUNCH(MV)                                                              \
+    do {                                                                               \
+        if (cog_mode)                                                                  \
+            qk_norm_rope_kernel<MV, true><<<grid, block, 0, stream>>>(p);              \
+        else                                                                           \
+            qk_norm_rope_kernel<MV, false><<<grid, block, 0, stream>>>(p);             \
+    } while (0)
+    if (nvec <= 32 * 4)
+        VAP_QK_LAUNCH(4);
+    else if (nvec <= 32 * 12)
+        VAP_QK_LAUNCH(12);
+    else if (nvec <= 32 * 20)
+        VAP_QK_LAUNCH(20);
+    else
+        VAP_QK_LAUNCH(32);
+#undef VAP_QK_LAUNCH
+    VAP_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace vap

@@ -1,0 +1,81 @@
+// vap_kernels.cuh — parameter structs and launcher declarations shared by the kernel translation units and capi.cu.
+#pragma once
+#include "vap_common.cuh"
+
+namespace vap {
+
+struct LnParams {
+    const __nv_bfloat16* x;
+    __nv_bfloat16* out;
+    int64_t rows;
+    int d;
+    int64_t x_stride, out_stride;  // elements
+    const float* ln_w;             // [d] or null
+    const float* ln_b;             // [d] or null
+    const float* scale1p;          // [(nbatch), d] (1 + scale) or null
+    const float* shift;            // [(nbatch), d] or null
+    int64_t mod_stride;            // elements between batches' modulation vectors
+    int64_t rows_per_batch;
+    float eps;
+    int cog_rounding;  // 1: round to bf16 after LN-affine, after the scale multiply and after the shift add
+};
+int launch_adaln_layernorm(const LnParams& p, cudaStream_t stream);
+
+struct QkParams {
+    __nv_bfloat16* q;
+    __nv_bfloat16* k;
+    int64_t rows;  // B * L
+    int heads, head_dim;
+    int64_t row_stride;  // elements, same for q and k
+    const float* wq;     // Wan: [H*D]; Cog: [D]
+    const float* bq;     // Cog only [D]
+    const float* wk;
+    const float* bk;
+    const float* cos;  // [rope_rows, D/2] fp32 (pair i: cos[i], sin[i]); null -> no RoPE
+    const float* sin;
+    int64_t rows_per_batch;  // L
+    int64_t rope_row0;       // positions < rope_row0 inside a batch are not rotated (Cog text tokens)
+    int64_t rope_rows;       // rows in the table
+    float eps;
+};
+int launch_qk_norm_rope(const QkParams& p, int cog_mode, cudaStream_t stream);
+
+struct AttnParams {
+    int B, H, Lq, Lkv;
+    __nv_bfloat16* o;
+    int64_t o_sb, o_sh, o_sl;  // element strides of O
+    float* lse;                // [B, H, Lq] or null
+    float scale_log2;          // softmax scale * log2(e)
+    float scale;
+};
+struct AttnTensor {
+    const __nv_bfloat16* ptr;
+    int64_t sb, sh, sl;  // element strides (batch, head, token); the head_dim axis is contiguous
+};
+int launch_attention_fwd(const AttnTensor& q, const AttnTensor& k, const AttnTensor& v, AttnParams p, int D, cudaStream_t stream);
+
+struct GemmParams {
+    int M, N, K;
+    __nv_bfloat16* C;
+    int64_t ldc;
+    const __nv_bfloat16* bias;  // [N] or null
+    int epilogue;
+    const __nv_bfloat16* R;  // residual [M, ldr]
+    int64_t ldr;
+    const float* gate;  // [(nbatch), N] fp32
+    int64_t gate_stride;
+    int64_t rows_per_batch;
+    int m_blocks, n_blocks;
+};
+int launch_gemm_bf16(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, GemmParams p, cudaStream_t stream);
+
+struct ProbeParams {
+    const __nv_bfloat16* A;  // [128, K] row-major (used directly when a_in_tmem)
+    float* Dout;             // [128, N]
+    int N, K;
+    int a_in_tmem, b_mn_major;
+    uint32_t lbo_b, sbo_b, kstep_b, layout_type;
+};
+int launch_probe_umma(const __nv_bfloat16* A, const __nv_bfloat16* B, ProbeParams p, cudaStream_t stream);
+
+}  // namespace vap

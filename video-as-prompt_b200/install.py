@@ -1,0 +1,70 @@
+"""`install(model)`: make a reference (or stand-alone) MoT transformer run its blocks on the sm_100a kernels.
+
+The module tree, parameter names and `state_dict()` keys are left untouched — `from_pretrained`, LoRA target regexes,
+FSDP wrapping and the trainer's `"_mot_ref" in name` trainable filter (finetrainers/trainer/sft_trainer/trainer.py:154-164)
+keep working.  Three seams, from coarse to fine:
+
+  level="block"      rebind `forward` on every WanTransformerBlock / CogVideoXBlock instance to the fused forward
+                     (B3; precedent for rebinding: finetrainers/patches/models/wan/patch.py:22-25)
+  level="processor"  swap the attention processors for the same-named ones of this package (B1), keep the reference's
+                     block arithmetic, and route the block's F.scaled_dot_product_attention call to `joint_sdpa` (B2)
+  level="sdpa"       only replace F.scaled_dot_product_attention (B2)
+"""
+from __future__ import annotations
+
+import types
+
+import torch.nn as nn
+
+from . import cogvideox, sdpa, wan
+
+_WAN_PROC = {"WanAttnMOTProcessor2_0": wan.WanAttnMOTProcessor2_0, "WanAttnCrossMOTProcessor2_0": wan.WanAttnCrossMOTProcessor2_0,
+             "WanAttnProcessor2_0": wan.WanAttnProcessor2_0}
+_COG_PROC = {"CogVideoXAttnMOTProcessor2_0": cogvideox.CogVideoXAttnMOTProcessor2_0, "CogVideoXAttnProcessor2_0": cogvideox.CogVideoXAttnProcessor2_0}
+
+
+def _blocks(model: nn.Module):
+    if hasattr(model, "blocks"):
+        return "wan", list(model.blocks)
+    if hasattr(model, "transformer_blocks"):
+        return "cog", list(model.transformer_blocks)
+    raise TypeError(f"{type(model).__name__} has neither `.blocks` (Wan) nor `.transformer_blocks` (CogVideoX)")
+
+
+def install(model: nn.Module, level: str = "block") -> nn.Module:
+    family, blocks = _blocks(model)
+    if level == "block":
+        fwd = wan.wan_block_forward if family == "wan" else cogvideox.cog_block_forward
+        for blk in blocks:
+            if not hasattr(blk, "with_mot_ref"):
+                raise TypeError(f"{type(blk).__name__} is not a MoT block (no `with_mot_ref`)")
+            blk.__dict__["_vap_original_forward"] = blk.forward
+            blk.forward = types.MethodType(fwd, blk)
+    elif level == "processor":
+        table = _WAN_PROC if family == "wan" else _COG_PROC
+        for blk in blocks:
+            for m in blk.modules():
+                proc = getattr(m, "processor", None)
+                if proc is not None and type(proc).__name__ in table and hasattr(m, "set_processor"):
+                    m.__dict__.setdefault("_vap_original_processor", proc)
+                    m.set_processor(table[type(proc).__name__]())
+        sdpa.patch_scaled_dot_product_attention()
+    elif level == "sdpa":
+        sdpa.patch_scaled_dot_product_attention()
+    else:
+        raise ValueError(f"unknown level {level!r}; expected 'block', 'processor' or 'sdpa'")
+    return model
+
+
+def uninstall(model: nn.Module) -> nn.Module:
+    _, blocks = _blocks(model)
+    for blk in blocks:
+        orig = blk.__dict__.pop("_vap_original_forward", None)
+        if orig is not None:
+            del blk.forward
+        for m in blk.modules():
+            proc = m.__dict__.pop("_vap_original_processor", None)
+            if proc is not None:
+                m.set_processor(proc)
+    sdpa.unpatch_scaled_dot_product_attention()
+    return model

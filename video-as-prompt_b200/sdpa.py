@@ -1,0 +1,50 @@
+"""Boundary B2: a drop-in for the `F.scaled_dot_product_attention` slot the MoT blocks call
+(transformer_wan_mot.py:637-644, cogvideox_transformer_3d_mot.py:424-431), with the signature of finetrainers'
+`attention_dispatch` (finetrainers/models/attention_dispatch.py:416-458) so it can be installed the same way
+finetrainers installs its own dispatcher (finetrainers/patches/__init__.py:66-69)."""
+from __future__ import annotations
+
+from typing import Any, Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+from . import ops
+
+_ORIGINAL_SDPA = None
+
+
+def joint_sdpa(query: torch.Tensor, key: torch.Tensor, value: torch.Tensor, attn_mask: Optional[torch.Tensor] = None,
+               dropout_p: float = 0.0, is_causal: bool = False, scale: Optional[float] = None, enable_gqa: bool = False,
+               attention_kwargs: Optional[Dict[str, Any]] = None) -> torch.Tensor:
+    """[B,H,L,D] in, [B,H,L,D] out, same dtype.  Constraint violations raise ValueError like attention_dispatch's
+    provider checks (attention_dispatch.py:471-530); nothing silently falls back to another backend."""
+    if attn_mask is not None:
+        raise ValueError("joint_sdpa: attn_mask is not supported (the MoT joint attention is unmasked)")
+    if dropout_p != 0.0:
+        raise ValueError("joint_sdpa: dropout_p must be 0.0")
+    if is_causal:
+        raise ValueError("joint_sdpa: is_causal=True is not supported")
+    if enable_gqa or key.shape[1] != query.shape[1]:
+        raise ValueError("joint_sdpa: grouped-query attention is not supported")
+    if query.dtype != torch.bfloat16 or key.dtype != torch.bfloat16 or value.dtype != torch.bfloat16:
+        raise ValueError(f"joint_sdpa: q/k/v must be bfloat16, got {query.dtype}/{key.dtype}/{value.dtype}")
+    if query.shape[-1] not in (64, 128):
+        raise ValueError(f"joint_sdpa: head_dim {query.shape[-1]} not in (64, 128)")
+    q, k, v = (t if t.stride(-1) == 1 else t.contiguous() for t in (query, key, value))
+    return ops.attention(q, k, v, scale=scale)
+
+
+def patch_scaled_dot_product_attention() -> None:
+    """Install `joint_sdpa` as torch.nn.functional.scaled_dot_product_attention (mirrors finetrainers/patches/__init__.py:66-69)."""
+    global _ORIGINAL_SDPA
+    if _ORIGINAL_SDPA is None:
+        _ORIGINAL_SDPA = F.scaled_dot_product_attention
+    F.scaled_dot_product_attention = joint_sdpa
+
+
+def unpatch_scaled_dot_product_attention() -> None:
+    global _ORIGINAL_SDPA
+    if _ORIGINAL_SDPA is not None:
+        F.scaled_dot_product_attention = _ORIGINAL_SDPA
+        _ORIGINAL_SDPA = None

@@ -1,0 +1,422 @@
+"""Wan2.1-VAP: fused MoT block forward, drop-in attention processors and the stand-alone transformer shell.
+
+Reference (paths relative to /root/reference/diffusers/src/diffusers/models/transformers/transformer_wan_mot.py):
+  WanTransformerBlock.forward :566-699   -> `wan_block_forward`  (boundary B3: rebind on the reference's block instances)
+  WanAttnMOTProcessor2_0      :193-244   -> `WanAttnMOTProcessor2_0`       (boundary B1, same __call__ kwargs)
+  WanAttnCrossMOTProcessor2_0 :110-190   -> `WanAttnCrossMOTProcessor2_0`
+  WanAttnProcessor2_0         :34-107    -> `WanAttnProcessor2_0`
+  WanTransformer3DMOTModel    :702-1000  -> `WanTransformer3DMOTModel` (same constructor kwargs, module tree, state_dict keys)
+
+Data layout of one MoT block on the device (B = 1 per CFG pass, S target tokens, Sr reference tokens, J = S + Sr):
+  qkv   [B, J, 3*d]  the fused QKV projections of BOTH streams write into one joint buffer (target rows first, then
+                     the reference rows), so the joint attention needs no torch.cat: q = qkv[..., :d], k = [..., d:2d],
+                     v = [..., 2d:] are strided views the attention kernel reads through TMA descriptors;
+  o     [B, J, d]    attention output, token-major = the A operand of the two output projections;
+  everything else is [B, S, d] / [B, Sr, d] bf16 as in the reference.
+"""
+from __future__ import annotations
+
+import math
+from typing import Any, Dict, List, Optional, Tuple, Union
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .modules import Attention, FeedForward, FP32LayerNorm, PixArtAlphaTextProjection, TimestepEmbedding
+from .rope import Tables, as_tables, wan_rope_tables
+
+TEXT_CONTEXT_LEN = 512  # hardcoded by the reference (:126-127)
+
+
+# ----------------------------------------------------------------------------------------------
+# cached, packed views of a module's parameters
+# ----------------------------------------------------------------------------------------------
+def _f32(owner: nn.Module, name: str, t: torch.Tensor) -> torch.Tensor:
+    """fp32 copy of a small per-channel parameter, refreshed when the parameter storage or version changes."""
+    cache = owner.__dict__.setdefault("_vap_f32", {})
+    key = (t.data_ptr(), t._version, t.device)
+    ent = cache.get(name)
+    if ent is None or ent[0] != key:
+        ent = (key, t.detach().to(torch.float32).contiguous())
+        cache[name] = ent
+    return ent[1]
+
+
+def _packed(owner: nn.Module, name: str, linears: List[nn.Linear]) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """Concatenate the weights (and biases) of several Linear layers that share their input into one [sum N, K]
+    matrix, ONCE, and re-point the original parameters at views of the packed storage — no duplicate memory, and
+    `state_dict()` / `load_state_dict()` keep working on the original names."""
+    cache = owner.__dict__.setdefault("_vap_packed", {})
+    ent = cache.get(name)
+    w0 = linears[0].weight
+    if ent is not None and ent[0].device == w0.device and w0.data_ptr() == ent[0].data_ptr():
+        return ent
+    with torch.no_grad():
+        W = torch.cat([l.weight.detach() for l in linears], dim=0).contiguous()
+        has_bias = linears[0].bias is not None
+        bvec = torch.cat([l.bias.detach() for l in linears], dim=0).contiguous() if has_bias else None
+        r = 0
+        for l in linears:
+            n = l.weight.shape[0]
+            l.weight.data = W[r:r + n]
+            if has_bias:
+                l.bias.data = bvec[r:r + n]
+            r += n
+    cache[name] = (W, bvec)
+    return cache[name]
+
+
+def _linear(lin: nn.Linear, x: torch.Tensor, **kw) -> torch.Tensor:
+    return ops.linear(x, lin.weight, lin.bias, **kw)
+
+
+def _heads_view(t: torch.Tensor, heads: int) -> torch.Tensor:
+    """[B, L, H*D] (row-strided) -> [B, H, L, D] strided view (no copy)."""
+    B, L, _ = t.shape
+    return t.unflatten(2, (heads, -1)).transpose(1, 2)
+
+
+def _token_major(o: torch.Tensor) -> torch.Tensor:
+    """[B, H, L, D] -> [B, L, H*D]; free when o came from ops.attention (token-major memory)."""
+    return o.transpose(1, 2).flatten(2, 3)
+
+
+# ----------------------------------------------------------------------------------------------
+# attention halves shared by the block forward and the processors
+# ----------------------------------------------------------------------------------------------
+def _self_attn_qkv(attn: nn.Module, x: torch.Tensor, tables: Optional[Tables], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Fused QKV projection + RMSNorm-across-heads + RoPE of one stream (:214-236).  x [B, L, d] -> qkv [B, L, 3*inner]
+    (written into `out` if given, which may be a row-slice of the joint buffer)."""
+    W, bvec = _packed(attn, "qkv", [attn.to_q, attn.to_k, attn.to_v])
+    inner = W.shape[0] // 3
+    B, L, _ = x.shape
+    if out is None:
+        out = torch.empty((B, L, 3 * inner), dtype=torch.bfloat16, device=x.device)
+    heads = attn.heads
+    for b in range(B):  # rows of one batch are uniformly strided inside the joint buffer
+        ops.linear(x[b], W, bvec, out=out[b])
+        q, k = out[b, :, :inner], out[b, :, inner:2 * inner]
+        ops.qk_norm_rope_(q, k, heads=heads, head_dim=inner // heads, wq=_f32(attn.norm_q, "w", attn.norm_q.weight),
+                          wk=_f32(attn.norm_k, "w", attn.norm_k.weight), cos=tables[0] if tables else None,
+                          sin=tables[1] if tables else None, rows_per_batch=L, eps=attn.norm_q.eps, mode=ops.QK_WAN)
+    return out
+
+
+def _split_qkv(qkv: torch.Tensor, heads: int):
+    inner = qkv.shape[-1] // 3
+    return (_heads_view(qkv[..., :inner], heads), _heads_view(qkv[..., inner:2 * inner], heads), _heads_view(qkv[..., 2 * inner:], heads))
+
+
+def _cross_attn(attn: nn.Module, x: torch.Tensor, ctx: torch.Tensor, num_mot_ref: int = 1) -> torch.Tensor:
+    """WanAttnCrossMOTProcessor2_0 arithmetic (:115-186) up to (and excluding) to_out: returns o_text + o_image [B, L, d]."""
+    if num_mot_ref != 1:
+        raise NotImplementedError("num_mot_ref > 1 is rejected by the reference block itself (transformer_wan_mot.py:611)")
+    heads = attn.heads
+    img_len = ctx.shape[1] - TEXT_CONTEXT_LEN * num_mot_ref
+    ctx_img, ctx_txt = ctx[:, :img_len], ctx[:, img_len:]
+    inner = attn.to_q.weight.shape[0]
+    hd = inner // heads
+    eps = attn.norm_q.eps
+    q = _linear(attn.to_q, x)
+    ops.qk_norm_rope_(q, None, heads=heads, head_dim=hd, wq=_f32(attn.norm_q, "w", attn.norm_q.weight), rows_per_batch=q.shape[1], eps=eps,
+                      mode=ops.QK_WAN)
+    Wkv, bkv = _packed(attn, "kv", [attn.to_k, attn.to_v])
+    kv = ops.linear(ctx_txt, Wkv, bkv)
+    ops.qk_norm_rope_(kv[..., :inner], None, heads=heads, head_dim=hd, wq=_f32(attn.norm_k, "w", attn.norm_k.weight),
+                      rows_per_batch=kv.shape[1], eps=eps, mode=ops.QK_WAN)
+    qh = _heads_view(q, heads)
+    o = ops.attention(qh, _heads_view(kv[..., :inner], heads), _heads_view(kv[..., inner:], heads))
+    o = _token_major(o)
+    if img_len > 0 and getattr(attn, "add_k_proj", None) is not None:
+        Wi, bi = _packed(attn, "kv_img", [attn.add_k_proj, attn.add_v_proj])
+        kvi = ops.linear(ctx_img, Wi, bi)
+        ops.qk_norm_rope_(kvi[..., :inner], None, heads=heads, head_dim=hd, wq=_f32(attn.norm_added_k, "w", attn.norm_added_k.weight),
+                          rows_per_batch=kvi.shape[1], eps=eps, mode=ops.QK_WAN)
+        o_img = _token_major(ops.attention(qh, _heads_view(kvi[..., :inner], heads), _heads_view(kvi[..., inner:], heads)))
+        o = o + o_img  # two independent softmaxes summed in bf16 (:186)
+    return o
+
+
+# ----------------------------------------------------------------------------------------------
+# fused block forward  (boundary B3)
+# ----------------------------------------------------------------------------------------------
+def _modulation(table: torch.Tensor, temb: torch.Tensor):
+    """(scale_shift_table + temb.float()).chunk(6, dim=1) (:606-608) -> fp32 [B,1,d] views; scale chunks come back as 1+scale."""
+    mod = table + temb.float()  # fresh fp32 [B,6,d]
+    mod[:, 1] += 1  # (1 + scale_msa), fp32 like the reference
+    mod[:, 4] += 1  # (1 + c_scale_msa)
+    shift, scale1p, gate, c_shift, c_scale1p, c_gate = mod.chunk(6, dim=1)  # views sharing one batch stride
+    return shift, scale1p, gate, c_shift, c_scale1p, c_gate
+
+
+def _stream_tail(block: nn.Module, sfx: str, x: torch.Tensor, ctx: torch.Tensor, c_shift, c_scale1p, c_gate, eps: float, num_mot_ref: int):
+    """cross-attention + FFN of one stream (:668-697); sfx = "" (target) or "_mot_ref"."""
+    norm2 = getattr(block, "norm2" + sfx)
+    attn2 = getattr(block, "attn2" + sfx)
+    ffn = getattr(block, "ffn" + sfx)
+    if isinstance(norm2, nn.Identity):
+        xc = x
+    else:
+        xc = ops.adaln_layernorm(x, eps=norm2.eps, rounding=ops.ROUND_WAN, ln_w=_f32(norm2, "w", norm2.weight), ln_b=_f32(norm2, "b", norm2.bias))
+    a = _cross_attn(attn2, xc, ctx, num_mot_ref)
+    x = _linear(attn2.to_out[0], a, epilogue=ops.EPI_RES_ADD, residual=x)
+    xf = ops.adaln_layernorm(x, eps=eps, rounding=ops.ROUND_WAN, scale1p=c_scale1p, shift=c_shift)
+    h = _linear(ffn.net[0].proj, xf, epilogue=ops.EPI_BIAS_GELU)
+    return _linear(ffn.net[2], h, epilogue=ops.EPI_GATE_RES_F32, residual=x, gate=c_gate)
+
+
+def wan_block_forward(self: nn.Module, hidden_states: torch.Tensor, encoder_hidden_states: torch.Tensor, temb: torch.Tensor,
+                      rotary_emb: Union[torch.Tensor, Tables], hidden_states_mot_ref: Optional[torch.Tensor] = None,
+                      encoder_hidden_states_mot_ref: Optional[torch.Tensor] = None, temb_mot_ref: Optional[torch.Tensor] = None,
+                      rotary_emb_mot_ref: Union[torch.Tensor, Tables, None] = None, num_mot_ref: Optional[int] = None):
+    """Drop-in for WanTransformerBlock.forward (:566-699), same signature and return value, running on the sm_100a kernels.
+    `self` is a WanTransformerBlock — the reference's or ours (duck-typed on the submodule names)."""
+    x = hidden_states
+    attn1 = self.attn1
+    heads = attn1.heads
+    eps = self.norm1.eps
+    hd = attn1.to_q.weight.shape[0] // heads
+    shift, scale1p, gate, c_shift, c_scale1p, c_gate = _modulation(self.scale_shift_table, temb)
+    tables = as_tables(rotary_emb, hd, x.device)
+
+    if not self.with_mot_ref:  # :580-601
+        xn = ops.adaln_layernorm(x, eps=eps, rounding=ops.ROUND_WAN, scale1p=scale1p, shift=shift)
+        q, k, v = _split_qkv(_self_attn_qkv(attn1, xn, tables), heads)
+        o = _token_major(ops.attention(q, k, v))
+        x = _linear(attn1.to_out[0], o, epilogue=ops.EPI_GATE_RES_F32, residual=x, gate=gate)
+        x = _stream_tail(self, "", x, encoder_hidden_states, c_shift, c_scale1p, c_gate, eps, 1)
+        return x, hidden_states_mot_ref
+
+    if num_mot_ref != 1:
+        raise AssertionError("num_mot_ref must be 1 (transformer_wan_mot.py:611)")
+    xr = hidden_states_mot_ref
+    attn1_r = self.attn1_mot_ref
+    shift_r, scale1p_r, gate_r, c_shift_r, c_scale1p_r, c_gate_r = _modulation(self.scale_shift_table_mot_ref, temb_mot_ref)
+    tables_r = as_tables(rotary_emb_mot_ref, hd, x.device)
+    B, S, d = x.shape
+    Sr = xr.shape[1]
+    inner = attn1.to_q.weight.shape[0]
+
+    # 1. joint self-attention (:620-663)
+    xn = ops.adaln_layernorm(x, eps=eps, rounding=ops.ROUND_WAN, scale1p=scale1p, shift=shift)
+    xn_r = ops.adaln_layernorm(xr, eps=self.norm1_mot_ref.eps, rounding=ops.ROUND_WAN, scale1p=scale1p_r, shift=shift_r)
+    qkv = torch.empty((B, S + Sr, 3 * inner), dtype=torch.bfloat16, device=x.device)
+    _self_attn_qkv(attn1, xn, tables, out=qkv[:, :S])
+    _self_attn_qkv(attn1_r, xn_r, tables_r, out=qkv[:, S:])
+    q, k, v = _split_qkv(qkv, heads)
+    o = _token_major(ops.attention(q, k, v))  # [B, J, inner], rows [target | ref]
+    x = _linear(attn1.to_out[0], o[:, :S], epilogue=ops.EPI_GATE_RES_F32, residual=x, gate=gate)
+    xr = _linear(attn1_r.to_out[0], o[:, S:], epilogue=ops.EPI_GATE_RES_F32, residual=xr, gate=gate_r)
+
+    # 2./3. per-stream cross-attention and FFN (:668-697)
+    x = _stream_tail(self, "", x, encoder_hidden_states, c_shift, c_scale1p, c_gate, eps, 1)
+    xr = _stream_tail(self, "_mot_ref", xr, encoder_hidden_states_mot_ref, c_shift_r, c_scale1p_r, c_gate_r, self.norm3_mot_ref.eps, num_mot_ref)
+    return x, xr
+
+
+# ----------------------------------------------------------------------------------------------
+# drop-in attention processors  (boundary B1)
+# ----------------------------------------------------------------------------------------------
+class WanAttnMOTProcessor2_0:
+    """Same two-phase protocol and kwarg names as the reference's WanAttnMOTProcessor2_0 (:198-244)."""
+
+    def __call__(self, attn, hidden_states: torch.Tensor, encoder_hidden_states: Optional[torch.Tensor] = None,
+                 attention_mask: Optional[torch.Tensor] = None, rotary_emb: Optional[torch.Tensor] = None, is_before_attn=True,
+                 query: Optional[torch.Tensor] = None, key: Optional[torch.Tensor] = None, value: Optional[torch.Tensor] = None):
+        if is_before_attn:
+            hd = attn.to_q.weight.shape[0] // attn.heads
+            qkv = _self_attn_qkv(attn, hidden_states, as_tables(rotary_emb, hd, hidden_states.device))
+            q, k, v = _split_qkv(qkv, attn.heads)
+            return q, k, v, attention_mask
+        return _linear(attn.to_out[0], _token_major(hidden_states))
+
+
+class WanAttnProcessor2_0:
+    """Plain (non-MoT) Wan processor (:39-107): self-attention, or text+image cross-attention when add_k_proj exists."""
+
+    def __call__(self, attn, hidden_states: torch.Tensor, encoder_hidden_states: Optional[torch.Tensor] = None,
+                 attention_mask: Optional[torch.Tensor] = None, rotary_emb: Optional[torch.Tensor] = None):
+        if attention_mask is not None:
+            raise ValueError("attention masks are not supported on the VAP path (the reference never passes one)")
+        if encoder_hidden_states is None:
+            hd = attn.to_q.weight.shape[0] // attn.heads
+            q, k, v = _split_qkv(_self_attn_qkv(attn, hidden_states, as_tables(rotary_emb, hd, hidden_states.device)), attn.heads)
+            return _linear(attn.to_out[0], _token_major(ops.attention(q, k, v)))
+        return _linear(attn.to_out[0], _cross_attn(attn, hidden_states, encoder_hidden_states, 1))
+
+
+class WanAttnCrossMOTProcessor2_0:
+    """Same kwargs as the reference's WanAttnCrossMOTProcessor2_0 (:115-190)."""
+
+    def __call__(self, attn, hidden_states: torch.Tensor, encoder_hidden_states: Optional[torch.Tensor] = None,
+                 attention_mask: Optional[torch.Tensor] = None, rotary_emb: Optional[torch.Tensor] = None, num_mot_ref=1):
+        if attention_mask is not None or rotary_emb is not None:
+            raise ValueError("attention_mask / rotary_emb are not used by the VAP cross-attention (never passed by the reference block)")
+        return _linear(attn.to_out[0], _cross_attn(attn, hidden_states, encoder_hidden_states, num_mot_ref))
+
+
+# ----------------------------------------------------------------------------------------------
+# stand-alone shell with the reference's module tree
+# ----------------------------------------------------------------------------------------------
+class WanTransformerBlock(nn.Module):
+    """Same submodule / parameter names as the reference block (:467-564); forward = the fused path."""
+
+    def __init__(self, dim: int, ffn_dim: int, num_heads: int, qk_norm: str = "rms_norm_across_heads", cross_attn_norm: bool = False,
+                 eps: float = 1e-6, added_kv_proj_dim: Optional[int] = None, with_mot_ref: bool = False, _block_idx: int = 0,
+                 dim_mot_ref: Optional[int] = None):
+        super().__init__()
+        if dim_mot_ref is not None and dim_mot_ref != dim:
+            raise NotImplementedError("dim_mot_ref != dim is not supported (joint attention needs equal head_dim; unused by the released configs)")
+        self.with_mot_ref = with_mot_ref
+        self._block_idx = _block_idx
+        self.dim_mot_ref = dim_mot_ref
+
+        def make(sfx: str):
+            setattr(self, "norm1" + sfx, FP32LayerNorm(dim, eps, elementwise_affine=False))
+            setattr(self, "attn1" + sfx, Attention(dim, num_heads, dim // num_heads, qk_norm, eps=eps, bias=True, out_bias=True,
+                                                    processor=WanAttnMOTProcessor2_0() if with_mot_ref else WanAttnProcessor2_0()))
+            setattr(self, "attn2" + sfx, Attention(dim, num_heads, dim // num_heads, qk_norm, eps=eps, bias=True, out_bias=True,
+                                                    added_kv_proj_dim=added_kv_proj_dim, added_proj_bias=True,
+                                                    processor=WanAttnCrossMOTProcessor2_0() if with_mot_ref else WanAttnProcessor2_0()))
+            setattr(self, "norm2" + sfx, FP32LayerNorm(dim, eps, elementwise_affine=True) if cross_attn_norm else nn.Identity())
+            setattr(self, "ffn" + sfx, FeedForward(dim, inner_dim=ffn_dim, activation_fn="gelu-approximate"))
+            setattr(self, "norm3" + sfx, FP32LayerNorm(dim, eps, elementwise_affine=False))
+            setattr(self, "scale_shift_table" + sfx, nn.Parameter(torch.randn(1, 6, dim) / dim ** 0.5))
+
+        make("")
+        if with_mot_ref:
+            make("_mot_ref")
+
+    forward = wan_block_forward
+
+
+class WanImageEmbedding(nn.Module):
+    """:247-268 (pos_embed_seq_len None); transformer-shell glue (torch)."""
+
+    def __init__(self, in_features: int, out_features: int):
+        super().__init__()
+        self.norm1 = FP32LayerNorm(in_features)
+        self.ff = FeedForward(in_features, out_features, mult=1, activation_fn="gelu")
+        self.norm2 = FP32LayerNorm(out_features)
+
+    @staticmethod
+    def _ln(norm: nn.LayerNorm, x: torch.Tensor) -> torch.Tensor:
+        return F.layer_norm(x.float(), norm.normalized_shape, norm.weight.float(), norm.bias.float(), norm.eps).to(x.dtype)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        x = self._ln(self.norm1, x)
+        x = self.ff.net[2](F.gelu(self.ff.net[0].proj(x)))
+        return self._ln(self.norm2, x)
+
+
+class WanTimeTextImageEmbedding(nn.Module):
+    """:271-365 — condition embedder of either stream (the reference's *Ref variant loops over a list of timesteps)."""
+
+    def __init__(self, dim: int, time_freq_dim: int, time_proj_dim: int, text_embed_dim: int, image_embed_dim: Optional[int]):
+        super().__init__()
+        self.time_freq_dim = time_freq_dim
+        self.time_embedder = TimestepEmbedding(time_freq_dim, dim)
+        self.act_fn = nn.SiLU()
+        self.time_proj = nn.Linear(dim, time_proj_dim)
+        self.text_embedder = PixArtAlphaTextProjection(text_embed_dim, dim)
+        self.image_embedder = WanImageEmbedding(image_embed_dim, dim) if image_embed_dim is not None else None
+
+    def _sinusoid(self, t: torch.Tensor) -> torch.Tensor:  # Timesteps(flip_sin_to_cos=True, downscale_freq_shift=0), embeddings.py:25-77
+        half = self.time_freq_dim // 2
+        exponent = -math.log(10000) * torch.arange(0, half, dtype=torch.float32, device=t.device) / half
+        emb = t[:, None].float() * torch.exp(exponent)[None, :]
+        return torch.cat([torch.cos(emb), torch.sin(emb)], dim=-1)
+
+    def forward(self, timesteps: List[torch.Tensor], text: torch.Tensor, image: Optional[torch.Tensor]):
+        w_dtype = self.time_embedder.linear_1.weight.dtype
+        tembs, projs = [], []
+        for ts in timesteps:
+            e = self.time_embedder(self._sinusoid(ts).to(w_dtype)).type_as(text)
+            tembs.append(e)
+            projs.append(self.time_proj(self.act_fn(e)))
+        text = self.text_embedder(text)
+        if image is not None:
+            image = self.image_embedder(image)
+        return torch.cat(tembs, 0), torch.cat(projs, 0), text, image
+
+
+class WanTransformer3DMOTModel(nn.Module):
+    """Stand-alone mirror of the reference model (:702-1000): same constructor kwargs, module names and forward
+    signature/outputs (returns ``(sample,)`` or an object with ``.sample``).  Patch-embed / condition embedders /
+    output head are transformer-shell glue kept in torch; every block runs the fused path."""
+
+    def __init__(self, patch_size: Tuple[int, int, int] = (1, 2, 2), num_attention_heads: int = 40, attention_head_dim: int = 128,
+                 in_channels: int = 16, out_channels: int = 16, text_dim: int = 4096, freq_dim: int = 256, ffn_dim: int = 13824,
+                 num_layers: int = 40, cross_attn_norm: bool = True, qk_norm: Optional[str] = "rms_norm_across_heads", eps: float = 1e-6,
+                 image_dim: Optional[int] = None, added_kv_proj_dim: Optional[int] = None, rope_max_seq_len: int = 1024,
+                 pos_embed_seq_len: Optional[int] = None, block_idx_with_mot_ref: List[int] = (0, 10, 20),
+                 attention_head_dim_mot_ref: Optional[int] = None, supported_effect_types=None, num_ref_embeddings=None,
+                 reference_train_mode: Optional[str] = None):
+        super().__init__()
+        if pos_embed_seq_len is not None or attention_head_dim_mot_ref is not None or reference_train_mode is not None:
+            raise NotImplementedError("pos_embed_seq_len / attention_head_dim_mot_ref / reference_train_mode are outside the VAP inference path")
+        self.config = dict(patch_size=tuple(patch_size), num_attention_heads=num_attention_heads, attention_head_dim=attention_head_dim,
+                           in_channels=in_channels, out_channels=out_channels, text_dim=text_dim, freq_dim=freq_dim, ffn_dim=ffn_dim,
+                           num_layers=num_layers, cross_attn_norm=cross_attn_norm, qk_norm=qk_norm, eps=eps, image_dim=image_dim,
+                           added_kv_proj_dim=added_kv_proj_dim, rope_max_seq_len=rope_max_seq_len,
+                           block_idx_with_mot_ref=list(block_idx_with_mot_ref))
+        inner = num_attention_heads * attention_head_dim
+        self.patch_embedding = nn.Conv3d(in_channels, inner, kernel_size=tuple(patch_size), stride=tuple(patch_size))
+        self.patch_embedding_mot_ref = nn.Conv3d(in_channels, inner, kernel_size=tuple(patch_size), stride=tuple(patch_size))
+        self.condition_embedder = WanTimeTextImageEmbedding(inner, freq_dim, inner * 6, text_dim, image_dim)
+        self.condition_embedder_mot_ref = WanTimeTextImageEmbedding(inner, freq_dim, inner * 6, text_dim, image_dim)
+        self.blocks = nn.ModuleList([
+            WanTransformerBlock(inner, ffn_dim, num_attention_heads, qk_norm, cross_attn_norm, eps, added_kv_proj_dim,
+                                with_mot_ref=i in block_idx_with_mot_ref, _block_idx=i) for i in range(num_layers)])
+        self.norm_out = FP32LayerNorm(inner, eps, elementwise_affine=False)
+        self.proj_out = nn.Linear(inner, out_channels * math.prod(patch_size))
+        self.scale_shift_table = nn.Parameter(torch.randn(1, 2, inner) / inner ** 0.5)
+
+    def forward(self, hidden_states: torch.Tensor, timestep: torch.Tensor, encoder_hidden_states: torch.Tensor,
+                encoder_hidden_states_image: Optional[torch.Tensor] = None, return_dict: bool = True,
+                attention_kwargs: Optional[Dict[str, Any]] = None, num_mot_ref: int = 1, hidden_states_mot_ref: Optional[torch.Tensor] = None,
+                timestep_list_mot_ref=None, encoder_hidden_states_mot_ref: Optional[torch.Tensor] = None,
+                encoder_hidden_states_image_mot_ref: Optional[torch.Tensor] = None, effect_types=None, reference_train_mode=None):
+        cfg = self.config
+        B, C, Fr, Hh, Ww = hidden_states.shape
+        p_t, p_h, p_w = cfg["patch_size"]
+        D = cfg["attention_head_dim"]
+        dev = hidden_states.device
+        rope = wan_rope_tables(D, cfg["patch_size"], hidden_states.shape[2:], ref=False, device=dev, max_seq_len=cfg["rope_max_seq_len"])
+        rope_r = wan_rope_tables(D, cfg["patch_size"], hidden_states_mot_ref.shape[2:], ref=True, device=dev, max_seq_len=cfg["rope_max_seq_len"])
+
+        x = self.patch_embedding(hidden_states).flatten(2).transpose(1, 2).contiguous()
+        xr = self.patch_embedding_mot_ref(hidden_states_mot_ref).flatten(2).transpose(1, 2).contiguous()
+        temb, proj, ctx, ctx_img = self.condition_embedder([timestep], encoder_hidden_states, encoder_hidden_states_image)
+        proj = proj.unflatten(1, (6, -1))
+        temb_r, proj_r, ctx_r, ctx_img_r = self.condition_embedder_mot_ref(list(timestep_list_mot_ref), encoder_hidden_states_mot_ref,
+                                                                          encoder_hidden_states_image_mot_ref)
+        proj_r = proj_r.unflatten(1, (6, -1))
+        if ctx_img is not None:
+            ctx = torch.cat([ctx_img, ctx], dim=1)
+            ctx_r = torch.cat([ctx_img_r, ctx_r], dim=1)
+
+        for block in self.blocks:
+            x, xr = block(hidden_states=x, encoder_hidden_states=ctx, temb=proj, rotary_emb=rope, hidden_states_mot_ref=xr,
+                          encoder_hidden_states_mot_ref=ctx_r, temb_mot_ref=proj_r, rotary_emb_mot_ref=rope_r, num_mot_ref=num_mot_ref)
+
+        shift, scale = (self.scale_shift_table + temb.unsqueeze(1)).chunk(2, dim=1)  # :952 (model dtype)
+        x = ops.adaln_layernorm(x, eps=cfg["eps"], rounding=ops.ROUND_WAN, scale1p=(1 + scale).float(), shift=shift.float())
+        x = self.proj_out(x)
+        x = x.reshape(B, Fr // p_t, Hh // p_h, Ww // p_w, p_t, p_h, p_w, -1).permute(0, 7, 1, 4, 2, 5, 3, 6)
+        out = x.flatten(6, 7).flatten(4, 5).flatten(2, 3)
+        if not return_dict:
+            return (out,)
+        return _Output(sample=out)
+
+
+class _Output:
+    """Tiny stand-in for diffusers' Transformer2DModelOutput (attribute + index access)."""
+
+    def __init__(self, sample):
+        self.sample = sample
+
+    def __getitem__(self, i):
+        return (self.sample,)[i]
