@@ -1,0 +1,466 @@
+"""GPU parity checks shared by the pytest `-m gpu` suite and tools/gpu_diag.py.
+
+Every check runs the CUDA path through the C ABI (ops.* -> libvap_b200.so) and compares it with the oracle
+(oracle/*, evaluated on CPU) on the same seeded inputs, or — at sizes where the CPU oracle would take minutes — with a
+size-independent property / torch's own GPU library kernel.  Each returns a dict of measured errors and raises
+AssertionError when a tolerance is exceeded.  Tolerances: north_star says per-block max-abs <= 2e-2 relative for bf16
+activations; single kernels are held to tighter bounds noted inline.
+"""
+from __future__ import annotations
+
+import importlib
+import json
+import math
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import cog_oracle, common as ocommon, denoise as odenoise, wan_oracle  # noqa: E402
+
+vap = importlib.import_module("video-as-prompt_b200")
+ops, synth = vap.ops, vap.synth
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+DEV = "cuda"
+
+
+def rel_err(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+
+
+def cosine(a, b):
+    a, b = a.detach().double().cpu().flatten(), b.detach().double().cpu().flatten()
+    return (torch.dot(a, b) / (a.norm() * b.norm())).item()
+
+
+def _randn(shape, seed, scale=1.0, dtype=torch.bfloat16):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dtype)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# tcgen05 descriptor probes
+# ---------------------------------------------------------------------------------------------------------------
+def check_probe(a_in_tmem: bool, b_mn_major: bool, N: int = 128, K: int = 128, **desc):
+    a = _randn((128, K), 1)
+    b = _randn((K, N) if b_mn_major else (N, K), 2)
+    d = ops.probe_umma(a.to(DEV), b.to(DEV), a_in_tmem=a_in_tmem, b_mn_major=b_mn_major, **desc)
+    torch.cuda.synchronize()
+    ref = a.float() @ (b.float() if b_mn_major else b.float().t())
+    err = rel_err(d, ref)
+    assert err < 1e-3, f"probe a_in_tmem={a_in_tmem} b_mn_major={b_mn_major} N={N} K={K}: rel err {err}"
+    return dict(err=err)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# LayerNorm / q-k norm + RoPE
+# ---------------------------------------------------------------------------------------------------------------
+def check_layernorm_wan(rows=333, d=5120, batch=1, affine=False, modulate=True):
+    x = _randn((batch, rows, d), 3, 2.0)
+    scale = _randn((batch, 1, d), 4, 0.3, torch.float32)
+    shift = _randn((batch, 1, d), 5, 0.3, torch.float32)
+    w = (1 + _randn((d,), 6, 0.1, torch.float32)).to(torch.bfloat16)
+    b = _randn((d,), 7, 0.1)
+    # oracle: transformer_wan_mot.py:620-623 / :668-669
+    y = ocommon.fp32_layer_norm(x.float(), w if affine else None, b if affine else None, 1e-6)
+    if modulate:
+        y = y * (1 + scale) + shift
+    ref = y.type_as(x)
+    out = ops.adaln_layernorm(x.to(DEV), eps=1e-6, rounding=ops.ROUND_WAN, ln_w=w.float().to(DEV) if affine else None,
+                              ln_b=b.float().to(DEV) if affine else None, scale1p=(1 + scale).to(DEV) if modulate else None,
+                              shift=shift.to(DEV) if modulate else None)
+    err = rel_err(out, ref)
+    mism = (out.cpu() != ref).float().mean().item()
+    assert err < 8e-3, f"layernorm wan: rel err {err}"
+    return dict(err=err, mismatch_frac=mism)
+
+
+def check_layernorm_cog(rows=226, d=3072, nmod=2):
+    x = _randn((nmod, rows, d), 8, 1.5)
+    w = (1 + _randn((d,), 9, 0.1, torch.float32)).to(torch.bfloat16)
+    b = _randn((d,), 10, 0.1)
+    scale = _randn((nmod, d), 11, 0.3)
+    shift = _randn((nmod, d), 12, 0.3)
+    ref = F.layer_norm(x, (d,), w, b, 1e-5) * (1 + scale)[:, None, :] + shift[:, None, :]  # normalization.py:468
+    out = ops.adaln_layernorm(x.reshape(nmod * rows, d).to(DEV), eps=1e-5, rounding=ops.ROUND_COG, ln_w=w.float().to(DEV), ln_b=b.float().to(DEV),
+                              scale1p=(1 + scale).float().to(DEV), shift=shift.float().to(DEV), rows_per_batch=rows)
+    err = rel_err(out.view(nmod, rows, d), ref)
+    mism = (out.view(nmod, rows, d).cpu() != ref).float().mean().item()
+    assert err < 8e-3, f"layernorm cog: rel err {err}"
+    return dict(err=err, mismatch_frac=mism)
+
+
+def check_qk_wan(S=300, H=40, D=128):
+    d = H * D
+    qkv = _randn((1, S, 3 * d), 13, 1.0)
+    wq = (1 + _randn((d,), 14, 0.1, torch.float32)).to(torch.bfloat16)
+    wk = (1 + _randn((d,), 15, 0.1, torch.float32)).to(torch.bfloat16)
+    frames, gh, gw = 3, 10, 10
+    freqs = wan_oracle.wan_rope(D, (1, 2, 2), 1024, (frames, 2 * gh, 2 * gw), ref=True)  # [1,1,300,64] complex128, negative t
+    assert freqs.shape[2] == S
+    q, k = qkv[..., :d], qkv[..., d:2 * d]
+    ref_q = wan_oracle.apply_rope_complex(ocommon.rms_norm_across(q, wq, 1e-6).unflatten(2, (H, -1)).transpose(1, 2), freqs)
+    ref_k = wan_oracle.apply_rope_complex(ocommon.rms_norm_across(k, wk, 1e-6).unflatten(2, (H, -1)).transpose(1, 2), freqs)
+    g = qkv.to(DEV)
+    cos, sin = vap.rope.as_tables(freqs, D, DEV)
+    ops.qk_norm_rope_(g[0, :, :d], g[0, :, d:2 * d], heads=H, head_dim=D, wq=wq.float().to(DEV), wk=wk.float().to(DEV), cos=cos, sin=sin,
+                      rows_per_batch=S, eps=1e-6, mode=ops.QK_WAN)
+    out_q = g[..., :d].unflatten(2, (H, -1)).transpose(1, 2)
+    out_k = g[..., d:2 * d].unflatten(2, (H, -1)).transpose(1, 2)
+    eq, ek = rel_err(out_q, ref_q), rel_err(out_k, ref_k)
+    assert torch.equal(g[..., 2 * d:].cpu(), qkv[..., 2 * d:]), "v must be untouched"
+    assert max(eq, ek) < 8e-3, f"qk wan: rel err q {eq} k {ek}"
+    # device-built tables == converted reference tables
+    t2 = vap.rope.wan_rope_tables(D, (1, 2, 2), (frames, 2 * gh, 2 * gw), ref=True, device=DEV)
+    assert torch.allclose(t2[0], cos, atol=1e-6) and torch.allclose(t2[1], sin, atol=1e-6)
+    return dict(err_q=eq, err_k=ek)
+
+
+def check_qk_cog(T=226, S=150, H=48, D=64):
+    d = H * D
+    L = T + S
+    qkv = _randn((1, L, 3 * d), 16, 1.0)
+    nw = lambda s: ((1 + _randn((D,), s, 0.1, torch.float32)).to(torch.bfloat16), _randn((D,), s + 100, 0.1))  # noqa: E731
+    (wq, bq), (wk, bk) = nw(17), nw(18)
+    rope = cog_oracle.cog_rope_3d(D, ((0, 0), (5, 10)), (5, 10), 3, mot_num=1)  # [150, 64] negative temporal positions
+    heads = lambda t: t.view(1, L, H, D).transpose(1, 2)  # noqa: E731
+    q = F.layer_norm(heads(qkv[..., :d]), (D,), wq, bq, 1e-6)
+    k = F.layer_norm(heads(qkv[..., d:2 * d]), (D,), wk, bk, 1e-6)
+    q[:, :, T:] = cog_oracle.apply_rope_real(q[:, :, T:], *rope)
+    k[:, :, T:] = cog_oracle.apply_rope_real(k[:, :, T:], *rope)
+    g = qkv.to(DEV)
+    cos, sin = vap.rope.as_tables(tuple(t.to(DEV) for t in rope), D, DEV)
+    ops.qk_norm_rope_(g[0, :, :d], g[0, :, d:2 * d], heads=H, head_dim=D, wq=wq.float().to(DEV), bq=bq.float().to(DEV), wk=wk.float().to(DEV),
+                      bk=bk.float().to(DEV), cos=cos, sin=sin, rows_per_batch=L, rope_row0=T, eps=1e-6, mode=ops.QK_COG)
+    eq, ek = rel_err(heads(g[..., :d]), q), rel_err(heads(g[..., d:2 * d]), k)
+    assert max(eq, ek) < 8e-3, f"qk cog: rel err q {eq} k {ek}"
+    return dict(err_q=eq, err_k=ek)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GEMM (+ epilogues)
+# ---------------------------------------------------------------------------------------------------------------
+def _gemm_ref(x, w, bias, epilogue, res=None, gate=None, rows_per_batch=None):
+    """Oracle arithmetic of the Linear call sites with the reference's rounding points (fp32 accumulate on CPU)."""
+    y = (x.float() @ w.float().t() + (bias.float() if bias is not None else 0)).to(torch.bfloat16)  # nn.Linear output is bf16
+    if epilogue == ops.EPI_BIAS:
+        return y
+    if epilogue == ops.EPI_BIAS_GELU:
+        return F.gelu(y, approximate="tanh")
+    M = x.shape[0]
+    g = None
+    if gate is not None:
+        g = gate.repeat_interleave(rows_per_batch, dim=0)[:M] if gate.dim() == 2 and gate.shape[0] > 1 else gate.reshape(1, -1)
+    if epilogue == ops.EPI_GATE_RES_F32:
+        return (res.float() + y * g).to(torch.bfloat16)  # transformer_wan_mot.py:658
+    if epilogue == ops.EPI_RES_ADD:
+        return res + y  # :675
+    if epilogue == ops.EPI_GATE_RES_BF16:
+        return res + g.to(torch.bfloat16) * y  # cogvideox_transformer_3d_mot.py:445
+    raise ValueError(epilogue)
+
+
+def check_gemm(M=300, N=512, K=256, epilogue=0, bias=True, nbatch=1, seed=20, tol=6e-3):
+    x = _randn((M, K), seed, 1.0)
+    w = _randn((N, K), seed + 1, 1.0 / math.sqrt(K))
+    b = _randn((N,), seed + 2, 0.1) if bias else None
+    res = _randn((M, N), seed + 3, 1.0)
+    rpb = (M + nbatch - 1) // nbatch
+    gate = _randn((nbatch, N), seed + 4, 0.5, torch.float32)
+    if epilogue == ops.EPI_GATE_RES_BF16:
+        gate = gate.to(torch.bfloat16).float()
+    needs_res = epilogue >= ops.EPI_GATE_RES_F32
+    needs_gate = epilogue in (ops.EPI_GATE_RES_F32, ops.EPI_GATE_RES_BF16)
+    ref = _gemm_ref(x, w, b, epilogue, res, gate, rpb)
+    out = ops.linear(x.to(DEV), w.to(DEV), b.to(DEV) if bias else None, epilogue=epilogue, residual=res.to(DEV) if needs_res else None,
+                     gate=gate.to(DEV) if needs_gate else None, rows_per_batch=rpb)
+    torch.cuda.synchronize()
+    err = rel_err(out, ref)
+    assert err < tol, f"gemm M={M} N={N} K={K} epi={epilogue}: rel err {err}"
+    return dict(err=err, mismatch_frac=(out.cpu() != ref).float().mean().item())
+
+
+def check_gemm_large(M=20280, N=15360, K=5120):
+    """Full Wan-14B fused-QKV size (BASELINE config #3): compare against torch's own bf16 GEMM on the GPU (library
+    cross-check; the CPU oracle would need minutes) + linearity property f(2x) == 2 f(x) exactly (power-of-two scaling)."""
+    g = torch.Generator(device=DEV).manual_seed(0)
+    x = torch.randn((M, K), generator=g, device=DEV, dtype=torch.float32).to(torch.bfloat16)
+    w = (torch.randn((N, K), generator=g, device=DEV, dtype=torch.float32) / math.sqrt(K)).to(torch.bfloat16)
+    b = (torch.randn((N,), generator=g, device=DEV, dtype=torch.float32) * 0.1).to(torch.bfloat16)
+    out = ops.linear(x, w, b)
+    ref = F.linear(x, w, b)
+    err = rel_err(out[::97], ref[::97])
+    out2 = ops.linear(x * 2, w, None)
+    out1 = ops.linear(x, w, None)
+    lin = torch.equal(out2, out1 * 2)
+    assert err < 6e-3 and lin, f"gemm large: rel err vs cuBLAS {err}, linearity {lin}"
+    return dict(err_vs_cublas=err, linear=lin)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# attention
+# ---------------------------------------------------------------------------------------------------------------
+def check_attention(B=1, H=2, Lq=300, Lkv=300, D=128, joint_layout=True, seed=30, tol=1e-2):
+    """vs the definition-level fp32 oracle.  joint_layout=True reads q/k/v as column slices of a [B, L, 3*H*D] buffer,
+    exactly how the block forward feeds the kernel."""
+    if joint_layout and Lq == Lkv:
+        buf = _randn((B, Lq, 3 * H * D), seed, 1.0)
+        views = lambda t: [t[..., i * H * D:(i + 1) * H * D].unflatten(2, (H, D)).transpose(1, 2) for i in range(3)]  # noqa: E731
+        q, k, v = views(buf)
+        gq, gk, gv = views(buf.to(DEV))
+    else:
+        q, k, v = _randn((B, H, Lq, D), seed), _randn((B, H, Lkv, D), seed + 1), _randn((B, H, Lkv, D), seed + 2)
+        gq, gk, gv = q.to(DEV), k.to(DEV), v.to(DEV)
+    ref = ocommon.sdpa_explicit_fp32(q, k, v)
+    out, lse = ops.attention(gq, gk, gv, return_lse=True)
+    torch.cuda.synchronize()
+    err = rel_err(out, ref)
+    s = torch.matmul(q.float(), k.float().transpose(-1, -2)) * D ** -0.5
+    lse_err = (lse.cpu() - torch.logsumexp(s, dim=-1)).abs().max().item()
+    assert out.shape == (B, H, Lq, D) and out.transpose(1, 2).is_contiguous()
+    assert err < tol and lse_err < 2e-2, f"attention B={B} H={H} Lq={Lq} Lkv={Lkv} D={D}: rel err {err}, lse err {lse_err}"
+    return dict(err=err, lse_err=lse_err)
+
+
+def check_attention_peaky(D=128):
+    """Scores with a large dynamic range (exercises the lazy O-rescale path: the running max keeps growing by > 2^8)."""
+    H, L = 2, 1024
+    q = _randn((1, H, L, D), 40, 3.0)
+    k = _randn((1, H, L, D), 41, 3.0)
+    k[:, :, 1::128] *= 4  # a few dominant keys appearing late in every tile sequence
+    v = _randn((1, H, L, D), 42)
+    ref = ocommon.sdpa_explicit_fp32(q, k, v)
+    out = ops.attention(q.to(DEV), k.to(DEV), v.to(DEV))
+    err = rel_err(out, ref)
+    assert err < 1.5e-2, f"attention peaky: rel err {err}"
+    return dict(err=err)
+
+
+def check_attention_full_size(J=40560, H=40, D=128, heads_checked=2):
+    """BASELINE config #3 joint attention size.  Size-independent properties + library cross-check on the GPU:
+    (1) V = 1  =>  O = 1 exactly-ish (softmax rows sum to one);  (2) permuting the K/V rows leaves O unchanged (the joint
+    order [target|ref] is irrelevant for unmasked attention, SURVEY §8 note 1);  (3) first heads vs torch SDPA."""
+    g = torch.Generator(device=DEV).manual_seed(1)
+    qkv = torch.randn((1, J, 3 * H * D), generator=g, device=DEV, dtype=torch.float32).to(torch.bfloat16)
+    q, k, v = (qkv[..., i * H * D:(i + 1) * H * D].unflatten(2, (H, D)).transpose(1, 2) for i in range(3))
+    out = ops.attention(q, k, v)
+    ones = torch.ones_like(v[:, :1].contiguous())
+    o1 = ops.attention(q[:, :1], k[:, :1], ones)
+    p1 = (o1.float() - 1).abs().max().item()
+    perm = torch.randperm(J, device=DEV, generator=g)
+    o_perm = ops.attention(q[:, :1], k[:, :1, perm].contiguous(), v[:, :1, perm].contiguous())
+    p2 = rel_err(o_perm, out[:, :1])
+    hs = slice(0, heads_checked)
+    ref = F.scaled_dot_product_attention(q[:, hs].contiguous(), k[:, hs].contiguous(), v[:, hs].contiguous())
+    p3 = rel_err(out[:, hs], ref)
+    assert p1 < 1e-2 and p2 < 1e-2 and p3 < 1.5e-2, f"attention full size: ones {p1}, permutation {p2}, vs torch SDPA {p3}"
+    return dict(ones_err=p1, perm_err=p2, err_vs_torch_sdpa=p3)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# block / model level against the golden fixtures recorded from the reference
+# ---------------------------------------------------------------------------------------------------------------
+def _golden(name):
+    return torch.load(os.path.join(GOLDEN, name), map_location="cpu", weights_only=False)
+
+
+def _to_dev(x):
+    if torch.is_tensor(x):
+        return x.to(DEV)
+    if isinstance(x, (list, tuple)):
+        return type(x)(_to_dev(t) for t in x)
+    return x
+
+
+def build_wan(cfg, seed):
+    m = vap.WanTransformer3DMOTModel(**cfg).to(torch.bfloat16)
+    synth.fill_module_(m, seed=seed, num_layers=cfg["num_layers"])
+    return m.to(DEV).eval()
+
+
+def build_cog(cfg, seed):
+    m = vap.CogVideoXTransformer3DMOTModel(**cfg).to(torch.bfloat16)
+    synth.fill_module_(m, seed=seed, num_layers=cfg["num_layers"])
+    return m.to(DEV).eval()
+
+
+def check_wan_blocks(tol=2e-2):
+    """Teacher-forced: block i of the CUDA path on the reference's recorded inputs of block i vs its recorded outputs."""
+    g = _golden("wan_tiny.pt")
+    cfg = g["cfg"]
+    model = build_wan(cfg, g["weight_seed"])
+    f, h, w = g["latent"]
+    rope = vap.rope.wan_rope_tables(128, cfg["patch_size"], (f, h, w), ref=False, device=DEV)
+    rope_r = vap.rope.wan_rope_tables(128, cfg["patch_size"], (f, h, w), ref=True, device=DEV)
+    sh = {k: v.to(DEV) for k, v in g["shared"].items()}
+    errs = {}
+    with torch.no_grad():
+        for i, blk in g["blocks"].items():
+            x, xr = model.blocks[i](hidden_states=blk["hidden_states"].to(DEV), encoder_hidden_states=sh["encoder_hidden_states"], temb=sh["temb"],
+                                    rotary_emb=rope, hidden_states_mot_ref=blk["hidden_states_mot_ref"].to(DEV),
+                                    encoder_hidden_states_mot_ref=sh["encoder_hidden_states_mot_ref"], temb_mot_ref=sh["temb_mot_ref"],
+                                    rotary_emb_mot_ref=rope_r, num_mot_ref=1)
+            errs[f"block{i}"] = rel_err(x, blk["out"])
+            errs[f"block{i}_ref"] = rel_err(xr, blk["out_ref"])
+    assert max(errs.values()) <= tol, f"wan blocks: {errs}"
+    return errs
+
+
+def check_wan_model(tol=2e-2):
+    g = _golden("wan_tiny.pt")
+    cfg = g["cfg"]
+    model = build_wan(cfg, g["weight_seed"])
+    inp = _to_dev(synth.wan_inputs(cfg, *g["latent"], seed=g["input_seed"]))
+    with torch.no_grad():
+        out = model(**inp, return_dict=False)[0]
+    err, cos = rel_err(out, g["final"]), cosine(out, g["final"])
+    assert err <= tol and cos >= 0.999, f"wan model: rel err {err}, cosine {cos}"
+    return dict(err=err, cosine=cos)
+
+
+def check_wan_denoise():
+    """north_star: final denoised latents cosine >= 0.999 after 4 steps (with CFG, FlowMatchEuler shift 3)."""
+    g = _golden("wan_tiny.pt")
+    cfg, dn = g["cfg"], g["denoise"]
+    model = build_wan(cfg, g["weight_seed"])
+    f, h, w = g["latent"]
+    inp = synth.wan_inputs(cfg, f, h, w, seed=g["input_seed"])
+    neg = synth.wan_inputs(cfg, f, h, w, seed=dn["neg_seed"])
+    gen = torch.Generator().manual_seed(dn["seed"])
+    lat0 = torch.randn((1, 16, f, h, w), generator=gen)
+    lat_ref = torch.randn((1, 16, f, h, w), generator=gen)
+    kw = {k: inp[k] for k in ("encoder_hidden_states", "encoder_hidden_states_image", "encoder_hidden_states_mot_ref",
+                              "encoder_hidden_states_image_mot_ref", "num_mot_ref")}
+    kw_u = dict(kw, encoder_hidden_states=neg["encoder_hidden_states"], encoder_hidden_states_mot_ref=neg["encoder_hidden_states_mot_ref"])
+    with torch.no_grad():
+        lat = vap.denoise.wan_denoise(model, lat0.to(DEV), inp["hidden_states"][:, 16:].float().to(DEV), lat_ref.to(DEV),
+                                      inp["hidden_states_mot_ref"][:, 16:].float().to(DEV), _to_dev(kw), _to_dev(kw_u), dn["steps"], dn["shift"],
+                                      dn["guidance"])
+    cos, err = cosine(lat, dn["final_latents"]), rel_err(lat, dn["final_latents"])
+    assert cos >= 0.999, f"wan 4-step denoise: cosine {cos} (rel err {err})"
+    return dict(cosine=cos, err=err)
+
+
+def check_cog_blocks(case="small", tol=2e-2):
+    g = _golden("cog_tiny.pt")
+    cfg, c = g["cfg"], g["cases"][case]
+    model = build_cog(cfg, g["weight_seed"])
+    inp = synth.cog_inputs(cfg, *c["latent"], seed=c["input_seed"], num_mot_ref=c["num_mot_ref"])
+    rope, rope_r = _to_dev(inp["image_rotary_emb"]), _to_dev(inp["image_rotary_emb_mot_ref"])
+    sh = c["shared"]
+    errs = {}
+    with torch.no_grad():
+        for i, blk in c["blocks"].items():
+            outs = model.transformer_blocks[i](
+                hidden_states=blk["hidden_states"].to(DEV), encoder_hidden_states=blk["encoder_hidden_states"].to(DEV), temb=sh["temb"].to(DEV),
+                image_rotary_emb=rope, hidden_states_mot_ref=blk["hidden_states_mot_ref"].to(DEV),
+                encoder_hidden_states_mot_ref=blk["encoder_hidden_states_mot_ref"].to(DEV),
+                temb_mot_ref=None if sh["temb_mot_ref"] is None else sh["temb_mot_ref"].to(DEV),
+                temb_list_mot_ref=None if sh["temb_list_mot_ref"] is None else [t.to(DEV) for t in sh["temb_list_mot_ref"]],
+                image_rotary_emb_mot_ref=rope_r)
+            for n, o in zip(("out_v", "out_e", "out_v_ref", "out_e_ref"), outs):
+                if blk[n] is not None:
+                    errs[f"block{i}_{n}"] = rel_err(o, blk[n])
+    assert max(errs.values()) <= tol, f"cog blocks[{case}]: {errs}"
+    return errs
+
+
+def check_cog_model(case="config1", tol=2e-2):
+    g = _golden("cog_tiny.pt")
+    cfg, c = g["cfg"], g["cases"][case]
+    model = build_cog(cfg, g["weight_seed"])
+    inp = synth.cog_inputs(cfg, *c["latent"], seed=c["input_seed"], num_mot_ref=c["num_mot_ref"])
+    if c["multi"]:
+        inp["timestep_list_mot_ref"] = [torch.full((1,), t) for t in c["timestep_list"]]
+    with torch.no_grad():
+        out = model(**_to_dev(inp), return_dict=False)[0]
+    err, cos = rel_err(out, c["final"]), cosine(out, c["final"])
+    assert err <= tol and cos >= 0.999, f"cog model[{case}]: rel err {err}, cosine {cos}"
+    return dict(err=err, cosine=cos)
+
+
+def check_processor_level():
+    """Boundary B1/B2: the drop-in processors + joint_sdpa reproduce the fused block (same kernels, reference-shaped calls)."""
+    g = _golden("wan_tiny.pt")
+    cfg = g["cfg"]
+    model = build_wan(cfg, g["weight_seed"])
+    blk = model.blocks[0]
+    f, h, w = g["latent"]
+    rope = vap.rope.wan_rope_tables(128, cfg["patch_size"], (f, h, w), ref=False, device=DEV)
+    x = g["blocks"][0]["hidden_states"].to(DEV)
+    with torch.no_grad():
+        q, k, v, _ = blk.attn1(hidden_states=x, rotary_emb=rope, is_before_attn=True)
+        o = vap.joint_sdpa(q, k, v)
+        y = blk.attn1(hidden_states=o, is_before_attn=False)
+    ref_q, ref_k, ref_v = wan_oracle.self_attn_pre({k_: v_.cpu() for k_, v_ in blk.state_dict().items() if k_.startswith("attn1.")}, "attn1",
+                                                   x.cpu(), cfg["num_attention_heads"], cfg["eps"],
+                                                   wan_oracle.wan_rope(128, cfg["patch_size"], 1024, (f, h, w), ref=False))
+    e = max(rel_err(q, ref_q), rel_err(k, ref_k), rel_err(v, ref_v))
+    assert e < 1e-2 and y.shape == x.shape, f"processor level: qkv rel err {e}"
+    try:
+        vap.joint_sdpa(q, k, v, is_causal=True)
+        raise AssertionError("joint_sdpa must reject is_causal=True")
+    except ValueError:
+        pass
+    return dict(err=e)
+
+
+def check_ulysses_relayout():
+    L, P, chunk = 37, 4, 64
+    src = _randn((L, P * chunk), 50).to(DEV)
+    out = torch.empty((P, L, 3, chunk), dtype=torch.bfloat16, device=DEV)
+    for wi in range(3):
+        ops.ulysses_pack(src, P, out[:, :, wi, :])
+    ref = src.view(L, P, chunk).permute(1, 0, 2)
+    ok = all(torch.equal(out[:, :, wi, :], ref) for wi in range(3))
+    back = ops.ulysses_unpack(out[:, :, 1, :])
+    assert ok and torch.equal(back, src), "ulysses pack/unpack round trip"
+    return dict(ok=True)
+
+
+CHECKS = {
+    "probe_ss": lambda: check_probe(False, False, 128, 128),
+    "probe_ss_n256": lambda: check_probe(False, False, 256, 64),
+    "probe_mn": lambda: check_probe(False, True, 128, 128),
+    "probe_mn_n64": lambda: check_probe(False, True, 64, 128),
+    "probe_ts": lambda: check_probe(True, False, 128, 128),
+    "probe_ts_mn": lambda: check_probe(True, True, 128, 128),
+    "ln_wan": lambda: check_layernorm_wan(),
+    "ln_wan_affine": lambda: check_layernorm_wan(rows=100, d=256, affine=True, modulate=False),
+    "ln_wan_batch": lambda: check_layernorm_wan(rows=64, d=3072, batch=2),
+    "ln_cog": lambda: check_layernorm_cog(),
+    "qk_wan": lambda: check_qk_wan(),
+    "qk_wan_tiny": lambda: check_qk_wan(S=300, H=2, D=128),
+    "qk_cog": lambda: check_qk_cog(),
+    "gemm_small": lambda: check_gemm(300, 512, 256, 0),
+    "gemm_n128": lambda: check_gemm(129, 128, 64, 0),
+    "gemm_tails": lambda: check_gemm(1000, 776, 328, 0),
+    "gemm_gelu": lambda: check_gemm(257, 1024, 512, 1),
+    "gemm_gate_f32": lambda: check_gemm(512, 256, 512, 2, nbatch=2),
+    "gemm_res_add": lambda: check_gemm(300, 256, 256, 3),
+    "gemm_gate_bf16": lambda: check_gemm(452, 256, 256, 4, nbatch=2),
+    "gemm_nobias_k5120": lambda: check_gemm(640, 768, 5120, 0, bias=False),
+    "attn_d128": lambda: check_attention(1, 2, 300, 300, 128),
+    "attn_d128_multi_tile": lambda: check_attention(1, 3, 1000, 1000, 128),
+    "attn_d64": lambda: check_attention(2, 4, 452, 452, 64),
+    "attn_cross": lambda: check_attention(1, 2, 600, 257, 128, joint_layout=False),
+    "attn_cross_512": lambda: check_attention(1, 2, 300, 512, 128, joint_layout=False),
+    "attn_one_tile": lambda: check_attention(1, 1, 64, 100, 128, joint_layout=False),
+    "attn_peaky": lambda: check_attention_peaky(),
+    "ulysses_relayout": check_ulysses_relayout,
+    "wan_blocks": check_wan_blocks,
+    "wan_model": check_wan_model,
+    "wan_denoise": check_wan_denoise,
+    "cog_blocks_small": lambda: check_cog_blocks("small"),
+    "cog_blocks_multi": lambda: check_cog_blocks("multi"),
+    "cog_model_config1": lambda: check_cog_model("config1"),
+    "processor_level": check_processor_level,
+    "gemm_large": check_gemm_large,
+    "attn_full_size": check_attention_full_size,
+}

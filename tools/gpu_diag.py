@@ -1,0 +1,64 @@
+"""Run every GPU parity check of tests/gpu_checks.py in its own subprocess (a kernel fault or an mbarrier-watchdog trap
+kills only that check), with a timeout, and write gpurun_out/diag.json + one log per failing check.
+
+    python tools/gpu_diag.py [--only name1,name2] [--timeout 180]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+OUT = os.path.join(ROOT, "gpurun_out")
+
+
+def run_one(name):
+    import gpu_checks
+    import torch
+    t0 = time.time()
+    res = gpu_checks.CHECKS[name]()
+    torch.cuda.synchronize()
+    print("RESULT " + json.dumps(dict(name=name, ok=True, seconds=round(time.time() - t0, 2), result=res)))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--check")
+    ap.add_argument("--only", default="")
+    ap.add_argument("--timeout", type=int, default=180)
+    a = ap.parse_args()
+    if a.check:
+        return run_one(a.check)
+    os.makedirs(OUT, exist_ok=True)
+    import gpu_checks
+    names = [n for n in gpu_checks.CHECKS if not a.only or n in a.only.split(",")]
+    summary = []
+    for n in names:
+        t0 = time.time()
+        try:
+            p = subprocess.run([sys.executable, os.path.abspath(__file__), "--check", n], capture_output=True, text=True, timeout=a.timeout)
+            out = p.stdout + p.stderr
+            line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]
+            if p.returncode == 0 and line:
+                rec = json.loads(line[-1][7:])
+            else:
+                tail = "\n".join(out.strip().splitlines()[-6:])
+                rec = dict(name=n, ok=False, rc=p.returncode, seconds=round(time.time() - t0, 2), tail=tail)
+                open(os.path.join(OUT, f"diag_{n}.log"), "w").write(out)
+        except subprocess.TimeoutExpired as e:
+            rec = dict(name=n, ok=False, rc="timeout", seconds=a.timeout)
+            open(os.path.join(OUT, f"diag_{n}.log"), "w").write((e.stdout or b"").decode(errors="replace") + (e.stderr or b"").decode(errors="replace"))
+        summary.append(rec)
+        print(json.dumps(rec), flush=True)
+    json.dump(summary, open(os.path.join(OUT, "diag.json"), "w"), indent=1)
+    bad = [r["name"] for r in summary if not r["ok"]]
+    print(f"{len(summary) - len(bad)}/{len(summary)} checks passed; failing: {bad}")
+    sys.exit(1 if bad else 0)
+
+
+if __name__ == "__main__":
+    main()
