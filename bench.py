@@ -1,0 +1,329 @@
+"""bench.py — DiT denoise steps/s of the Wan2.1-14B VAP MoT transformer (49 frames, 480x832) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config wan14b|wan14b_720p|cog5b|wan_tiny]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+One "step" = one transformer forward at B=1 (what both reference pipelines repeat; Wan's CFG doubles it) + the scheduler
+update.  Weights are random-init (synthetic, per-name seeded), latents / text / CLIP tokens synthetic.  N > 1 shards the
+token sequence of both streams with Ulysses sequence parallelism (strong scaling of one step).
+
+Printed JSON line (rank 0): value = device-timed steps/s with inputs resident in HBM; e2e = the same through the public
+`model(...)` call with inputs coming from pinned HOST buffers and the noise prediction read back to the host every step;
+roofline = joint-attention kernel FLOP/s (4*H*J^2*D per launch, CUDA-event timed inside the timed region) against the
+measured dense-bf16 peak; cpu_baseline = the oracle (a CPU port of the reference's arithmetic) on a bounded sample.
+`--impl reference` times only that CPU oracle (the reference is pure PyTorch; its own CPU path == the oracle's ops).
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+METRIC = "DiT denoise steps/s (Wan2.1-14B VAP, 49f 480p)"
+UNIT = "steps/s"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# workloads
+# ---------------------------------------------------------------------------------------------------------------
+def workloads(synth):
+    return {
+        # BASELINE.json configs[2]: the configuration the metric is quoted on (fits one GPU: ~65 GB of bf16 weights)
+        "wan14b": dict(family="wan", cfg=synth.WAN_14B, latent=(13, 60, 104), name="Wan2.1-I2V-14B VAP (40/40 MoT blocks), 49f 480x832"),
+        "wan14b_720p": dict(family="wan", cfg=synth.WAN_14B, latent=(21, 90, 160), name="Wan2.1-I2V-14B VAP (40/40 MoT blocks), 81f 720x1280"),
+        "cog5b": dict(family="cog", cfg=synth.COG_5B, latent=(13, 60, 90), name="CogVideoX-5B-I2V VAP (41/42 MoT blocks), 49f 480x720"),
+        "wan_tiny": dict(family="wan", cfg=dict(synth.WAN_TINY, num_layers=2, block_idx_with_mot_ref=[0, 1]), latent=(3, 16, 24), name="tiny Wan VAP"),
+    }
+
+
+def wan_flops(cfg, S, Sr):
+    """Algorithmic FLOPs of one forward: attention 4*H*J^2*D, GEMMs 2*M*N*K; shell glue excluded."""
+    d = cfg["num_attention_heads"] * cfg["attention_head_dim"]
+    H, D, ffn = cfg["num_attention_heads"], cfg["attention_head_dim"], cfg["ffn_dim"]
+    ctx_t, ctx_i = 512, 257
+    per_stream = lambda L: 2 * L * d * d * 4 + 2 * L * d * d * 2 + 2 * (ctx_t + ctx_i) * d * d * 2 + 4 * H * L * (ctx_t + ctx_i) * D + 2 * 2 * L * d * ffn  # noqa: E731
+    mot = 4 * H * (S + Sr) ** 2 * D + per_stream(S) + per_stream(Sr)
+    plain = 4 * H * S ** 2 * D + per_stream(S)
+    n_mot = len(cfg["block_idx_with_mot_ref"])
+    return n_mot * mot + (cfg["num_layers"] - n_mot) * plain, 4 * H * (S + Sr) ** 2 * D
+
+
+def build_model(vap, w, device):
+    """Construct on the meta device (no 130 GB fp32 host allocation for 14B), materialise in bf16 on the GPU, fill synthetically."""
+    cls = vap.WanTransformer3DMOTModel if w["family"] == "wan" else vap.CogVideoXTransformer3DMOTModel
+    with torch.device("meta"):
+        model = cls(**w["cfg"])
+    model = model.to(torch.bfloat16).to_empty(device=device)
+    vap.synth.fill_module_(model, seed=1234, num_layers=w["cfg"]["num_layers"])
+    return model.eval()
+
+
+def make_inputs(vap, w, device):
+    f, h, wd = w["latent"]
+    if w["family"] == "wan":
+        return vap.synth.wan_inputs(w["cfg"], f, h, wd, seed=0, device=device)
+    return vap.synth.cog_inputs(w["cfg"], f, h, wd, seed=0, device=device)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.samples = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        rows = [s.split(", ") for t, s in self.samples if t0 <= t <= t1] or [s.split(", ") for _, s in self.samples[-3:]]
+        sm, mx, reasons = [], None, set()
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU oracle baseline
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_oracle_sample(vap, w, repeats: int = 1):
+    """Time the oracle (CPU restatement of the reference's arithmetic == the reference's own CPU PyTorch path) on a bounded
+    sample: ONE full-width MoT block of the workload's model at 1 latent frame per stream, all host threads.  Returns
+    (seconds per sample, FLOPs of the sample, description)."""
+    from oracle import wan_oracle
+    synth = vap.synth
+    cfg = dict(w["cfg"], num_layers=1, block_idx_with_mot_ref=[0])
+    torch.set_num_threads(os.cpu_count() or 1)
+    shapes = {k: tuple(v.shape) for k, v in _meta_state_dict(vap, w, cfg).items() if k.startswith("blocks.0.")}
+    sd = synth.synth_state_dict(shapes, seed=1234, num_layers=w["cfg"]["num_layers"])
+    d = cfg["num_attention_heads"] * cfg["attention_head_dim"]
+    f, h, wd = 1, w["latent"][1], w["latent"][2]
+    S = f * (h // 2) * (wd // 2)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn((1, S, d), generator=g).to(torch.bfloat16)
+    xr = torch.randn((1, S, d), generator=g).to(torch.bfloat16)
+    ctx = (torch.randn((1, 769, d), generator=g) * 0.5).to(torch.bfloat16)
+    temb = (torch.randn((1, 6, d), generator=g) * 0.5).to(torch.bfloat16)
+    fr = wan_oracle.wan_rope(cfg["attention_head_dim"], cfg["patch_size"], 1024, (f, h, wd), ref=False)
+    fr_r = wan_oracle.wan_rope(cfg["attention_head_dim"], cfg["patch_size"], 1024, (f, h, wd), ref=True)
+    times = []
+    with torch.no_grad():
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            wan_oracle.wan_block(sd, "blocks.0", cfg, True, x, ctx, temb, fr, xr, ctx, temb, fr_r, 1)
+            times.append(time.perf_counter() - t0)
+    flops, _ = wan_flops(cfg, S, S)
+    return min(times), flops, f"one Wan-14B-width MoT block (d={d}, H={cfg['num_attention_heads']}), {S}+{S} tokens (1 latent frame per stream), bf16 on CPU"
+
+
+def _meta_state_dict(vap, w, cfg):
+    with torch.device("meta"):
+        m = vap.WanTransformer3DMOTModel(**cfg)
+    return m.state_dict()
+
+
+def cpu_baseline_entry(vap, w, S, Sr):
+    sec, sample_flops, desc = cpu_oracle_sample(vap, w)
+    full_flops, _ = wan_flops(w["cfg"], S, Sr)
+    est = sec * full_flops / sample_flops  # FLOP-proportional scaling of the sample to one full step
+    return dict(value=1.0 / est, unit=UNIT, cores=os.cpu_count(), kind="port",
+                sample=f"{desc}: {sec:.2f} s measured for {sample_flops:.3e} FLOP; scaled by FLOPs to one full step ({full_flops:.3e} FLOP)")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="vap")
+    ap.add_argument("--config", default="wan14b")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    vap = importlib.import_module("video-as-prompt_b200")
+    w = workloads(vap.synth)[a.config]
+    f, h, wd = w["latent"]
+    S = f * (h // 2) * (wd // 2)
+    config = dict(workload=w["name"], tokens_per_stream=S, joint_tokens=2 * S + (452 if w["family"] == "cog" else 0), batch=1,
+                  parallelism=f"ulysses-sp{world}" if world > 1 else "single-gpu",
+                  l2="working set (65 GB of weights + activations per step) >> 126 MB L2: no flush needed")
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        if w["family"] != "wan":
+            print(json.dumps({"impl": "reference", "unavailable": "CPU oracle bench is implemented for the Wan workloads only"}))
+            return
+        vals = []
+        for _ in range(max(a.warmup, 0)):
+            cpu_oracle_sample(vap, w)
+        for _ in range(max(a.steps, 1)):
+            e = cpu_baseline_entry(vap, w, S, S)
+            vals.append(e)
+        best = max(vals, key=lambda e: e["value"])
+        print(json.dumps({"metric": METRIC, "value": best["value"], "unit": UNIT, "n_gpus": 0, "steps": a.steps, "warmup": a.warmup,
+                          "ms_per_step": 1000.0 / best["value"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                          "dtype": "bf16", "data": "synthetic", "impl": "reference", "config": config, "cpu_baseline": best,
+                          "e2e": {"value": best["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback for the product path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        vap.ulysses.enable()
+    model = build_model(vap, w, dev)
+    inp = make_inputs(vap, w, dev)
+    host = {k: (v.cpu().pin_memory() if torch.is_tensor(v) else v) for k, v in inp.items()}
+    h2d = sum(v.numel() * v.element_size() for v in host.values() if torch.is_tensor(v))
+
+    # per-launch timing of the dominant kernel (joint attention) with CUDA events on the launching stream
+    attn_events = []
+    launches = [0]
+    orig_attention = vap.ops.attention
+
+    def timed_attention(q, k, v, **kw):
+        if q.shape[2] == k.shape[2] and record[0]:  # joint self-attention (cross-attention has Lkv = 512 / 257)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = orig_attention(q, k, v, **kw)
+            e1.record()
+            attn_events.append((e0, e1, q.shape))
+            return out
+        return orig_attention(q, k, v, **kw)
+
+    record = [False]
+    vap.ops.attention = timed_attention
+    lib = vap._lib.load()
+    for name in ("vap_adaln_layernorm", "vap_qk_norm_rope", "vap_attention_fwd", "vap_gemm_bf16", "vap_ulysses_pack", "vap_ulysses_unpack"):
+        fn = getattr(lib, name)
+
+        def counted(*args, _fn=fn):
+            launches[0] += 1
+            return _fn(*args)
+        setattr(lib, name, counted)
+
+    sigmas = vap.denoise.flow_match_schedule(max(a.steps + a.warmup, 2), 3.0, device=dev)[1]
+
+    def step(i, x_latent, from_host):
+        kw = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in host.items()} if from_host else inp
+        if w["family"] == "wan":
+            noise = model(**kw, return_dict=False)[0]
+            x_latent = vap.denoise.flow_match_step(noise, x_latent, sigmas[i], sigmas[i + 1])  # scheduler update (fp32 Euler)
+        else:
+            noise = model(**kw, return_dict=False)[0]
+        if from_host:
+            noise_host.copy_(noise, non_blocking=True)
+        return x_latent
+
+    lat_shape = (1, 16, f, h, wd)
+    latents = torch.zeros(lat_shape, dtype=torch.float32, device=dev) if w["family"] == "wan" else None
+    with torch.no_grad():
+        out0 = model(**inp, return_dict=False)[0]
+    noise_host = torch.empty(out0.shape, dtype=out0.dtype).pin_memory()
+    d2h = out0.numel() * out0.element_size()
+
+    def timed(from_host):
+        nonlocal latents
+        with torch.no_grad():
+            for i in range(a.warmup):
+                latents = step(i, latents, from_host)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            launches[0] = 0
+            record[0] = not from_host
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.time()
+            e0.record()
+            for i in range(a.steps):
+                latents = step(a.warmup + i, latents, from_host)
+            e1.record()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t1 = time.time()
+            record[0] = False
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item(), t0, t1, launches[0]
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_dev, t0, t1, n_launch = timed(from_host=False)
+    clocks = sampler.stop(t0, t1) if sampler else None
+    ms_e2e, _, _, _ = timed(from_host=True)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+        roof = None
+        if attn_events:
+            times = [e0.elapsed_time(e1) for e0, e1, _ in attn_events]
+            B_, H_, J_, D_ = attn_events[0][2]
+            fl = 4.0 * B_ * H_ * J_ * J_ * D_
+            avg = sum(times) / len(times)
+            roof = dict(bound="tensor", kernel="attn_fwd_kernel (joint attention)", achieved=fl / (avg * 1e-3) / 1e12, peak=peak, unit="TFLOP/s",
+                        frac=fl / (avg * 1e-3) / 1e12 / peak, traffic=None, launches=len(times), avg_ms=avg, flop_per_launch=fl, peak_source=peak_src,
+                        shape=dict(B=B_, H=H_, J=J_, D=D_))
+        total_flops, _ = wan_flops(w["cfg"], S // world * world, S) if w["family"] == "wan" else (None, None)
+        line = {"metric": METRIC if a.config == "wan14b" else f"DiT denoise steps/s ({w['name']})", "value": a.steps / (ms_dev * 1e-3), "unit": UNIT,
+                "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic (random-init weights, synthetic latents / text / CLIP tokens)", "config": config,
+                "clocks": clocks, "gpu_launches": n_launch,
+                "e2e": {"value": a.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "roofline": roof, "model_tflops": (total_flops / (ms_dev / a.steps * 1e-3) / 1e12) if total_flops else None}
+        if world == 1 and not a.no_cpu_baseline and w["family"] == "wan":
+            line["cpu_baseline"] = cpu_baseline_entry(vap, w, S, S)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

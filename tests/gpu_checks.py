@@ -275,6 +275,8 @@ def _to_dev(x):
         return x.to(DEV)
     if isinstance(x, (list, tuple)):
         return type(x)(_to_dev(t) for t in x)
+    if isinstance(x, dict):
+        return {k: _to_dev(v) for k, v in x.items()}
     return x
 
 
@@ -393,7 +395,7 @@ def check_processor_level():
     blk = model.blocks[0]
     f, h, w = g["latent"]
     rope = vap.rope.wan_rope_tables(128, cfg["patch_size"], (f, h, w), ref=False, device=DEV)
-    x = g["blocks"][0]["hidden_states"].to(DEV)
+    x = g["blocks"][0]["hidden_states"].to(DEV).contiguous()
     with torch.no_grad():
         q, k, v, _ = blk.attn1(hidden_states=x, rotary_emb=rope, is_before_attn=True)
         o = vap.joint_sdpa(q, k, v)

@@ -1,0 +1,167 @@
+"""CPU: the C-ABI library loads and exports every declared symbol, the stand-alone shells mirror the reference's
+state_dict, RoPE table builders agree with the oracle, argument validation / error behaviour, install() seams.
+No kernel is launched here (there is no GPU)."""
+import importlib
+import json
+import os
+import re
+
+import pytest
+import torch
+
+from oracle import cog_oracle, wan_oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+vap = importlib.import_module("video-as-prompt_b200")
+
+
+def test_library_exports_every_header_symbol():
+    header = open(os.path.join(ROOT, "include", "vap_b200.h")).read()
+    declared = set(re.findall(r"\b(vap_[a-z0-9_]+)\s*\(", header))
+    assert {"vap_attention_fwd", "vap_gemm_bf16", "vap_adaln_layernorm", "vap_qk_norm_rope", "vap_ulysses_pack"} <= declared
+    lib = vap._lib.load()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/vap_b200.h but not exported by libvap_b200.so"
+    assert declared == set(vap._lib.SIGNATURES), "ctypes SIGNATURES out of sync with the header"
+    assert lib.vap_version() == int(re.search(r"#define VAP_B200_VERSION (\d+)", header).group(1))
+    assert lib.vap_last_error() is not None
+
+
+def test_alias_import():
+    import vap_b200
+    assert vap_b200 is vap and hasattr(vap_b200, "install")
+
+
+def test_c_abi_rejects_bad_arguments_without_a_gpu():
+    lib = vap._lib.load()
+    assert lib.vap_gemm_bf16(0, 0, 0, 0, 0, 0, 1, 8, 8, 0, 0, 0, 0, 0, 0, 1, 0) == -1
+    assert b"null tensor" in lib.vap_last_error()
+    assert lib.vap_attention_fwd(16, 16, 16, 16, 0, 1, 1, 8, 8, 96, *([8] * 12), 1.0, 0) == -1
+    assert b"head_dim" in lib.vap_last_error()
+    assert lib.vap_adaln_layernorm(16, 16, 4, 12, 16, 16, 0, 0, 0, 0, 0, 1, 1e-6, 0, 0) == -1
+    assert lib.vap_qk_norm_rope(16, 16, 4, 2, 48, 96, 16, 0, 16, 0, 0, 0, 4, 0, 0, 1e-6, 0, 0) == -1
+
+
+def test_ops_fail_loudly_on_cpu_tensors():
+    x = torch.zeros(4, 256, dtype=torch.bfloat16)
+    with pytest.raises(vap.VapError, match="no CPU fallback"):
+        vap.ops.linear(x, torch.zeros(256, 256, dtype=torch.bfloat16))
+    with pytest.raises(vap.VapError):
+        vap.ops.adaln_layernorm(x, eps=1e-6, rounding=0)
+    with pytest.raises(vap.VapError):
+        vap.ops.attention(torch.zeros(1, 1, 8, 128, dtype=torch.bfloat16), torch.zeros(1, 1, 8, 128, dtype=torch.bfloat16),
+                          torch.zeros(1, 1, 8, 128, dtype=torch.bfloat16))
+    with pytest.raises(TypeError):
+        vap.ops._need_cuda_bf16("nope", "x")
+
+
+def test_joint_sdpa_constraints():
+    q = torch.zeros(1, 2, 8, 128, dtype=torch.bfloat16)
+    for kw in (dict(attn_mask=torch.zeros(8, 8)), dict(dropout_p=0.1), dict(is_causal=True), dict(enable_gqa=True)):
+        with pytest.raises(ValueError):
+            vap.joint_sdpa(q, q, q, **kw)
+    with pytest.raises(ValueError, match="bfloat16"):
+        vap.joint_sdpa(q.float(), q.float(), q.float())
+    with pytest.raises(ValueError, match="head_dim"):
+        vap.joint_sdpa(q[..., :96], q[..., :96], q[..., :96])
+
+
+@pytest.mark.parametrize("family", ["wan", "cog"])
+def test_shell_state_dict_matches_reference(family):
+    """Key-for-key and shape-for-shape equal to the reference model's state_dict (recorded by oracle/gen_golden.py)."""
+    spec = json.load(open(os.path.join(ROOT, "tests", "golden", f"{family}_tiny_keys.json")))
+    cfg = spec["config"]
+    if family == "wan":
+        cfg["patch_size"] = tuple(cfg["patch_size"])
+        model = vap.WanTransformer3DMOTModel(**cfg)
+    else:
+        model = vap.CogVideoXTransformer3DMOTModel(**cfg)
+    mine = {k: list(v.shape) for k, v in model.state_dict().items()}
+    assert mine.keys() == spec["shapes"].keys(), (set(mine) ^ set(spec["shapes"]))
+    assert mine == spec["shapes"]
+    # the trainer's trainable filter (finetrainers/trainer/sft_trainer/trainer.py:154-164) selects the expert by name
+    assert any("_mot_ref" in k for k in mine)
+
+
+def test_wan_rope_tables_match_oracle():
+    for ref in (False, True):
+        fr = wan_oracle.wan_rope(128, (1, 2, 2), 1024, (3, 8, 12), ref=ref)[0, 0]
+        cos, sin = vap.rope.wan_rope_tables(128, (1, 2, 2), (3, 8, 12), ref=ref, device="cpu")
+        assert cos.dtype == torch.float32 and cos.shape == (3 * 4 * 6, 64)
+        assert torch.allclose(cos.double(), fr.real, atol=1e-7) and torch.allclose(sin.double(), fr.imag, atol=1e-7)
+        c2, s2 = vap.rope.as_tables(fr.view(1, 1, -1, 64), 128, "cpu")
+        assert torch.equal(c2, cos) or torch.allclose(c2, cos, atol=1e-7)
+
+
+def test_cog_rope_matches_oracle_and_compacts():
+    for kw in (dict(), dict(mot_num=1), dict(mot_num=2), dict(mot_num=1, ref_type="discrete_long_reference")):
+        a = vap.rope.get_3d_rotary_pos_embed(64, ((0, 0), (6, 8)), (6, 8), 3, **kw)
+        b = cog_oracle.cog_rope_3d(64, ((0, 0), (6, 8)), (6, 8), 3, **kw)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+        c, s = vap.rope.as_tables(a, 64, "cpu")
+        assert c.shape == (a[0].shape[0], 32) and torch.equal(c, a[0][:, ::2].contiguous())
+    with pytest.raises(ValueError):
+        vap.rope.get_3d_rotary_pos_embed(64, ((0, 0), (6, 8)), (6, 8), 3, mot_num=1, ref_type="bogus")
+
+
+def test_synth_is_deterministic_and_name_keyed():
+    a = vap.synth.synth_tensor("blocks.0.attn1.to_q.weight", (8, 8), seed=1)
+    assert torch.equal(a, vap.synth.synth_tensor("blocks.0.attn1.to_q.weight", (8, 8), seed=1))
+    assert not torch.equal(a, vap.synth.synth_tensor("blocks.0.attn1.to_k.weight", (8, 8), seed=1))
+    assert abs(vap.synth.synth_tensor("blocks.0.norm2.weight", (4096,), 0).mean().item() - 1.0) < 0.02
+
+
+def test_install_rebinds_block_forward_and_keeps_state_dict():
+    cfg = dict(vap.synth.WAN_TINY)
+    model = vap.WanTransformer3DMOTModel(**cfg)
+    keys = list(model.state_dict())
+    vap.install(model, level="block")
+    assert all(b.forward.__func__ is vap.wan_block_forward for b in model.blocks)
+    assert list(model.state_dict()) == keys
+    vap.uninstall(model)
+    vap.install(model, level="processor")
+    import torch.nn.functional as F
+    assert F.scaled_dot_product_attention is vap.joint_sdpa
+    assert type(model.blocks[0].attn1.processor).__name__ == "WanAttnMOTProcessor2_0"
+    vap.uninstall(model)
+    assert F.scaled_dot_product_attention is not vap.joint_sdpa
+    with pytest.raises(ValueError):
+        vap.install(model, level="nope")
+    with pytest.raises(TypeError):
+        vap.install(torch.nn.Linear(2, 2))
+
+
+def test_attention_module_filters_unknown_kwargs(caplog):
+    """Attention.forward drops kwargs the processor does not declare, with a warning (attention_processor.py:593-602)."""
+    seen = {}
+
+    class Proc:
+        def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, rotary_emb=None):
+            seen["rotary"] = rotary_emb
+            return hidden_states
+
+    a = vap.modules.Attention(16, 2, 8, "rms_norm_across_heads", processor=Proc())
+    with caplog.at_level("WARNING", logger="vap_b200"):
+        out = a(torch.zeros(1, 2, 16), rotary_emb="r", bogus=1)
+    assert seen["rotary"] == "r" and out.shape == (1, 2, 16)
+    assert any("bogus" in r.message for r in caplog.records)
+
+
+def test_packed_qkv_views_keep_state_dict_roundtrip():
+    a = vap.modules.Attention(16, 2, 8, "rms_norm_across_heads", bias=True)
+    before = {k: v.clone() for k, v in a.state_dict().items()}
+    W, b = vap.wan._packed(a, "qkv", [a.to_q, a.to_k, a.to_v])
+    assert W.shape == (48, 16) and a.to_k.weight.data_ptr() == W[16:32].data_ptr()
+    after = a.state_dict()
+    assert all(torch.equal(before[k], after[k]) for k in before)
+    a.load_state_dict({k: v + 1 for k, v in before.items()})
+    assert torch.equal(W[:16], before["to_q.weight"] + 1), "load_state_dict must write through to the packed storage"
+    assert vap.wan._packed(a, "qkv", [a.to_q, a.to_k, a.to_v])[0] is W
+
+
+def test_flow_match_schedule_matches_oracle():
+    from oracle import denoise as od
+    for n, sh in ((4, 3.0), (50, 5.0), (4, 1.0)):
+        t1, s1 = vap.denoise.flow_match_schedule(n, sh)
+        t2, s2 = od.flow_match_schedule(n, sh)
+        assert torch.allclose(t1, t2, rtol=1e-6) and torch.allclose(s1, s2, rtol=1e-6)

@@ -23,7 +23,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops
+from . import ops, ulysses
 from .modules import Attention, FeedForward, FP32LayerNorm, PixArtAlphaTextProjection, TimestepEmbedding
 from .rope import Tables, as_tables, wan_rope_tables
 
@@ -139,6 +139,23 @@ def _cross_attn(attn: nn.Module, x: torch.Tensor, ctx: torch.Tensor, num_mot_ref
     return o
 
 
+def _joint_attention(qkv: torch.Tensor, heads: int) -> torch.Tensor:
+    """Joint attention over the rows of `qkv` [B, J, 3*inner] -> O [B, J, inner] (token-major).
+
+    Single GPU: the kernel reads q/k/v as strided views of the joint buffer.  Under Ulysses sequence parallelism
+    (ulysses.enable()) the rows are this rank's token shard of both streams: all-to-all #1 trades them for all rows of
+    H/P heads, the kernel runs on those heads over the full joint sequence, all-to-all #2 brings O back."""
+    sp = ulysses.current()
+    if sp is None:
+        q, k, v = _split_qkv(qkv, heads)
+        return _token_major(ops.attention(q, k, v))
+    if qkv.shape[0] != 1:
+        raise NotImplementedError("Ulysses sequence parallelism expects batch 1 per forward (the Wan pipeline's CFG passes are B=1)")
+    q, k, v = ulysses.exchange_qkv(qkv[0], heads, sp)
+    o = _token_major(ops.attention(q, k, v))[0]  # [P*L_loc, (H/P)*D]
+    return ulysses.exchange_out(o, sp).unsqueeze(0)
+
+
 # ----------------------------------------------------------------------------------------------
 # fused block forward  (boundary B3)
 # ----------------------------------------------------------------------------------------------
@@ -173,7 +190,8 @@ def wan_block_forward(self: nn.Module, hidden_states: torch.Tensor, encoder_hidd
                       rotary_emb_mot_ref: Union[torch.Tensor, Tables, None] = None, num_mot_ref: Optional[int] = None):
     """Drop-in for WanTransformerBlock.forward (:566-699), same signature and return value, running on the sm_100a kernels.
     `self` is a WanTransformerBlock — the reference's or ours (duck-typed on the submodule names)."""
-    x = hidden_states
+    # the reference shell hands block 0 a transposed view (patch_embedding(...).flatten(2).transpose(1, 2), :897-898)
+    x = hidden_states.contiguous()
     attn1 = self.attn1
     heads = attn1.heads
     eps = self.norm1.eps
@@ -183,15 +201,14 @@ def wan_block_forward(self: nn.Module, hidden_states: torch.Tensor, encoder_hidd
 
     if not self.with_mot_ref:  # :580-601
         xn = ops.adaln_layernorm(x, eps=eps, rounding=ops.ROUND_WAN, scale1p=scale1p, shift=shift)
-        q, k, v = _split_qkv(_self_attn_qkv(attn1, xn, tables), heads)
-        o = _token_major(ops.attention(q, k, v))
+        o = _joint_attention(_self_attn_qkv(attn1, xn, tables), heads)
         x = _linear(attn1.to_out[0], o, epilogue=ops.EPI_GATE_RES_F32, residual=x, gate=gate)
         x = _stream_tail(self, "", x, encoder_hidden_states, c_shift, c_scale1p, c_gate, eps, 1)
         return x, hidden_states_mot_ref
 
     if num_mot_ref != 1:
         raise AssertionError("num_mot_ref must be 1 (transformer_wan_mot.py:611)")
-    xr = hidden_states_mot_ref
+    xr = hidden_states_mot_ref.contiguous()
     attn1_r = self.attn1_mot_ref
     shift_r, scale1p_r, gate_r, c_shift_r, c_scale1p_r, c_gate_r = _modulation(self.scale_shift_table_mot_ref, temb_mot_ref)
     tables_r = as_tables(rotary_emb_mot_ref, hd, x.device)
@@ -205,8 +222,7 @@ def wan_block_forward(self: nn.Module, hidden_states: torch.Tensor, encoder_hidd
     qkv = torch.empty((B, S + Sr, 3 * inner), dtype=torch.bfloat16, device=x.device)
     _self_attn_qkv(attn1, xn, tables, out=qkv[:, :S])
     _self_attn_qkv(attn1_r, xn_r, tables_r, out=qkv[:, S:])
-    q, k, v = _split_qkv(qkv, heads)
-    o = _token_major(ops.attention(q, k, v))  # [B, J, inner], rows [target | ref]
+    o = _joint_attention(qkv, heads)  # [B, J, inner], rows [target | ref]
     x = _linear(attn1.to_out[0], o[:, :S], epilogue=ops.EPI_GATE_RES_F32, residual=x, gate=gate)
     xr = _linear(attn1_r.to_out[0], o[:, S:], epilogue=ops.EPI_GATE_RES_F32, residual=xr, gate=gate_r)
 
@@ -227,10 +243,11 @@ class WanAttnMOTProcessor2_0:
                  query: Optional[torch.Tensor] = None, key: Optional[torch.Tensor] = None, value: Optional[torch.Tensor] = None):
         if is_before_attn:
             hd = attn.to_q.weight.shape[0] // attn.heads
+            hidden_states = hidden_states.contiguous()
             qkv = _self_attn_qkv(attn, hidden_states, as_tables(rotary_emb, hd, hidden_states.device))
             q, k, v = _split_qkv(qkv, attn.heads)
             return q, k, v, attention_mask
-        return _linear(attn.to_out[0], _token_major(hidden_states))
+        return _linear(attn.to_out[0], _token_major(hidden_states).contiguous())
 
 
 class WanAttnProcessor2_0:
@@ -389,6 +406,13 @@ class WanTransformer3DMOTModel(nn.Module):
 
         x = self.patch_embedding(hidden_states).flatten(2).transpose(1, 2).contiguous()
         xr = self.patch_embedding_mot_ref(hidden_states_mot_ref).flatten(2).transpose(1, 2).contiguous()
+        sp = ulysses.current()
+        if sp is not None:  # token-shard both streams (and their RoPE tables) — same place the reference's CP plan splits
+            ulysses.check_divisible(x.shape[1], cfg["num_attention_heads"], sp.world)
+            ulysses.check_divisible(xr.shape[1], cfg["num_attention_heads"], sp.world)
+            x, xr = ulysses.shard_rows(x, sp).contiguous(), ulysses.shard_rows(xr, sp).contiguous()
+            rope = tuple(ulysses.shard_rows(t, sp, 0) for t in rope)
+            rope_r = tuple(ulysses.shard_rows(t, sp, 0) for t in rope_r)
         temb, proj, ctx, ctx_img = self.condition_embedder([timestep], encoder_hidden_states, encoder_hidden_states_image)
         proj = proj.unflatten(1, (6, -1))
         temb_r, proj_r, ctx_r, ctx_img_r = self.condition_embedder_mot_ref(list(timestep_list_mot_ref), encoder_hidden_states_mot_ref,
@@ -405,6 +429,8 @@ class WanTransformer3DMOTModel(nn.Module):
         shift, scale = (self.scale_shift_table + temb.unsqueeze(1)).chunk(2, dim=1)  # :952 (model dtype)
         x = ops.adaln_layernorm(x, eps=cfg["eps"], rounding=ops.ROUND_WAN, scale1p=(1 + scale).float(), shift=shift.float())
         x = self.proj_out(x)
+        if sp is not None:  # all-gather the rank-local rows at proj_out, like the reference's ContextParallelGatherHook (ptd.py:675-679)
+            x = ulysses.gather_rows(x, sp)
         x = x.reshape(B, Fr // p_t, Hh // p_h, Ww // p_w, p_t, p_h, p_w, -1).permute(0, 7, 1, 4, 2, 5, 3, 6)
         out = x.flatten(6, 7).flatten(4, 5).flatten(2, 3)
         if not return_dict:
