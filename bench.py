@@ -45,6 +45,9 @@ def workloads(synth):
         "wan14b": dict(family="wan", cfg=synth.WAN_14B, latent=(13, 60, 104), name="Wan2.1-I2V-14B VAP (40/40 MoT blocks), 49f 480x832"),
         "wan14b_720p": dict(family="wan", cfg=synth.WAN_14B, latent=(21, 90, 160), name="Wan2.1-I2V-14B VAP (40/40 MoT blocks), 81f 720x1280"),
         "cog5b": dict(family="cog", cfg=synth.COG_5B, latent=(13, 60, 90), name="CogVideoX-5B-I2V VAP (41/42 MoT blocks), 49f 480x720"),
+        # same widths as wan14b with 2 of the 40 blocks: fast to initialise, used for the ncu launch list (per-block kernel shares are identical)
+        "wan14b_2l": dict(family="wan", cfg=dict(synth.WAN_14B, num_layers=2, block_idx_with_mot_ref=[0, 1]), latent=(13, 60, 104),
+                          name="Wan2.1-I2V-14B VAP widths, 2 MoT blocks, 49f 480x832 (profiling only)"),
         "wan_tiny": dict(family="wan", cfg=dict(synth.WAN_TINY, num_layers=2, block_idx_with_mot_ref=[0, 1]), latent=(3, 16, 24), name="tiny Wan VAP"),
     }
 
@@ -172,6 +175,7 @@ def main():
     ap.add_argument("--impl", default="vap")
     ap.add_argument("--config", default="wan14b")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="bracket the device-timed steps with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     a = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -274,10 +278,15 @@ def main():
             record[0] = not from_host
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             t0 = time.time()
+            if a.profile and not from_host:
+                torch.cuda.profiler.start()
             e0.record()
             for i in range(a.steps):
                 latents = step(a.warmup + i, latents, from_host)
             e1.record()
+            if a.profile and not from_host:
+                torch.cuda.synchronize()
+                torch.cuda.profiler.stop()
             torch.cuda.synchronize()
             if world > 1:
                 dist.barrier()
