@@ -25,6 +25,10 @@ constexpr int kAttnThreads = 384;
 constexpr int kBlockM = 128;  // rows per Q tile
 constexpr int kBlockN = 128;  // kv rows per tile
 constexpr float kRescaleThreshold = 8.0f;
+#ifndef VAP_ATTN_POLY_PAIRS
+#define VAP_ATTN_POLY_PAIRS 3
+#endif
+constexpr int kPolyPairs = VAP_ATTN_POLY_PAIRS;  // of every 8 (p0,p1) pairs, how many take the software exp2
 
 template <int D>
 struct AttnCfg {
@@ -90,7 +94,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
 
-    if (warp == 0) {
+    // register re-balancing between the warpgroups: the producer/MMA/allocator warps need few registers, the
+    // one-thread-per-row softmax warps hold a whole 128-column S row (128 x 80 + 256 x 208 = 63488 <= 65536)
+    if (warp < 4) {
+      setmaxnreg_dec<80>();
+      if (warp == 0) {
         if (lane == 0) {
             // ===== TMA producer =====
             mbar_arrive_expect_tx(q_full, 2 * Cfg::kTileBytes);
@@ -181,7 +189,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 if (has_next) umma_commit(kv_empty(k_stage));
             }
         }
-    } else if (warp >= 4) {
+      }
+    } else {
+        setmaxnreg_inc<208>();
         // ===== softmax + epilogue warps =====
         const int i = (warp - 4) >> 2;  // Q tile
         const int q = warp & 3;         // TMEM lane quarter
@@ -207,11 +217,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     for (int e = 0; e < 32; ++e)
                         if (32 * ch + e >= valid) sr[ch][e] = __float_as_uint(-INFINITY);
             }
-            float m_t = -INFINITY;
+            // row max: four independent FMNMX3 chains (one per 32-column chunk)
+            float mx[4];
 #pragma unroll
-            for (int ch = 0; ch < 4; ++ch)
+            for (int ch = 0; ch < 4; ++ch) {
+                mx[ch] = fmax3(__uint_as_float(sr[ch][0]), __uint_as_float(sr[ch][1]), __uint_as_float(sr[ch][2]));
 #pragma unroll
-                for (int e = 0; e < 32; ++e) m_t = fmaxf(m_t, __uint_as_float(sr[ch][e]));
+                for (int e = 3; e < 31; e += 2) mx[ch] = fmax3(mx[ch], __uint_as_float(sr[ch][e]), __uint_as_float(sr[ch][e + 1]));
+                mx[ch] = fmaxf(mx[ch], __uint_as_float(sr[ch][31]));
+            }
+            const float m_t = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
             const float m_new = fmaxf(m_used, m_t);
             if (j == 0) {
                 m_used = m_new;
@@ -221,7 +236,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     // O_i must be quiescent: PV_{j-1} complete (PV_j cannot start before our p_full arrive)
                     mbar_wait(o_done(i), (j - 1) & 1);
                     tc_fence_after();
-                    const float f = exp2f((m_used - m_new) * c);
+                    const float f = ex2_approx((m_used - m_new) * c);
                     l *= f;
 #pragma unroll 1
                     for (int c0 = 0; c0 < D; c0 += 32) {
@@ -236,21 +251,37 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     m_used = m_new;
                 }
             }
-            const float mc = m_used * c;
-            float lsum = 0.f;
+            // p = 2^(s*c - m*c): packed FFMA2 for the scale/shift, MUFU.EX2 for most pairs and the FMA-pipe polynomial for
+            // kPolyPairs of every 8 pairs (the MUFU issues one warp-instruction per 8 clk and would otherwise pace the loop)
+            const uint64_t c2 = pack_f32x2(c, c);
+            const float nmc = -m_used * c;
+            const uint64_t nmc2 = pack_f32x2(nmc, nmc);
+            uint64_t lsum2[2] = {0ull, 0ull};
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
                 uint32_t pk[16];
 #pragma unroll
                 for (int e = 0; e < 16; ++e) {
-                    const float p0 = exp2f(fmaf(__uint_as_float(sr[ch][2 * e]), c, -mc));
-                    const float p1 = exp2f(fmaf(__uint_as_float(sr[ch][2 * e + 1]), c, -mc));
-                    lsum += p0 + p1;
+                    const uint64_t x2 = fma_f32x2(pack_f32x2(__uint_as_float(sr[ch][2 * e]), __uint_as_float(sr[ch][2 * e + 1])), c2, nmc2);
+                    float x0, x1, p0, p1;
+                    unpack_f32x2(x2, x0, x1);
+                    if ((e & 7) < kPolyPairs) {
+                        ex2_poly_x2(x0, x1, p0, p1);
+                    } else {
+                        p0 = ex2_approx(x0);
+                        p1 = ex2_approx(x1);
+                    }
+                    lsum2[e & 1] = add_f32x2(lsum2[e & 1], pack_f32x2(p0, p1));
                     pk[e] = pack_bf16x2(p0, p1);
                 }
                 tmem_st_x16(s_col + 16 * ch, pk);
             }
-            l += lsum;
+            {
+                float a0, a1, b0, b1;
+                unpack_f32x2(lsum2[0], a0, a1);
+                unpack_f32x2(lsum2[1], b0, b1);
+                l += (a0 + a1) + (b0 + b1);
+            }
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(p_full(i));

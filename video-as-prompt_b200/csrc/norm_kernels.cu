@@ -26,7 +26,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 // ------------------------------------------------------------------------------------------
 
 template <int MAXV>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) adaln_layernorm_kernel(LnParams p) {
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, (MAXV <= 20) ? 2 : 1) adaln_layernorm_kernel(LnParams p) {
     const int lane = threadIdx.x & 31;
     const int64_t row = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
     if (row >= p.rows) return;
@@ -148,7 +148,7 @@ int launch_adaln_layernorm(const LnParams& p, cudaStream_t stream) {
 // (vector v = lane + 32*i  ->  channel-in-head 8*(v % (D/8)) = 8*(lane % (D/8)) because 32 % (D/8) == 0),
 // so its 4 RoPE (cos,sin) pairs and (Cog) its per-head LN affine values are loaded once.
 template <int MAXV, bool COG>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) qk_norm_rope_kernel(QkParams p) {
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, (MAXV <= 20) ? 2 : 1) qk_norm_rope_kernel(QkParams p) {
     const int lane = threadIdx.x & 31;
     const int64_t row = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
     if (row >= p.rows) return;

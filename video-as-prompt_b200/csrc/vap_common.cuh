@@ -244,6 +244,68 @@ __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// ------------------------------------------------------------------------------------------
+// packed fp32x2 arithmetic (sm_100 FFMA2 / FADD2), 3-input max (FMNMX3), raw MUFU.EX2
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t add_rm_f32x2(uint64_t a, uint64_t b) {  // round toward -inf
+    uint64_t d;
+    asm("add.rm.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t sub_f32x2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// 2^x for a pair, x <= ~100, evaluated on the FMA pipe instead of the MUFU (FlashAttention-4 style software exp2):
+// x = n + f with n = floor(x) (add.rm against 1.5*2^23), 2^f by a degree-3 minimax polynomial on [0,1) (rel. error
+// ~1e-4, far below the bf16 rounding of P), n added into the exponent field.  x is clamped to >= -127 (result -> 0).
+__device__ __forceinline__ void ex2_poly_x2(float x0, float x1, float& y0, float& y1) {
+    const float kMagic = 12582912.f;  // 2^23 + 2^22
+    x0 = fmaxf(x0, -127.f);
+    x1 = fmaxf(x1, -127.f);
+    const uint64_t x = pack_f32x2(x0, x1);
+    const uint64_t r = add_rm_f32x2(x, pack_f32x2(kMagic, kMagic));
+    const uint64_t n = sub_f32x2(r, pack_f32x2(kMagic, kMagic));
+    const uint64_t f = sub_f32x2(x, n);
+    uint64_t pl = fma_f32x2(pack_f32x2(0.077119089663028717f, 0.077119089663028717f), f, pack_f32x2(0.227564394474029541f, 0.227564394474029541f));
+    pl = fma_f32x2(pl, f, pack_f32x2(0.695146143436431885f, 0.695146143436431885f));
+    pl = fma_f32x2(pl, f, pack_f32x2(1.0f, 1.0f));
+    float p0, p1, r0, r1;
+    unpack_f32x2(pl, p0, p1);
+    unpack_f32x2(r, r0, r1);
+    y0 = __int_as_float(__float_as_int(p0) + (__float_as_int(r0) << 23));
+    y1 = __int_as_float(__float_as_int(p1) + (__float_as_int(r1) << 23));
+}
+
 // named barrier over a subset of warps
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
