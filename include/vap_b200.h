@@ -103,6 +103,10 @@ int vap_ulysses_unpack(const void* src, void* dst, int64_t L, int nsplit, int64_
 int vap_probe_umma(const void* A, const void* B, float* Dout, int N, int K, int a_in_tmem, int b_mn_major, int lbo_b, int sbo_b,
                    int kstep_b, int layout_type, void* stream);
 
+/* (7) Debug: when set to a device buffer of 3*64*8 int64, CTA (0,0,0) of every following vap_attention_fwd records
+ *     clock64() stamps of its softmax warps and MMA issuer (see tools/attn_trace.py).  NULL disables it. */
+int vap_debug_set_attention_trace(void* device_buffer);
+
 #ifdef __cplusplus
 }
 #endif

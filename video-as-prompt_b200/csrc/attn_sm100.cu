@@ -79,7 +79,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_init(q_full, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(s_full(i), 1);
-            mbar_init(p_full(i), 128);
+            mbar_init(p_full(i), 4);  // one arrive per softmax warp
             mbar_init(o_done(i), 1);
         }
         fence_mbar_init();
@@ -95,34 +95,39 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
 
     // register re-balancing between the warpgroups: the producer/MMA/allocator warps need few registers, the
-    // one-thread-per-row softmax warps hold a whole 128-column S row (128 x 80 + 256 x 208 = 63488 <= 65536)
+    // one-thread-per-row softmax warps hold a whole 128-column S row (128 x 96 + 256 x 200 = 63488 <= 65536).
+    // The producer and MMA warps run their loops warp-wide (all lanes wait on the mbarriers, one elected lane issues):
+    // control flow and descriptors stay warp-uniform, so ptxas keeps them in uniform registers instead of wrapping
+    // every UTCHMMA / UTMALDG in an R2UR waterfall loop.
     if (warp < 4) {
-      setmaxnreg_dec<80>();
+      setmaxnreg_dec<96>();
       if (warp == 0) {
-        if (lane == 0) {
             // ===== TMA producer =====
-            mbar_arrive_expect_tx(q_full, 2 * Cfg::kTileBytes);
-            for (int t = 0; t < 2; ++t)
-                for (int h = 0; h < Cfg::kHalves; ++h)
-                    tma_load_4d(q_smem + t * Cfg::kTileBytes + h * Cfg::kHalfBytes, &tmQ, q_full, h * 64, q0 + t * kBlockM, head, batch);
+            if (elect_one()) {
+                mbar_arrive_expect_tx(q_full, 2 * Cfg::kTileBytes);
+                for (int t = 0; t < 2; ++t)
+                    for (int h = 0; h < Cfg::kHalves; ++h)
+                        tma_load_4d(q_smem + t * Cfg::kTileBytes + h * Cfg::kHalfBytes, &tmQ, q_full, h * 64, q0 + t * kBlockM, head, batch);
+            }
             int stage = 0;
             uint32_t phase = 0;
             for (int j = 0; j < n_kv; ++j) {
                 for (int kv = 0; kv < 2; ++kv) {  // K_j then V_j
                     mbar_wait(kv_empty(stage), phase ^ 1);
-                    mbar_arrive_expect_tx(kv_full(stage), Cfg::kTileBytes);
-                    const uint32_t dst = kv_smem + stage * Cfg::kTileBytes;
-                    for (int h = 0; h < Cfg::kHalves; ++h)
-                        tma_load_4d(dst + h * Cfg::kHalfBytes, kv == 0 ? &tmK : &tmV, kv_full(stage), h * 64, j * kBlockN, head, batch);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(kv_full(stage), Cfg::kTileBytes);
+                        const uint32_t dst = kv_smem + stage * Cfg::kTileBytes;
+                        for (int h = 0; h < Cfg::kHalves; ++h)
+                            tma_load_4d(dst + h * Cfg::kHalfBytes, kv == 0 ? &tmK : &tmV, kv_full(stage), h * 64, j * kBlockN, head, batch);
+                    }
+                    __syncwarp();
                     if (++stage == Cfg::kKvStages) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
             }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
+      } else if (warp == 1) {
             // ===== MMA issuer =====
             constexpr uint32_t idesc_qk = make_idesc_bf16(kBlockM, kBlockN, 0, 0);  // S = Q K^T : A, B K-major
             constexpr uint32_t idesc_pv = make_idesc_bf16(kBlockM, D, 0, 1);        // O = P V   : A (TMEM) K-major, B MN-major
@@ -131,21 +136,31 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
             auto issue_qk = [&](int i, uint32_t k_addr) {
                 const uint32_t q_addr = q_smem + i * Cfg::kTileBytes;
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < D / 16; ++k) {
-                    const uint32_t off = (k >> 2) * Cfg::kHalfBytes + (k & 3) * 32;
-                    umma_ss(col_s[i], make_smem_desc(q_addr + off, 0, 1024, kLayoutSw128),
-                            make_smem_desc(k_addr + off, 0, 1024, kLayoutSw128), idesc_qk, k != 0 ? 1u : 0u);
+                    for (int k = 0; k < D / 16; ++k) {
+                        const uint32_t off = (k >> 2) * Cfg::kHalfBytes + (k & 3) * 32;
+                        umma_ss(col_s[i], make_smem_desc(q_addr + off, 0, 1024, kLayoutSw128),
+                                make_smem_desc(k_addr + off, 0, 1024, kLayoutSw128), idesc_qk, k != 0 ? 1u : 0u);
+                    }
                 }
+                __syncwarp();
             };
-            auto issue_pv = [&](int i, uint32_t v_addr, bool accumulate) {
+            auto issue_pv = [&](int i, uint32_t v_addr, uint32_t accumulate) {
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < kBlockN / 16; ++k) {
-                    // A: P_i, packed bf16 pairs, 8 TMEM columns per 16 kv;  B: V rows [16k, 16k+16) (2048 B apart),
-                    // MN-major: 64-column slabs kHalfBytes apart (LBO), 8-row groups 1024 B apart (SBO)
-                    umma_ts(col_o[i], col_s[i] + 8 * k, make_smem_desc(v_addr + k * 2048, Cfg::kHalfBytes, 1024, kLayoutSw128),
-                            idesc_pv, (accumulate || k != 0) ? 1u : 0u);
+                    for (int k = 0; k < kBlockN / 16; ++k) {
+                        // A: P_i, packed bf16 pairs, 8 TMEM columns per 16 kv;  B: V rows [16k, 16k+16) (2048 B apart),
+                        // MN-major: 64-column slabs kHalfBytes apart (LBO), 8-row groups 1024 B apart (SBO)
+                        umma_ts(col_o[i], col_s[i] + 8 * k, make_smem_desc(v_addr + k * 2048, Cfg::kHalfBytes, 1024, kLayoutSw128),
+                                idesc_pv, k != 0 ? 1u : accumulate);
+                    }
                 }
+                __syncwarp();
+            };
+            auto commit = [&](uint32_t bar) {
+                if (elect_one()) umma_commit(bar);
+                __syncwarp();
             };
 
             int stage = 0;
@@ -160,13 +175,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             mbar_wait(kv_full(stage), phase);  // K_0
             tc_fence_after();
             issue_qk(0, kv_smem + stage * Cfg::kTileBytes);
-            umma_commit(s_full(0));
+            commit(s_full(0));
             issue_qk(1, kv_smem + stage * Cfg::kTileBytes);
-            umma_commit(s_full(1));
-            umma_commit(kv_empty(stage));
+            commit(s_full(1));
+            commit(kv_empty(stage));
             advance();
+            long long* trm = (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) ? p.trace + 1024 : nullptr;
+#define TRM(k) do { if (trm && j < 64) trm[j * 8 + (k)] = clock64(); } while (0)
             for (int j = 0; j < n_kv; ++j) {
                 const int v_stage = stage;
+                TRM(0);
                 mbar_wait(kv_full(stage), phase);  // V_j
                 advance();
                 const int k_stage = stage;
@@ -175,23 +193,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     mbar_wait(kv_full(stage), phase);  // K_{j+1}
                     advance();
                 }
+                TRM(1);
                 for (int i = 0; i < 2; ++i) {
                     mbar_wait(p_full(i), j & 1);
                     tc_fence_after();
-                    issue_pv(i, kv_smem + v_stage * Cfg::kTileBytes, j > 0);
-                    umma_commit(o_done(i));
+                    TRM(2 + 2 * i);
+                    issue_pv(i, kv_smem + v_stage * Cfg::kTileBytes, j > 0 ? 1u : 0u);
+                    commit(o_done(i));
                     if (has_next) {
                         issue_qk(i, kv_smem + k_stage * Cfg::kTileBytes);
-                        umma_commit(s_full(i));
+                        commit(s_full(i));
                     }
+                    TRM(3 + 2 * i);
                 }
-                umma_commit(kv_empty(v_stage));
-                if (has_next) umma_commit(kv_empty(k_stage));
+                commit(kv_empty(v_stage));
+                if (has_next) commit(kv_empty(k_stage));
             }
-        }
       }
     } else {
-        setmaxnreg_inc<208>();
+        setmaxnreg_inc<200>();
         // ===== softmax + epilogue warps =====
         const int i = (warp - 4) >> 2;  // Q tile
         const int q = warp & 3;         // TMEM lane quarter
@@ -202,13 +222,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const float c = p.scale_log2;
         float m_used = -INFINITY;
         float l = 0.f;
+        long long* tr = (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && q == 0 && lane == 0) ? p.trace + i * 512 : nullptr;
+#define TR(k) do { if (tr && j < 64) tr[j * 8 + (k)] = clock64(); } while (0)
         for (int j = 0; j < n_kv; ++j) {
+            TR(0);
             mbar_wait(s_full(i), j & 1);
             tc_fence_after();
+            TR(1);
             uint32_t sr[4][32];
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) tmem_ld_x32(s_col + 32 * ch, sr[ch]);
             tmem_ld_wait();
+            TR(2);
             const int valid = p.Lkv - j * kBlockN;  // >= 1
             if (valid < kBlockN) {
 #pragma unroll
@@ -228,6 +253,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
             const float m_t = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
             const float m_new = fmaxf(m_used, m_t);
+            // o_done(i) completes one phase per KV tile; mbarrier waits only carry a parity bit, so every phase is consumed
+            // exactly once, in order: phase j-1 either in the rescale branch or right before this tile's p_full arrive.
+            bool o_waited = (j == 0);
             if (j == 0) {
                 m_used = m_new;
             } else {
@@ -235,6 +263,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 if (__any_sync(0xffffffffu, need)) {
                     // O_i must be quiescent: PV_{j-1} complete (PV_j cannot start before our p_full arrive)
                     mbar_wait(o_done(i), (j - 1) & 1);
+                    o_waited = true;
                     tc_fence_after();
                     const float f = ex2_approx((m_used - m_new) * c);
                     l *= f;
@@ -251,6 +280,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     m_used = m_new;
                 }
             }
+            TR(3);
             // p = 2^(s*c - m*c): packed FFMA2 for the scale/shift, MUFU.EX2 for most pairs and the FMA-pipe polynomial for
             // kPolyPairs of every 8 pairs (the MUFU issues one warp-instruction per 8 clk and would otherwise pace the loop)
             const uint64_t c2 = pack_f32x2(c, c);
@@ -282,9 +312,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 unpack_f32x2(lsum2[1], b0, b1);
                 l += (a0 + a1) + (b0 + b1);
             }
+            TR(5);
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(p_full(i));
+            if (!o_waited) mbar_wait(o_done(i), (j - 1) & 1);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full(i));
+            TR(6);
         }
         // ===== epilogue: O / l -> bf16 -> global =====
         mbar_wait(o_done(i), (n_kv - 1) & 1);

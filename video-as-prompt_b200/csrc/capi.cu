@@ -11,6 +11,7 @@
 namespace vap {
 
 static thread_local char g_err[512] = "";
+static long long* g_attn_trace = nullptr;  // debug: device buffer for the attention kernel's clock64() trace
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -165,6 +166,7 @@ int vap_attention_fwd(const void* q, const void* k, const void* v, void* o, floa
     p.lse = lse;
     p.scale = scale;
     p.scale_log2 = scale * 1.4426950408889634f;
+    p.trace = g_attn_trace;
     const AttnTensor tq{static_cast<const __nv_bfloat16*>(q), q_sb, q_sh, q_sl};
     const AttnTensor tk{static_cast<const __nv_bfloat16*>(k), k_sb, k_sh, k_sl};
     const AttnTensor tv{static_cast<const __nv_bfloat16*>(v), v_sb, v_sh, v_sl};
@@ -198,6 +200,11 @@ int vap_ulysses_unpack(const void* src, void* dst, int64_t L, int nsplit, int64_
                        int64_t dst_row_stride, void* stream) {
     VAP_REQUIRE(src && dst, "vap_ulysses_unpack: null tensor");
     return launch_ulysses(src, dst, L, nsplit, chunk, dst_row_stride, src_row_stride, src_split_stride, 1, static_cast<cudaStream_t>(stream));
+}
+
+int vap_debug_set_attention_trace(void* device_buffer) {
+    g_attn_trace = static_cast<long long*>(device_buffer);
+    return 0;
 }
 
 int vap_probe_umma(const void* A, const void* B, float* Dout, int N, int K, int a_in_tmem, int b_mn_major, int lbo_b, int sbo_b,

@@ -47,6 +47,7 @@ struct AttnParams {
     float* lse;                // [B, H, Lq] or null
     float scale_log2;          // softmax scale * log2(e)
     float scale;
+    long long* trace;          // optional clock64() trace of CTA (0,0,0): [3 roles][64 iterations][8 stamps], or null
 };
 struct AttnTensor {
     const __nv_bfloat16* ptr;
