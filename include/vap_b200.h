@@ -97,7 +97,8 @@ int vap_ulysses_unpack(const void* src, void* dst, int64_t L, int nsplit, int64_
                        int64_t src_split_stride, int64_t dst_row_stride, void* stream);
 
 /* (6) Bring-up probe for the tcgen05 descriptors: one CTA computes D[128,N] = A[128,K] * B, fp32 out.
- *     a_in_tmem: 0 = A from shared memory (K-major, SWIZZLE_128B), 1 = A staged to TMEM as packed bf16.
+ *     a_in_tmem: bit 0: 0 = A from shared memory (K-major, SWIZZLE_128B), 1 = A staged to TMEM as packed bf16;
+ *                bit 1: stage A / read D back with the 16-lane TMEM shapes (tcgen05.st 16x128b, tcgen05.ld 16x256b).
  *     b_mn_major: 0 = B is [N,K] (K contiguous), 1 = B is [K,N] (N contiguous; the V operand of P*V).
  *     Descriptor fields are runtime arguments so alternative encodings can be swept from the test-suite. */
 int vap_probe_umma(const void* A, const void* B, float* Dout, int N, int K, int a_in_tmem, int b_mn_major, int lbo_b, int sbo_b,

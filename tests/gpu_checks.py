@@ -433,6 +433,8 @@ CHECKS = {
     "probe_mn_n64": lambda: check_probe(False, True, 64, 128),
     "probe_ts": lambda: check_probe(True, False, 128, 128),
     "probe_ts_mn": lambda: check_probe(True, True, 128, 128),
+    "probe_lane16_ld": lambda: check_probe(False, False, 128, 128, lane16_shapes=True),
+    "probe_lane16_st_ld": lambda: check_probe(True, True, 128, 128, lane16_shapes=True),
     "ln_wan": lambda: check_layernorm_wan(),
     "ln_wan_affine": lambda: check_layernorm_wan(rows=100, d=256, affine=True, modulate=False),
     "ln_wan_batch": lambda: check_layernorm_wan(rows=64, d=3072, batch=2),

@@ -7,21 +7,26 @@
 // output [tokens, 3, H, D] of BOTH streams (no torch.cat, no head-major transpose) and writes O token-major
 // [tokens, H*D], which is the A operand of the output projection.
 //
-// One CTA = one (batch, head, 256 query rows) work item = two 128-row Q tiles that ping-pong on the tensor
-// core (while the softmax warps of tile 0 work, the MMAs of tile 1 run).  12 warps:
+// One CTA = one (batch, head, 256 query rows) work item = two 128-row Q tiles that ping-pong: while the softmax
+// warps work on tile i, the tensor core runs PV / QK^T of tile 1-i.  20 warps:
 //   warp 0    : TMA producer — Q once, then K_j / V_j tiles into a ring of 128xD bf16 stages (SWIZZLE_128B)
 //   warp 1    : MMA issuer   — S_i = Q_i K_j^T (SS, both K-major), O_i += P_i V_j (A = P from TMEM, B = V MN-major)
 //   warp 2    : TMEM allocator (S0 | S1 | O0 | O1, fp32 columns; P_i is written as packed bf16 over S_i)
-//   warps 4-7 : softmax of Q tile 0 — one thread per query row: tcgen05.ld S row, online softmax in the
-//               exp2 domain, lazy rescale of the O row (only when the running max grew by > 2^8), P -> TMEM
-//   warps 8-11: softmax of Q tile 1
+//   warps 4-19: softmax — ALL 16 warps take the same Q tile and alternate between the two tiles.  Warp (q, ch) owns
+//               32 query rows (TMEM lane quarter q = warp % 4, one row per thread) x 32 kv columns (chunk ch):
+//               tcgen05.ld, partial row max -> shared-memory exchange inside the quarter, online softmax in the exp2
+//               domain, lazy rescale of its D/4 O columns (only when the running max grew by > 2^8), P -> TMEM.
+// Why 16 warps on one tile: the softmax of a 128x128 tile costs ~1000 clk of MUFU / FMA / ALU pipe time per SM
+// sub-partition (tools/softmax_pipe_probe.cu) against 1024 clk of MMA per tile; with warps dedicated to a tile the two
+// softmaxes ran concurrently at half speed each and the tensor pipe idled 42 % of the time (profiles/r01).
 // The last KV tile is masked against Lkv (TMA zero-fills out-of-range K/V rows).
 #include "vap_kernels.cuh"
 
 namespace vap {
 
 
-constexpr int kAttnThreads = 384;
+constexpr int kSoftmaxWarps = 16;  // four per TMEM lane quarter, one per 32-column chunk of the S tile
+constexpr int kAttnThreads = (4 + kSoftmaxWarps) * 32;
 constexpr int kBlockM = 128;  // rows per Q tile
 constexpr int kBlockN = 128;  // kv rows per tile
 constexpr float kRescaleThreshold = 8.0f;
@@ -35,8 +40,9 @@ struct AttnCfg {
     static constexpr int kTileBytes = 128 * D * 2;  // one Q / K / V tile
     static constexpr int kHalfBytes = 128 * 64 * 2;  // one 64-column (128-byte) swizzle slab
     static constexpr int kHalves = D / 64;
-    static constexpr int kKvStages = (D == 128) ? 5 : 8;
-    static constexpr int kSmemBytes = 2 * kTileBytes + kKvStages * kTileBytes + 1024 + 256;
+    static constexpr int kKvStages = (D == 128) ? 4 : 8;
+    static constexpr int kXchgBytes = 2 * 4 * 128 * 4;  // [Q tile][kv chunk][row] fp32: row-max / row-sum exchange between the warps of a lane quarter
+    static constexpr int kSmemBytes = 2 * kTileBytes + kKvStages * kTileBytes + kXchgBytes + 1024 + 256;
     static constexpr int kTmemCols = 512;
     static constexpr int kColS0 = 0, kColS1 = 128, kColO0 = 256, kColO1 = 256 + D;
 };
@@ -50,7 +56,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t q_smem = smem_base;
     const uint32_t kv_smem = smem_base + 2 * Cfg::kTileBytes;
-    const uint32_t bar_base = kv_smem + Cfg::kKvStages * Cfg::kTileBytes;
+    const uint32_t xchg_smem = kv_smem + Cfg::kKvStages * Cfg::kTileBytes;
+    const uint32_t bar_base = xchg_smem + Cfg::kXchgBytes;
     auto kv_full = [&](int s) { return bar_base + 8u * s; };
     auto kv_empty = [&](int s) { return bar_base + 8u * (Cfg::kKvStages + s); };
     const uint32_t q_full = bar_base + 8u * (2 * Cfg::kKvStages);
@@ -79,7 +86,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_init(q_full, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(s_full(i), 1);
-            mbar_init(p_full(i), 4);  // one arrive per softmax warp
+            mbar_init(p_full(i), kSoftmaxWarps);  // one arrive per softmax warp
             mbar_init(o_done(i), 1);
         }
         fence_mbar_init();
@@ -94,13 +101,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
 
-    // register re-balancing between the warpgroups: the producer/MMA/allocator warps need few registers, the
-    // one-thread-per-row softmax warps hold a whole 128-column S row (128 x 96 + 256 x 200 = 63488 <= 65536).
+    // 640 threads x 96 registers: a softmax thread holds 32 S values + 16 packed P words, so no setmaxnreg re-balancing.
     // The producer and MMA warps run their loops warp-wide (all lanes wait on the mbarriers, one elected lane issues):
     // control flow and descriptors stay warp-uniform, so ptxas keeps them in uniform registers instead of wrapping
     // every UTCHMMA / UTMALDG in an R2UR waterfall loop.
     if (warp < 4) {
-      setmaxnreg_dec<96>();
       if (warp == 0) {
             // ===== TMA producer =====
             if (elect_one()) {
@@ -199,7 +204,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     tc_fence_after();
                     TRM(2 + 2 * i);
                     issue_pv(i, kv_smem + v_stage * Cfg::kTileBytes, j > 0 ? 1u : 0u);
-                    commit(o_done(i));
+                    if (!has_next) commit(o_done(i));  // the final PV; earlier ones are covered by the next s_full commit
                     if (has_next) {
                         issue_qk(i, kv_smem + k_stage * Cfg::kTileBytes);
                         commit(s_full(i));
@@ -211,88 +216,86 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
       }
     } else {
-        setmaxnreg_inc<200>();
         // ===== softmax + epilogue warps =====
-        const int i = (warp - 4) >> 2;  // Q tile
-        const int q = warp & 3;         // TMEM lane quarter
+        // All 16 warps work on ONE Q tile at a time and alternate between the two tiles (unit u = (kv tile j, Q tile i)), so
+        // the softmax of tile i overlaps the MMAs of tile 1-i by construction.  Warp (q, ch): q = warp % 4 is the TMEM lane
+        // quarter the hardware lets it touch (32 query rows, one per thread), ch = kv column chunk [32 ch, 32 ch + 32).
+        // The row max needs all four chunks: the warps of a quarter exchange their partial maxima through shared memory
+        // behind a 128-thread named barrier (they sit on the same SM sub-partition).
+        const int sw = warp - 4;
+        const int q = warp & 3;
+        const int ch = sw >> 2;
+        const int row_in_tile = q * 32 + lane;
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-        const uint32_t s_col = tmem_base + lane_addr + (i == 0 ? Cfg::kColS0 : Cfg::kColS1);
-        const uint32_t o_col = tmem_base + lane_addr + (i == 0 ? Cfg::kColO0 : Cfg::kColO1);
-        const int row = q0 + i * kBlockM + q * 32 + lane;
+        const uint32_t s_col[2] = {tmem_base + lane_addr + Cfg::kColS0, tmem_base + lane_addr + Cfg::kColS1};
+        const uint32_t o_col[2] = {tmem_base + lane_addr + Cfg::kColO0, tmem_base + lane_addr + Cfg::kColO1};
+        constexpr int kOCols = D / 4;  // O columns this warp rescales / writes out
         const float c = p.scale_log2;
-        float m_used = -INFINITY;
-        float l = 0.f;
-        long long* tr = (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && q == 0 && lane == 0) ? p.trace + i * 512 : nullptr;
-#define TR(k) do { if (tr && j < 64) tr[j * 8 + (k)] = clock64(); } while (0)
+        const uint64_t c2 = pack_f32x2(c, c);
+        float m_used[2] = {-INFINITY, -INFINITY};  // the row maximum the accumulators of tile i are scaled by (lazily updated)
+        uint64_t l2[2] = {0ull, 0ull};              // packed partial row sums of this thread's 32 columns
+        long long* tr = (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && sw == 0 && lane == 0) ? p.trace : nullptr;
+#define TR(k) do { if (tr && j < 64) tr[i * 512 + j * 8 + (k)] = clock64(); } while (0)
         for (int j = 0; j < n_kv; ++j) {
-            TR(0);
-            mbar_wait(s_full(i), j & 1);
-            tc_fence_after();
-            TR(1);
-            uint32_t sr[4][32];
 #pragma unroll
-            for (int ch = 0; ch < 4; ++ch) tmem_ld_x32(s_col + 32 * ch, sr[ch]);
-            tmem_ld_wait();
-            TR(2);
-            const int valid = p.Lkv - j * kBlockN;  // >= 1
-            if (valid < kBlockN) {
-#pragma unroll
-                for (int ch = 0; ch < 4; ++ch)
+            for (int i = 0; i < 2; ++i) {
+                TR(0);
+                // s_full(i) phase j: QK_i(j) is complete, and with it PV_i(j-1) (issued earlier by the same thread), so O_i is
+                // quiescent until the p_full arrive below
+                mbar_wait(s_full(i), j & 1);
+                tc_fence_after();
+                TR(1);
+                uint32_t sr[32];
+                tmem_ld_x32(s_col[i] + 32 * ch, sr);
+                tmem_ld_wait();
+                TR(2);
+                const int valid = p.Lkv - j * kBlockN - 32 * ch;  // columns of this chunk inside the sequence (may be <= 0)
+                if (valid < 32) {
 #pragma unroll
                     for (int e = 0; e < 32; ++e)
-                        if (32 * ch + e >= valid) sr[ch][e] = __float_as_uint(-INFINITY);
-            }
-            // row max: four independent FMNMX3 chains (one per 32-column chunk)
-            float mx[4];
+                        if (e >= valid) sr[e] = __float_as_uint(-INFINITY);
+                }
+                float mx0 = fmax3(__uint_as_float(sr[0]), __uint_as_float(sr[1]), __uint_as_float(sr[2]));
+                float mx1 = fmax3(__uint_as_float(sr[3]), __uint_as_float(sr[4]), __uint_as_float(sr[5]));
 #pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-                mx[ch] = fmax3(__uint_as_float(sr[ch][0]), __uint_as_float(sr[ch][1]), __uint_as_float(sr[ch][2]));
-#pragma unroll
-                for (int e = 3; e < 31; e += 2) mx[ch] = fmax3(mx[ch], __uint_as_float(sr[ch][e]), __uint_as_float(sr[ch][e + 1]));
-                mx[ch] = fmaxf(mx[ch], __uint_as_float(sr[ch][31]));
-            }
-            const float m_t = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-            const float m_new = fmaxf(m_used, m_t);
-            // o_done(i) completes one phase per KV tile; mbarrier waits only carry a parity bit, so every phase is consumed
-            // exactly once, in order: phase j-1 either in the rescale branch or right before this tile's p_full arrive.
-            bool o_waited = (j == 0);
-            if (j == 0) {
-                m_used = m_new;
-            } else {
-                const bool need = (m_new - m_used) * c > kRescaleThreshold;
-                if (__any_sync(0xffffffffu, need)) {
-                    // O_i must be quiescent: PV_{j-1} complete (PV_j cannot start before our p_full arrive)
-                    mbar_wait(o_done(i), (j - 1) & 1);
-                    o_waited = true;
-                    tc_fence_after();
-                    const float f = ex2_approx((m_used - m_new) * c);
-                    l *= f;
-#pragma unroll 1
-                    for (int c0 = 0; c0 < D; c0 += 32) {
-                        uint32_t ov[32];
-                        tmem_ld_x32(o_col + c0, ov);
+                for (int e = 6; e < 30; e += 4) {
+                    mx0 = fmax3(mx0, __uint_as_float(sr[e]), __uint_as_float(sr[e + 1]));
+                    mx1 = fmax3(mx1, __uint_as_float(sr[e + 2]), __uint_as_float(sr[e + 3]));
+                }
+                const float m_loc = fmaxf(fmax3(mx0, __uint_as_float(sr[30]), __uint_as_float(sr[31])), mx1);
+                const uint32_t xaddr = xchg_smem + static_cast<uint32_t>(i * 512 + row_in_tile) * 4u;
+                st_shared_f32(xaddr + ch * 512u, m_loc);
+                named_bar_sync(1 + q, 128);  // also orders every S load of the quarter before any P store below
+                const float m_t = fmaxf(fmaxf(ld_shared_f32(xaddr), ld_shared_f32(xaddr + 512u)), fmaxf(ld_shared_f32(xaddr + 1024u), ld_shared_f32(xaddr + 1536u)));
+                const float m_new = fmaxf(m_used[i], m_t);
+                if (j == 0) {
+                    m_used[i] = m_new;
+                } else {
+                    const bool need = (m_new - m_used[i]) * c > kRescaleThreshold;
+                    if (__any_sync(0xffffffffu, need)) {  // identical in the four warps of the quarter (same rows, same maxima)
+                        const float f = ex2_approx((m_used[i] - m_new) * c);
+                        l2[i] = mul_f32x2(l2[i], pack_f32x2(f, f));
+                        uint32_t ov[kOCols];
+                        if constexpr (kOCols == 32) tmem_ld_x32(o_col[i] + kOCols * ch, ov);
+                        else tmem_ld_x16(o_col[i] + kOCols * ch, ov);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * f);
-                        tmem_st_x32(o_col + c0, ov);
+                        for (int e = 0; e < kOCols; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * f);
+                        if constexpr (kOCols == 32) tmem_st_x32(o_col[i] + kOCols * ch, ov);
+                        else tmem_st_x16(o_col[i] + kOCols * ch, ov);
+                        m_used[i] = m_new;
                     }
-                    tmem_st_wait();
-                    m_used = m_new;
                 }
-            }
-            TR(3);
-            // p = 2^(s*c - m*c): packed FFMA2 for the scale/shift, MUFU.EX2 for most pairs and the FMA-pipe polynomial for
-            // kPolyPairs of every 8 pairs (the MUFU issues one warp-instruction per 8 clk and would otherwise pace the loop)
-            const uint64_t c2 = pack_f32x2(c, c);
-            const float nmc = -m_used * c;
-            const uint64_t nmc2 = pack_f32x2(nmc, nmc);
-            uint64_t lsum2[2] = {0ull, 0ull};
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
+                TR(3);
+                // p = 2^(s*c - m*c): packed FFMA2 for the scale/shift, MUFU.EX2 for most pairs and the FMA-pipe polynomial for
+                // kPolyPairs of every 8 pairs (the MUFU retires one warp-instruction per 8 clk and would otherwise pace the loop)
+                const float nmc = -m_used[i] * c;
+                const uint64_t nmc2 = pack_f32x2(nmc, nmc);
                 uint32_t pk[16];
+                uint64_t ls[2] = {0ull, 0ull};
 #pragma unroll
                 for (int e = 0; e < 16; ++e) {
-                    const uint64_t x2 = fma_f32x2(pack_f32x2(__uint_as_float(sr[ch][2 * e]), __uint_as_float(sr[ch][2 * e + 1])), c2, nmc2);
+                    const uint64_t x2 = fma_f32x2(pack_f32x2(__uint_as_float(sr[2 * e]), __uint_as_float(sr[2 * e + 1])), c2, nmc2);
                     float x0, x1, p0, p1;
                     unpack_f32x2(x2, x0, x1);
                     if ((e & 7) < kPolyPairs) {
@@ -301,50 +304,51 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                         p0 = ex2_approx(x0);
                         p1 = ex2_approx(x1);
                     }
-                    lsum2[e & 1] = add_f32x2(lsum2[e & 1], pack_f32x2(p0, p1));
+                    ls[e & 1] = add_f32x2(ls[e & 1], pack_f32x2(p0, p1));
                     pk[e] = pack_bf16x2(p0, p1);
                 }
-                tmem_st_x16(s_col + 16 * ch, pk);
+                l2[i] = add_f32x2(l2[i], add_f32x2(ls[0], ls[1]));
+                tmem_st_x16(s_col[i] + 16 * ch, pk);
+                TR(5);
+                tmem_st_wait();  // covers the rescaled O columns too
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(p_full(i));
+                TR(6);
             }
-            {
-                float a0, a1, b0, b1;
-                unpack_f32x2(lsum2[0], a0, a1);
-                unpack_f32x2(lsum2[1], b0, b1);
-                l += (a0 + a1) + (b0 + b1);
-            }
-            TR(5);
-            tmem_st_wait();
-            tc_fence_before();
-            if (!o_waited) mbar_wait(o_done(i), (j - 1) & 1);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(p_full(i));
-            TR(6);
         }
-        // ===== epilogue: O / l -> bf16 -> global =====
-        mbar_wait(o_done(i), (n_kv - 1) & 1);
-        tc_fence_after();
-        const float inv_l = 1.f / l;
-        const bool row_ok = row < p.Lq;
-        __nv_bfloat16* orow = p.o + batch * p.o_sb + head * p.o_sh + static_cast<int64_t>(row) * p.o_sl;
-#pragma unroll 1
-        for (int c0 = 0; c0 < D; c0 += 32) {
-            uint32_t ov[32];
-            tmem_ld_x32(o_col + c0, ov);
-            tmem_ld_wait();
-            if (row_ok) {
+        // ===== epilogue: O / l -> bf16 -> global; warp (q, ch) writes columns [ch D/4, (ch+1) D/4) of its 32 rows =====
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
+        for (int i = 0; i < 2; ++i) {
+            float lo, hi;
+            unpack_f32x2(l2[i], lo, hi);
+            const uint32_t xaddr = xchg_smem + static_cast<uint32_t>(i * 512 + row_in_tile) * 4u;
+            named_bar_sync(1 + q, 128);  // the last row-max exchange of this slot has been read by everyone
+            st_shared_f32(xaddr + ch * 512u, lo + hi);
+            named_bar_sync(1 + q, 128);
+            const float l = (ld_shared_f32(xaddr) + ld_shared_f32(xaddr + 512u)) + (ld_shared_f32(xaddr + 1024u) + ld_shared_f32(xaddr + 1536u));
+            mbar_wait(o_done(i), 0);
+            tc_fence_after();
+            const float inv_l = 1.f / l;
+            const int row = q0 + i * kBlockM + row_in_tile;
+            uint32_t ov[kOCols];
+            if constexpr (kOCols == 32) tmem_ld_x32(o_col[i] + kOCols * ch, ov);
+            else tmem_ld_x16(o_col[i] + kOCols * ch, ov);
+            tmem_ld_wait();
+            if (row < p.Lq) {
+                __nv_bfloat16* orow = p.o + batch * p.o_sb + head * p.o_sh + static_cast<int64_t>(row) * p.o_sl + kOCols * ch;
+#pragma unroll
+                for (int g = 0; g < kOCols / 8; ++g) {
                     uint4 o;
                     o.x = pack_bf16x2(__uint_as_float(ov[8 * g + 0]) * inv_l, __uint_as_float(ov[8 * g + 1]) * inv_l);
                     o.y = pack_bf16x2(__uint_as_float(ov[8 * g + 2]) * inv_l, __uint_as_float(ov[8 * g + 3]) * inv_l);
                     o.z = pack_bf16x2(__uint_as_float(ov[8 * g + 4]) * inv_l, __uint_as_float(ov[8 * g + 5]) * inv_l);
                     o.w = pack_bf16x2(__uint_as_float(ov[8 * g + 6]) * inv_l, __uint_as_float(ov[8 * g + 7]) * inv_l);
-                    *reinterpret_cast<uint4*>(orow + c0 + 8 * g) = o;
+                    *reinterpret_cast<uint4*>(orow + 8 * g) = o;
                 }
+                if (p.lse && ch == 0) p.lse[(static_cast<int64_t>(batch) * p.H + head) * p.Lq + row] = m_used[i] * p.scale + logf(l);
             }
         }
-        if (p.lse && row_ok)
-            p.lse[(static_cast<int64_t>(batch) * p.H + head) * p.Lq + row] = m_used * p.scale + logf(l);
     }
 
     tc_fence_before();

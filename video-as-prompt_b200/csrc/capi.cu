@@ -214,7 +214,8 @@ int vap_probe_umma(const void* A, const void* B, float* Dout, int N, int K, int 
     p.A = static_cast<const __nv_bfloat16*>(A);
     p.Dout = Dout;
     p.N = N, p.K = K;
-    p.a_in_tmem = a_in_tmem, p.b_mn_major = b_mn_major;
+    p.a_in_tmem = a_in_tmem & 1, p.b_mn_major = b_mn_major;
+    p.lane16_shapes = (a_in_tmem >> 1) & 1;
     // defaults = the encodings gemm_sm100.cu / attn_sm100.cu use
     p.lbo_b = lbo_b >= 0 ? lbo_b : (b_mn_major ? K * 128 : 0);
     p.sbo_b = sbo_b >= 0 ? sbo_b : 1024;

@@ -49,7 +49,22 @@ probe_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
     }
     const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
-    if (p.a_in_tmem) {
+    if (p.a_in_tmem && p.lane16_shapes) {
+        // 16-lane shapes: per half hf the warp writes lanes 32*warp + 16*hf + {t/4, t/4+8}, packed column 4g + t%4 (K = 128)
+        for (int hf = 0; hf < 2; ++hf) {
+            const int r0 = warp * 32 + 16 * hf + (lane >> 2);
+            const uint32_t* a0 = reinterpret_cast<const uint32_t*>(p.A + static_cast<int64_t>(r0) * p.K);
+            const uint32_t* a1 = reinterpret_cast<const uint32_t*>(p.A + static_cast<int64_t>(r0 + 8) * p.K);
+            uint32_t v[32];
+#pragma unroll
+            for (int g = 0; g < 16; ++g) {
+                v[2 * g] = a0[4 * g + (lane & 3)];
+                v[2 * g + 1] = a1[4 * g + (lane & 3)];
+            }
+            tmem_st_16x128b_x16(tmem_base + (static_cast<uint32_t>(warp * 32 + 16 * hf) << 16) + 256, v);
+        }
+        tmem_st_wait();
+    } else if (p.a_in_tmem) {
         // thread t owns row t: pack (A[t,2c], A[t,2c+1]) into TMEM column 256 + c
         const uint32_t* arow = reinterpret_cast<const uint32_t*>(p.A + static_cast<int64_t>(threadIdx.x) * p.K);
         for (int c0 = 0; c0 < p.K / 2; c0 += 16) {
@@ -84,13 +99,30 @@ probe_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     mbar_wait(mma_bar, 0);
     tc_fence_after();
-    const int row = warp * 32 + lane;
-    for (int c0 = 0; c0 < p.N; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld_x16(tmem_base + lane_addr + c0, v);
-        tmem_ld_wait();
+    if (p.lane16_shapes) {
+        // read D back with 16x256b: r[4g+0..1] = (lane t/4, cols 8g + 2(t%4) + {0,1}), r[4g+2..3] = lane t/4 + 8
+        for (int hf = 0; hf < 2; ++hf) {
+            const int r0 = warp * 32 + 16 * hf + (lane >> 2);
+            for (int c0 = 0; c0 < p.N; c0 += 32) {
+                uint32_t v[16];
+                tmem_ld_16x256b_x4(tmem_base + (static_cast<uint32_t>(warp * 32 + 16 * hf) << 16) + c0, v);
+                tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 16; ++e) p.Dout[static_cast<int64_t>(row) * p.N + c0 + e] = __uint_as_float(v[e]);
+                for (int g = 0; g < 4; ++g)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        p.Dout[static_cast<int64_t>(r0 + (e >> 1) * 8) * p.N + c0 + 8 * g + 2 * (lane & 3) + (e & 1)] = __uint_as_float(v[4 * g + e]);
+            }
+        }
+    } else {
+        const int row = warp * 32 + lane;
+        for (int c0 = 0; c0 < p.N; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld_x16(tmem_base + lane_addr + c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) p.Dout[static_cast<int64_t>(row) * p.N + c0 + e] = __uint_as_float(v[e]);
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -104,6 +136,7 @@ int launch_probe_umma(const __nv_bfloat16* A, const __nv_bfloat16* B, ProbeParam
     VAP_REQUIRE(p.K == 64 || p.K == 128, "probe: K must be 64 or 128");
     VAP_REQUIRE(p.N % 64 == 0 && p.N >= 64 && p.N <= 256, "probe: N must be 64, 128, 192 or 256");
     VAP_REQUIRE(!p.b_mn_major || p.N <= 128, "probe: MN-major B supports N <= 128");
+    VAP_REQUIRE(!p.lane16_shapes || (p.K == 128 && p.N % 32 == 0), "probe: the 16-lane TMEM shapes need K = 128");
     CUtensorMap tmA, tmB;
     {
         const uint64_t dims[2] = {static_cast<uint64_t>(p.K), 128};

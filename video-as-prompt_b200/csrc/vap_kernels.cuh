@@ -75,6 +75,7 @@ struct ProbeParams {
     float* Dout;             // [128, N]
     int N, K;
     int a_in_tmem, b_mn_major;
+    int lane16_shapes;  // stage A / read D back with the 16-lane TMEM shapes (16x128b st, 16x256b ld) the attention softmax uses
     uint32_t lbo_b, sbo_b, kstep_b, layout_type;
 };
 int launch_probe_umma(const __nv_bfloat16* A, const __nv_bfloat16* B, ProbeParams p, cudaStream_t stream);

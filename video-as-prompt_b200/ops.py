@@ -241,7 +241,7 @@ def ulysses_unpack(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> tor
 
 
 def probe_umma(a: torch.Tensor, b: torch.Tensor, *, a_in_tmem: bool, b_mn_major: bool, lbo_b: int = -1, sbo_b: int = -1,
-               kstep_b: int = -1, layout_type: int = -1) -> torch.Tensor:
+               kstep_b: int = -1, layout_type: int = -1, lane16_shapes: bool = False) -> torch.Tensor:
     """Bring-up probe (vap_probe_umma): D[128,N] fp32 = A[128,K] @ (B[N,K].T if not b_mn_major else B[K,N])."""
     _need_cuda_bf16(a, "a"), _need_cuda_bf16(b, "b")
     K = a.shape[1]
@@ -249,7 +249,7 @@ def probe_umma(a: torch.Tensor, b: torch.Tensor, *, a_in_tmem: bool, b_mn_major:
     if a.shape != (128, K) or not a.is_contiguous() or not b.is_contiguous():
         raise ValueError("probe_umma: a must be contiguous [128, K], b contiguous")
     d = torch.empty((128, N), dtype=torch.float32, device=a.device)
-    rc = _lib.load().vap_probe_umma(a.data_ptr(), b.data_ptr(), d.data_ptr(), N, K, int(a_in_tmem), int(b_mn_major), lbo_b, sbo_b, kstep_b,
+    rc = _lib.load().vap_probe_umma(a.data_ptr(), b.data_ptr(), d.data_ptr(), N, K, int(a_in_tmem) | (int(lane16_shapes) << 1), int(b_mn_major), lbo_b, sbo_b, kstep_b,
                                     layout_type, _stream())
     _lib.check(rc, "vap_probe_umma")
     return d
