@@ -7,64 +7,81 @@
 // output [tokens, 3, H, D] of BOTH streams (no torch.cat, no head-major transpose) and writes O token-major
 // [tokens, H*D], which is the A operand of the output projection.
 //
-// One CTA = one (batch, head, 256 query rows) work item = two 128-row Q tiles that ping-pong: while the softmax
-// warps work on tile i, the tensor core runs PV / QK^T of tile 1-i.  20 warps:
-//   warp 0    : TMA producer — Q once, then K_j / V_j tiles into a ring of 128xD bf16 stages (SWIZZLE_128B)
-//   warp 1    : MMA issuer   — S_i = Q_i K_j^T (SS, both K-major), O_i += P_i V_j (A = P from TMEM, B = V MN-major)
-//   warp 2    : TMEM allocator (S0 | S1 | O0 | O1, fp32 columns; P_i is written as packed bf16 over S_i)
-//   warps 4-19: softmax — ALL 16 warps take the same Q tile and alternate between the two tiles.  Warp (q, ch) owns
-//               32 query rows (TMEM lane quarter q = warp % 4, one row per thread) x 32 kv columns (chunk ch):
-//               tcgen05.ld, partial row max -> shared-memory exchange inside the quarter, online softmax in the exp2
-//               domain, lazy rescale of its D/4 O columns (only when the running max grew by > 2^8), P -> TMEM.
-// Why 16 warps on one tile: the softmax of a 128x128 tile costs ~1000 clk of MUFU / FMA / ALU pipe time per SM
-// sub-partition (tools/softmax_pipe_probe.cu) against 1024 clk of MMA per tile; with warps dedicated to a tile the two
-// softmaxes ran concurrently at half speed each and the tensor pipe idled 42 % of the time (profiles/r01).
+// One CTA = one (batch, head, 256 query rows) work item = two 128-row Q tiles that ping-pong on the tensor core: while
+// the softmax warps of tile i work, the MMAs of tile 1-i run.  18 warps:
+//   warp 0     : TMEM allocator, then TMA producer — Q once, then K_j / V_j tiles into a ring of 128xD bf16 stages (SWIZZLE_128B)
+//   warp 1     : MMA issuer   — S_i = Q_i K_j^T (SS, both K-major, N = 128), O_i += P_i V_j (A = P from TMEM, B = V MN-major)
+//   TMEM       : S0 | S1 | O0 | O1, fp32 columns; P_i is written as packed bf16 over columns [0, 64) of S_i
+//   warps 2-9  : softmax of Q tile 0;  warps 10-17: softmax of Q tile 1.
+// Measured floors that shape this (tools/mma_rate_probe.cu, tools/softmax_pipe_probe.cu): an M128 N<=128 K16 MMA costs
+// ~71 clk whatever N is (so N = 128 tiles; a double-buffered N = 64 variant ran at half the tensor rate), and ONE softmax
+// warp per SM sub-partition issues at IPC ~0.35, two at ~0.5, four at ~0.6 — a tile handled by four warps (one thread per
+// row) takes longer than the MMAs it overlaps with.  So each tile's softmax runs on EIGHT warps, two per sub-partition, using the 16-lane TMEM
+// shapes: warp (q, hl) owns TMEM lanes 32 q + 16 hl .. +15 (tcgen05.ld.16x256b — the mma.sync accumulator layout, a row
+// lives in one quad; tcgen05.st.16x128b writes the packed P in the layout the MMA reads).  No cross-warp exchange exists:
+//   * the common step has NO max reduction: p = 2^(s c - m_used c) is computed speculatively against the running reference
+//     m_used, and the warp votes afterwards on whether a score sat more than 2^8 above it (a thread's partial row sum
+//     exceeds 2^8; ex2.approx overflows cleanly to +inf).  Only when the vote fires (first half-tile, or a new maximum
+//     far above the reference) the quad reduces the row maxima by shuffle, the warp rescales its 16 rows of O (lazy
+//     rescale) and repeats the pass;
+//   * P is published in two 64-column halves (p_full(i, 0/1)), so the first four PV MMAs of a step overlap the second
+//     half of the softmax.
 // The last KV tile is masked against Lkv (TMA zero-fills out-of-range K/V rows).
 #include "vap_kernels.cuh"
 
 namespace vap {
 
-
-constexpr int kSoftmaxWarps = 16;  // four per TMEM lane quarter, one per 32-column chunk of the S tile
-constexpr int kAttnThreads = (4 + kSoftmaxWarps) * 32;
+constexpr int kSoftmaxWarps = 16;  // eight per Q tile
+constexpr int kFirstSoftmaxWarp = 2;
+constexpr int kAttnThreads = (kFirstSoftmaxWarp + kSoftmaxWarps) * 32;
 constexpr int kBlockM = 128;  // rows per Q tile
 constexpr int kBlockN = 128;  // kv rows per tile
 constexpr float kRescaleThreshold = 8.0f;
-#ifndef VAP_ATTN_POLY_PAIRS
-#define VAP_ATTN_POLY_PAIRS 3
+constexpr float kSumTrigger = 256.0f;  // 2^kRescaleThreshold
+// Of every 8 (p0,p1) pairs, how many take the FMA-pipe polynomial exp2 instead of MUFU.EX2.  Measured (tools/attn_variants.sh):
+// at D = 128 the loop is issue-bound and every polynomial pair costs TFLOP/s; at D = 64 (half the MMA work per score) the
+// MUFU is the bound and 1 of 8 is best.
+#ifndef VAP_ATTN_POLY_PAIRS_D128
+#define VAP_ATTN_POLY_PAIRS_D128 0
 #endif
-constexpr int kPolyPairs = VAP_ATTN_POLY_PAIRS;  // of every 8 (p0,p1) pairs, how many take the software exp2
+#ifndef VAP_ATTN_POLY_PAIRS_D64
+#define VAP_ATTN_POLY_PAIRS_D64 1
+#endif
+#ifndef VAP_ATTN_TRACE
+#define VAP_ATTN_TRACE 0  // 1: clock64() stamps of CTA (0,0,0) when a trace buffer is installed (tools/attn_trace.py)
+#endif
 
 template <int D>
 struct AttnCfg {
-    static constexpr int kTileBytes = 128 * D * 2;  // one Q / K / V tile
+    static constexpr int kTileBytes = 128 * D * 2;   // one Q / K / V tile
     static constexpr int kHalfBytes = 128 * 64 * 2;  // one 64-column (128-byte) swizzle slab
     static constexpr int kHalves = D / 64;
-    static constexpr int kKvStages = (D == 128) ? 4 : 8;
-    static constexpr int kXchgBytes = 2 * 4 * 128 * 4;  // [Q tile][kv chunk][row] fp32: row-max / row-sum exchange between the warps of a lane quarter
-    static constexpr int kSmemBytes = 2 * kTileBytes + kKvStages * kTileBytes + kXchgBytes + 1024 + 256;
+    static constexpr int kKvStages = (D == 128) ? 5 : 8;
+    static constexpr int kBarBytes = 512;
+    static constexpr int kSmemBytes = 2 * kTileBytes + kKvStages * kTileBytes + kBarBytes + 1024;
     static constexpr int kTmemCols = 512;
     static constexpr int kColS0 = 0, kColS1 = 128, kColO0 = 256, kColO1 = 256 + D;
 };
 
 template <int D>
-__global__ void __launch_bounds__(kAttnThreads, 1)
+__global__ void __launch_bounds__(kAttnThreads, 1)  // registers are granted per 4 warps: 18 warps cost 20 -> 96 per thread
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
     using Cfg = AttnCfg<D>;
+    constexpr int kPolyPairs = (D == 128) ? VAP_ATTN_POLY_PAIRS_D128 : VAP_ATTN_POLY_PAIRS_D64;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t q_smem = smem_base;
     const uint32_t kv_smem = smem_base + 2 * Cfg::kTileBytes;
-    const uint32_t xchg_smem = kv_smem + Cfg::kKvStages * Cfg::kTileBytes;
-    const uint32_t bar_base = xchg_smem + Cfg::kXchgBytes;
+    const uint32_t bar_base = kv_smem + Cfg::kKvStages * Cfg::kTileBytes;
     auto kv_full = [&](int s) { return bar_base + 8u * s; };
     auto kv_empty = [&](int s) { return bar_base + 8u * (Cfg::kKvStages + s); };
     const uint32_t q_full = bar_base + 8u * (2 * Cfg::kKvStages);
-    auto s_full = [&](int i) { return bar_base + 8u * (2 * Cfg::kKvStages + 1 + i); };
-    auto p_full = [&](int i) { return bar_base + 8u * (2 * Cfg::kKvStages + 3 + i); };
-    auto o_done = [&](int i) { return bar_base + 8u * (2 * Cfg::kKvStages + 5 + i); };
-    const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * Cfg::kKvStages + 7);
+    auto s_full = [&](int i) { return bar_base + 8u * (2 * Cfg::kKvStages + 1 + i); };            // S_i(j) in TMEM (and PV_i(j-1) done)
+    auto p_full = [&](int i, int c) { return bar_base + 8u * (2 * Cfg::kKvStages + 3 + 2 * i + c); };  // half c of P_i(j) in TMEM
+    auto pv_half = [&](int i) { return bar_base + 8u * (2 * Cfg::kKvStages + 7 + i); };           // the PV MMAs of half 0 have completed
+    auto o_done = [&](int i) { return bar_base + 8u * (2 * Cfg::kKvStages + 9 + i); };
+    const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * Cfg::kKvStages + 11);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -86,12 +103,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_init(q_full, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(s_full(i), 1);
-            mbar_init(p_full(i), kSoftmaxWarps);  // one arrive per softmax warp
+            mbar_init(p_full(i, 0), kSoftmaxWarps / 2);  // one arrive per softmax warp of the tile
+            mbar_init(p_full(i, 1), kSoftmaxWarps / 2);
+            mbar_init(pv_half(i), 1);
             mbar_init(o_done(i), 1);
         }
         fence_mbar_init();
     }
-    if (warp == 2) {
+    if (warp == 0) {
         tmem_alloc(tmem_ptr_addr, Cfg::kTmemCols);
         tmem_relinquish();
     }
@@ -101,12 +120,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
 
-    // 640 threads x 96 registers: a softmax thread holds 32 S values + 16 packed P words, so no setmaxnreg re-balancing.
     // The producer and MMA warps run their loops warp-wide (all lanes wait on the mbarriers, one elected lane issues):
     // control flow and descriptors stay warp-uniform, so ptxas keeps them in uniform registers instead of wrapping
     // every UTCHMMA / UTMALDG in an R2UR waterfall loop.
-    if (warp < 4) {
-      if (warp == 0) {
+    if (warp < kFirstSoftmaxWarp) {
+        if (warp == 0) {
             // ===== TMA producer =====
             if (elect_one()) {
                 mbar_arrive_expect_tx(q_full, 2 * Cfg::kTileBytes);
@@ -114,6 +132,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     for (int h = 0; h < Cfg::kHalves; ++h)
                         tma_load_4d(q_smem + t * Cfg::kTileBytes + h * Cfg::kHalfBytes, &tmQ, q_full, h * 64, q0 + t * kBlockM, head, batch);
             }
+            __syncwarp();
             int stage = 0;
             uint32_t phase = 0;
             for (int j = 0; j < n_kv; ++j) {
@@ -132,7 +151,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     }
                 }
             }
-      } else if (warp == 1) {
+        } else if (warp == 1) {
             // ===== MMA issuer =====
             constexpr uint32_t idesc_qk = make_idesc_bf16(kBlockM, kBlockN, 0, 0);  // S = Q K^T : A, B K-major
             constexpr uint32_t idesc_pv = make_idesc_bf16(kBlockM, D, 0, 1);        // O = P V   : A (TMEM) K-major, B MN-major
@@ -151,14 +170,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 }
                 __syncwarp();
             };
-            auto issue_pv = [&](int i, uint32_t v_addr, uint32_t accumulate) {
+            auto issue_pv_half = [&](int i, int c, uint32_t v_addr, uint32_t accumulate) {
                 if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < kBlockN / 16; ++k) {
+                    for (int kk = 0; kk < kBlockN / 32; ++kk) {
+                        const int k = 4 * c + kk;
                         // A: P_i, packed bf16 pairs, 8 TMEM columns per 16 kv;  B: V rows [16k, 16k+16) (2048 B apart),
                         // MN-major: 64-column slabs kHalfBytes apart (LBO), 8-row groups 1024 B apart (SBO)
-                        umma_ts(col_o[i], col_s[i] + 8 * k, make_smem_desc(v_addr + k * 2048, Cfg::kHalfBytes, 1024, kLayoutSw128),
-                                idesc_pv, k != 0 ? 1u : accumulate);
+                        umma_ts(col_o[i], col_s[i] + 8 * k, make_smem_desc(v_addr + k * 2048, Cfg::kHalfBytes, 1024, kLayoutSw128), idesc_pv,
+                                k != 0 ? 1u : accumulate);
                     }
                 }
                 __syncwarp();
@@ -186,8 +206,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             commit(kv_empty(stage));
             advance();
             long long* trm = (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) ? p.trace + 1024 : nullptr;
+#if VAP_ATTN_TRACE
 #define TRM(k) do { if (trm && j < 64) trm[j * 8 + (k)] = clock64(); } while (0)
+#else
+#define TRM(k) do { } while (0)
+#endif
             for (int j = 0; j < n_kv; ++j) {
+                const uint32_t par = j & 1;
                 const int v_stage = stage;
                 TRM(0);
                 mbar_wait(kv_full(stage), phase);  // V_j
@@ -199,161 +224,212 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     advance();
                 }
                 TRM(1);
+#pragma unroll
                 for (int i = 0; i < 2; ++i) {
-                    mbar_wait(p_full(i), j & 1);
+                    mbar_wait(p_full(i, 0), par);
                     tc_fence_after();
                     TRM(2 + 2 * i);
-                    issue_pv(i, kv_smem + v_stage * Cfg::kTileBytes, j > 0 ? 1u : 0u);
-                    if (!has_next) commit(o_done(i));  // the final PV; earlier ones are covered by the next s_full commit
+                    issue_pv_half(i, 0, kv_smem + v_stage * Cfg::kTileBytes, j > 0 ? 1u : 0u);
+                    commit(pv_half(i));
+                    mbar_wait(p_full(i, 1), par);
+                    tc_fence_after();
+                    issue_pv_half(i, 1, kv_smem + v_stage * Cfg::kTileBytes, 1u);
                     if (has_next) {
                         issue_qk(i, kv_smem + k_stage * Cfg::kTileBytes);
-                        commit(s_full(i));
+                        commit(s_full(i));  // also covers PV_i(j): O_i is quiescent when the softmax sees S_i(j+1)
+                    } else {
+                        commit(o_done(i));
                     }
                     TRM(3 + 2 * i);
                 }
                 commit(kv_empty(v_stage));
                 if (has_next) commit(kv_empty(k_stage));
             }
-      }
+        }
     } else {
         // ===== softmax + epilogue warps =====
-        // All 16 warps work on ONE Q tile at a time and alternate between the two tiles (unit u = (kv tile j, Q tile i)), so
-        // the softmax of tile i overlaps the MMAs of tile 1-i by construction.  Warp (q, ch): q = warp % 4 is the TMEM lane
-        // quarter the hardware lets it touch (32 query rows, one per thread), ch = kv column chunk [32 ch, 32 ch + 32).
-        // The row max needs all four chunks: the warps of a quarter exchange their partial maxima through shared memory
-        // behind a 128-thread named barrier (they sit on the same SM sub-partition).
-        const int sw = warp - 4;
-        const int q = warp & 3;
-        const int ch = sw >> 2;
-        const int row_in_tile = q * 32 + lane;
-        const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-        const uint32_t s_col[2] = {tmem_base + lane_addr + Cfg::kColS0, tmem_base + lane_addr + Cfg::kColS1};
-        const uint32_t o_col[2] = {tmem_base + lane_addr + Cfg::kColO0, tmem_base + lane_addr + Cfg::kColO1};
-        constexpr int kOCols = D / 4;  // O columns this warp rescales / writes out
+        const int sw = warp - kFirstSoftmaxWarp;
+        const int i = sw >> 3;         // Q tile
+        const int q = warp & 3;        // TMEM lane quarter this warp may touch
+        const int hl = (sw >> 2) & 1;  // which 16 lanes of the quarter
+        const int cp = lane & 3;       // column phase inside a quad
+        const int row0_in_tile = q * 32 + hl * 16 + (lane >> 2);  // this thread's rows: row0 and row0 + 8
+        const uint32_t lane_addr = static_cast<uint32_t>(q * 32 + hl * 16) << 16;
+        const uint32_t s_col = tmem_base + lane_addr + (i == 0 ? Cfg::kColS0 : Cfg::kColS1);
+        const uint32_t o_col = tmem_base + lane_addr + (i == 0 ? Cfg::kColO0 : Cfg::kColO1);
         const float c = p.scale_log2;
         const uint64_t c2 = pack_f32x2(c, c);
-        float m_used[2] = {-INFINITY, -INFINITY};  // the row maximum the accumulators of tile i are scaled by (lazily updated)
-        uint64_t l2[2] = {0ull, 0ull};              // packed partial row sums of this thread's 32 columns
-        long long* tr = (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && sw == 0 && lane == 0) ? p.trace : nullptr;
-#define TR(k) do { if (tr && j < 64) tr[i * 512 + j * 8 + (k)] = clock64(); } while (0)
+        const float thr_off = kRescaleThreshold / c;
+        float m_used[2] = {-INFINITY, -INFINITY};  // the reference the accumulators of row r are scaled by (lazily updated)
+        float thr[2] = {-INFINITY, -INFINITY};     // m_used + 8 / c : a score above it forces a reference update
+        uint64_t nmc2[2] = {0ull, 0ull};           // packed (-m_used c, -m_used c)
+        uint64_t l2[2] = {0ull, 0ull};             // packed partial row sums of this thread's columns
+        long long* tr = (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && q == 0 && hl == 0 && lane == 0) ? p.trace + i * 512 : nullptr;
+#if VAP_ATTN_TRACE
+#define TR(k) do { if (tr && j < 64) tr[j * 8 + (k)] = clock64(); } while (0)
+#else
+#define TR(k) do { } while (0)
+#endif
         for (int j = 0; j < n_kv; ++j) {
+            TR(0);
+            // s_full(i) phase j: QK_i(j) is complete, and with it PV_i(j-1) (issued earlier by the same thread), so O_i is
+            // quiescent until the first p_full arrive below
+            mbar_wait(s_full(i), j & 1);
+            tc_fence_after();
+            TR(1);
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                TR(0);
-                // s_full(i) phase j: QK_i(j) is complete, and with it PV_i(j-1) (issued earlier by the same thread), so O_i is
-                // quiescent until the p_full arrive below
-                mbar_wait(s_full(i), j & 1);
-                tc_fence_after();
-                TR(1);
-                uint32_t sr[32];
-                tmem_ld_x32(s_col[i] + 32 * ch, sr);
+            for (int ch = 0; ch < 2; ++ch) {
+                uint32_t sr[32];  // sr[4g + e]: columns 64 ch + 8 g + 2 cp + (e & 1) of row0 (e < 2) / row0 + 8 (e >= 2)
+                tmem_ld_16x256b_x8(s_col + 64 * ch, sr);
                 tmem_ld_wait();
-                TR(2);
-                const int valid = p.Lkv - j * kBlockN - 32 * ch;  // columns of this chunk inside the sequence (may be <= 0)
-                if (valid < 32) {
+                if (ch == 0) TR(2);
+                const int valid = p.Lkv - j * kBlockN - 64 * ch - 2 * cp;  // this thread's column 8 g + e is inside the sequence iff 8 g + e < valid
+                if (valid < 58) {
 #pragma unroll
-                    for (int e = 0; e < 32; ++e)
-                        if (e >= valid) sr[e] = __float_as_uint(-INFINITY);
+                    for (int g = 0; g < 8; ++g)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (8 * g + (e & 1) >= valid) sr[4 * g + e] = __float_as_uint(-INFINITY);
                 }
-                float mx0 = fmax3(__uint_as_float(sr[0]), __uint_as_float(sr[1]), __uint_as_float(sr[2]));
-                float mx1 = fmax3(__uint_as_float(sr[3]), __uint_as_float(sr[4]), __uint_as_float(sr[5]));
+#define SF(x) __uint_as_float(sr[x])
+                // p = 2^(s*c - m*c) is computed SPECULATIVELY against the current reference; the warp votes afterwards on whether
+                // any score sat more than 2^8 above it.  Only when the vote fires (always at the
+                // very first half-tile, rarely later) the reference is updated and the pass repeated — so the common step has
+                // no max -> exp dependency.  Packed FFMA2 for the scale/shift, MUFU.EX2 for most pairs and the FMA-pipe
+                // polynomial for kPolyPairs of every 8 pairs (tools/softmax_pipe_probe.cu: MUFU.EX2 costs 8 clk per warp
+                // instruction, the polynomial 9 clk per element of FMA pipe: they only pay off side by side).
+                uint32_t pk[16];  // pk[2g] = row0, pk[2g+1] = row0 + 8 : packed P column 32 ch + 4 g + cp
+                uint64_t ls[2];
+#pragma unroll 1
+                for (int pass = 0;; ++pass) {  // at most two passes: the second one runs against the refreshed reference
+                    ls[0] = 0ull, ls[1] = 0ull;
 #pragma unroll
-                for (int e = 6; e < 30; e += 4) {
-                    mx0 = fmax3(mx0, __uint_as_float(sr[e]), __uint_as_float(sr[e + 1]));
-                    mx1 = fmax3(mx1, __uint_as_float(sr[e + 2]), __uint_as_float(sr[e + 3]));
-                }
-                const float m_loc = fmaxf(fmax3(mx0, __uint_as_float(sr[30]), __uint_as_float(sr[31])), mx1);
-                const uint32_t xaddr = xchg_smem + static_cast<uint32_t>(i * 512 + row_in_tile) * 4u;
-                st_shared_f32(xaddr + ch * 512u, m_loc);
-                named_bar_sync(1 + q, 128);  // also orders every S load of the quarter before any P store below
-                const float m_t = fmaxf(fmaxf(ld_shared_f32(xaddr), ld_shared_f32(xaddr + 512u)), fmaxf(ld_shared_f32(xaddr + 1024u), ld_shared_f32(xaddr + 1536u)));
-                const float m_new = fmaxf(m_used[i], m_t);
-                if (j == 0) {
-                    m_used[i] = m_new;
-                } else {
-                    const bool need = (m_new - m_used[i]) * c > kRescaleThreshold;
-                    if (__any_sync(0xffffffffu, need)) {  // identical in the four warps of the quarter (same rows, same maxima)
-                        const float f = ex2_approx((m_used[i] - m_new) * c);
-                        l2[i] = mul_f32x2(l2[i], pack_f32x2(f, f));
-                        uint32_t ov[kOCols];
-                        if constexpr (kOCols == 32) tmem_ld_x32(o_col[i] + kOCols * ch, ov);
-                        else tmem_ld_x16(o_col[i] + kOCols * ch, ov);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int e = 0; e < kOCols; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * f);
-                        if constexpr (kOCols == 32) tmem_st_x32(o_col[i] + kOCols * ch, ov);
-                        else tmem_st_x16(o_col[i] + kOCols * ch, ov);
-                        m_used[i] = m_new;
+                    for (int e = 0; e < 16; ++e) {  // pair e: group g = e / 2, row r = e & 1
+                        const int r = e & 1;
+                        const uint64_t x2 = fma_f32x2(pack_f32x2(SF(2 * e), SF(2 * e + 1)), c2, nmc2[r]);
+                        float x0, x1, p0, p1;
+                        unpack_f32x2(x2, x0, x1);
+                        if ((e & 7) < kPolyPairs) {
+                            ex2_poly_x2(x0, x1, p0, p1);
+                        } else {
+                            p0 = ex2_approx(x0);
+                            p1 = ex2_approx(x1);
+                        }
+                        ls[r] = add_f32x2(ls[r], pack_f32x2(p0, p1));
+                        pk[e] = pack_bf16x2(p0, p1);
                     }
-                }
-                TR(3);
-                // p = 2^(s*c - m*c): packed FFMA2 for the scale/shift, MUFU.EX2 for most pairs and the FMA-pipe polynomial for
-                // kPolyPairs of every 8 pairs (the MUFU retires one warp-instruction per 8 clk and would otherwise pace the loop)
-                const float nmc = -m_used[i] * c;
-                const uint64_t nmc2 = pack_f32x2(nmc, nmc);
-                uint32_t pk[16];
-                uint64_t ls[2] = {0ull, 0ull};
+                    // Vote: does any score of this half-tile sit more than 2^8 above the reference?  The MUFU pairs are judged by
+                    // their results (a p > 2^8 makes this thread's partial row sum > 2^8; ex2.approx overflows cleanly to +inf), the
+                    // polynomial pairs by their scores (the exponent-field arithmetic is only valid for x < 128).  A false positive
+                    // merely refreshes the reference.  The very first half-tile always votes yes (no reference yet).
+                    float lo0, hi0, lo1, hi1;
+                    unpack_f32x2(ls[0], lo0, hi0);
+                    unpack_f32x2(ls[1], lo1, hi1);
+                    bool need = (lo0 + hi0 > kSumTrigger) || (lo1 + hi1 > kSumTrigger) || (m_used[0] == -INFINITY);
+                    if constexpr (kPolyPairs > 0) {
+                        float pm0 = -INFINITY, pm1 = -INFINITY;
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    const uint64_t x2 = fma_f32x2(pack_f32x2(__uint_as_float(sr[2 * e]), __uint_as_float(sr[2 * e + 1])), c2, nmc2);
-                    float x0, x1, p0, p1;
-                    unpack_f32x2(x2, x0, x1);
-                    if ((e & 7) < kPolyPairs) {
-                        ex2_poly_x2(x0, x1, p0, p1);
-                    } else {
-                        p0 = ex2_approx(x0);
-                        p1 = ex2_approx(x1);
+                        for (int e = 0; e < 16; ++e)
+                            if ((e & 7) < kPolyPairs) {
+                                if (e & 1) pm1 = fmax3(pm1, SF(2 * e), SF(2 * e + 1));
+                                else pm0 = fmax3(pm0, SF(2 * e), SF(2 * e + 1));
+                            }
+                        need = need || (pm0 > thr[0]) || (pm1 > thr[1]);
                     }
-                    ls[e & 1] = add_f32x2(ls[e & 1], pack_f32x2(p0, p1));
-                    pk[e] = pack_bf16x2(p0, p1);
+                    if (pass == 1 || !__any_sync(0xffffffffu, need)) break;
+                    float mx0 = fmax3(SF(0), SF(1), SF(4)), mx1 = fmax3(SF(2), SF(3), SF(6));
+                    mx0 = fmax3(mx0, SF(5), SF(8)), mx1 = fmax3(mx1, SF(7), SF(10));
+#pragma unroll
+                    for (int g = 2; g < 7; ++g) {
+                        mx0 = fmax3(mx0, SF(4 * g + 1), SF(4 * g + 4));
+                        mx1 = fmax3(mx1, SF(4 * g + 3), SF(4 * g + 6));
+                    }
+                    mx0 = fmaxf(mx0, SF(29));
+                    mx1 = fmaxf(mx1, SF(31));
+                    // ---- reference update: quad-reduce the row maxima, rescale this warp's 16 rows of O, repeat the pass ----
+                    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+                    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+                    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+                    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+                    const float mn0 = fmaxf(m_used[0], mx0), mn1 = fmaxf(m_used[1], mx1);
+                    if (j > 0 || ch > 0) {
+                        if (ch > 0) {  // the PV MMAs of this step's first half must have left O_i
+                            mbar_wait(pv_half(i), j & 1);
+                            tc_fence_after();
+                        }
+                        const float f0 = ex2_approx((m_used[0] - mn0) * c), f1 = ex2_approx((m_used[1] - mn1) * c);
+                        l2[0] = mul_f32x2(l2[0], pack_f32x2(f0, f0));
+                        l2[1] = mul_f32x2(l2[1], pack_f32x2(f1, f1));
+#pragma unroll 1
+                        for (int g = 0; g < D / 32; ++g) {
+                            uint32_t ov[16];
+                            tmem_ld_16x256b_x4(o_col + 32 * g, ov);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * ((e & 2) ? f1 : f0));
+                            tmem_st_16x256b_x4(o_col + 32 * g, ov);
+                        }
+                    }
+                    m_used[0] = mn0, m_used[1] = mn1;
+                    thr[0] = mn0 + thr_off, thr[1] = mn1 + thr_off;
+                    nmc2[0] = pack_f32x2(-mn0 * c, -mn0 * c), nmc2[1] = pack_f32x2(-mn1 * c, -mn1 * c);
                 }
-                l2[i] = add_f32x2(l2[i], add_f32x2(ls[0], ls[1]));
-                tmem_st_x16(s_col[i] + 16 * ch, pk);
-                TR(5);
+#undef SF
+                if (ch == 0) TR(3);
+                l2[0] = add_f32x2(l2[0], ls[0]);
+                l2[1] = add_f32x2(l2[1], ls[1]);
+                tmem_st_16x128b_x8(s_col + 32 * ch, pk);
+                if (ch == 1) TR(5);
                 tmem_st_wait();  // covers the rescaled O columns too
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(p_full(i));
-                TR(6);
+                if (lane == 0) mbar_arrive(p_full(i, ch));
             }
+            TR(6);
         }
-        // ===== epilogue: O / l -> bf16 -> global; warp (q, ch) writes columns [ch D/4, (ch+1) D/4) of its 32 rows =====
+        // ===== epilogue: O / l -> bf16 -> global; the quad of a row writes 16 contiguous bytes per 8-column group =====
+        {
+            float l[2];
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            float lo, hi;
-            unpack_f32x2(l2[i], lo, hi);
-            const uint32_t xaddr = xchg_smem + static_cast<uint32_t>(i * 512 + row_in_tile) * 4u;
-            named_bar_sync(1 + q, 128);  // the last row-max exchange of this slot has been read by everyone
-            st_shared_f32(xaddr + ch * 512u, lo + hi);
-            named_bar_sync(1 + q, 128);
-            const float l = (ld_shared_f32(xaddr) + ld_shared_f32(xaddr + 512u)) + (ld_shared_f32(xaddr + 1024u) + ld_shared_f32(xaddr + 1536u));
+            for (int r = 0; r < 2; ++r) {
+                float lo, hi;
+                unpack_f32x2(l2[r], lo, hi);
+                l[r] = lo + hi;
+                l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
+                l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
+            }
             mbar_wait(o_done(i), 0);
             tc_fence_after();
-            const float inv_l = 1.f / l;
-            const int row = q0 + i * kBlockM + row_in_tile;
-            uint32_t ov[kOCols];
-            if constexpr (kOCols == 32) tmem_ld_x32(o_col[i] + kOCols * ch, ov);
-            else tmem_ld_x16(o_col[i] + kOCols * ch, ov);
-            tmem_ld_wait();
-            if (row < p.Lq) {
-                __nv_bfloat16* orow = p.o + batch * p.o_sb + head * p.o_sh + static_cast<int64_t>(row) * p.o_sl + kOCols * ch;
+            const float inv_l[2] = {1.f / l[0], 1.f / l[1]};
+            const int row[2] = {q0 + i * kBlockM + row0_in_tile, q0 + i * kBlockM + row0_in_tile + 8};
+            __nv_bfloat16* obase = p.o + batch * p.o_sb + head * p.o_sh + 2 * cp;
+#pragma unroll 1
+            for (int g4 = 0; g4 < D / 32; ++g4) {
+                uint32_t ov[16];
+                tmem_ld_16x256b_x4(o_col + 32 * g4, ov);
+                tmem_ld_wait();
 #pragma unroll
-                for (int g = 0; g < kOCols / 8; ++g) {
-                    uint4 o;
-                    o.x = pack_bf16x2(__uint_as_float(ov[8 * g + 0]) * inv_l, __uint_as_float(ov[8 * g + 1]) * inv_l);
-                    o.y = pack_bf16x2(__uint_as_float(ov[8 * g + 2]) * inv_l, __uint_as_float(ov[8 * g + 3]) * inv_l);
-                    o.z = pack_bf16x2(__uint_as_float(ov[8 * g + 4]) * inv_l, __uint_as_float(ov[8 * g + 5]) * inv_l);
-                    o.w = pack_bf16x2(__uint_as_float(ov[8 * g + 6]) * inv_l, __uint_as_float(ov[8 * g + 7]) * inv_l);
-                    *reinterpret_cast<uint4*>(orow + 8 * g) = o;
+                for (int r = 0; r < 2; ++r) {
+                    if (row[r] < p.Lq) {
+                        __nv_bfloat16* orow = obase + static_cast<int64_t>(row[r]) * p.o_sl + 32 * g4;
+#pragma unroll
+                        for (int g = 0; g < 4; ++g)
+                            *reinterpret_cast<uint32_t*>(orow + 8 * g) =
+                                pack_bf16x2(__uint_as_float(ov[4 * g + 2 * r]) * inv_l[r], __uint_as_float(ov[4 * g + 2 * r + 1]) * inv_l[r]);
+                    }
                 }
-                if (p.lse && ch == 0) p.lse[(static_cast<int64_t>(batch) * p.H + head) * p.Lq + row] = m_used[i] * p.scale + logf(l);
+            }
+            if (p.lse && cp == 0) {
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+                    if (row[r] < p.Lq) p.lse[(static_cast<int64_t>(batch) * p.H + head) * p.Lq + row[r]] = m_used[r] * p.scale + logf(l[r]);
             }
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) {
+    if (warp == 0) {
         tc_fence_after();
         tmem_dealloc(tmem_base, Cfg::kTmemCols);
     }
@@ -374,6 +450,8 @@ static int make_attn_tmap(CUtensorMap* tm, const AttnTensor& t, int B, int H, in
 template <int D>
 static int launch_attn_d(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const AttnParams& p, cudaStream_t stream) {
     using Cfg = AttnCfg<D>;
+    static_assert(Cfg::kSmemBytes <= 232448, "shared memory budget");
+    static_assert(2 * Cfg::kKvStages + 12 <= Cfg::kBarBytes / 8, "barrier area");
     static bool attr_set = false;
     if (!attr_set) {
         VAP_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));

@@ -72,13 +72,26 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// try_wait suspends the thread in hardware until the phase completes or the (optional) time hint expires, so a long hint
+// means few polling iterations (spinning warps steal issue slots from the warps that share their SM sub-partition).
+#ifndef VAP_MBAR_SUSPEND_HINT_NS
+#define VAP_MBAR_SUSPEND_HINT_NS 0
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
+#if VAP_MBAR_SUSPEND_HINT_NS > 0
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(static_cast<uint32_t>(VAP_MBAR_SUSPEND_HINT_NS))
+        : "memory");
+#else
     asm volatile(
         "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
         : "=r"(ok)
         : "r"(bar), "r"(parity)
         : "memory");
+#endif
     return ok != 0;
 }
 // Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU box.
