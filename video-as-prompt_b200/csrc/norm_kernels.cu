@@ -1,6 +1,6 @@
 // norm_kernels.cu — HBM-bound kernels of the MoT block (sm_100a).
 //
-//  * adaln_layernorm_kernel : (adaLN-modulated) LayerNorm, one warp per token row, the row lives in
+//  * adaln_layernorm_kernel : (adaLN-modulated) LayerNorm, one or four warps per token row, the row lives in
 //    registers (16-byte vector loads, read once / written once: 4 B per element of algorithmic traffic).
 //      Wan : (LN_fp32(x) [*w+b]) * (1+scale) + shift -> bf16            transformer_wan_mot.py:620-623, 668-669, 680-689
 //      Cog : bf16(bf16(bf16(LN_affine(x)) * bf16(1+scale)) + shift)     normalization.py:464-471
@@ -25,24 +25,33 @@ __device__ __forceinline__ float warp_sum(float v) {
 // (adaLN) LayerNorm
 // ------------------------------------------------------------------------------------------
 
-template <int MAXV>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, (MAXV <= 20) ? 2 : 1) adaln_layernorm_kernel(LnParams p) {
-    const int lane = threadIdx.x & 31;
-    const int64_t row = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
-    if (row >= p.rows) return;
+// WPR warps share one token row (WPR = 1 for d <= 2048, 4 above): a thread then holds at most MAXV = 8 16-byte vectors, so
+// the row stays in registers WITHOUT spilling (the one-warp-per-row version held 20 vectors per lane at d = 5120, spilled
+// and reached 1.3 TB/s) and 1024 threads per SM keep ~80 KB of loads in flight.  Row statistics: two passes over the
+// registers, warp shuffles, and for WPR = 4 a 4-float exchange through shared memory behind a 128-thread named barrier.
+template <int MAXV, int WPR>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, (MAXV <= 5) ? 4 : 3) adaln_layernorm_kernel(LnParams p) {
+    __shared__ float red[2][kWarpsPerBlock];
+    const int warp = threadIdx.x >> 5;
+    const int tl = threadIdx.x & (32 * WPR - 1);  // thread index inside the row group
+    const int group = warp / WPR;
+    const int64_t row = static_cast<int64_t>(blockIdx.x) * (kWarpsPerBlock / WPR) + group;
+    if (row >= p.rows) return;  // whole row groups leave together (the named barrier below is per group)
     const int nvec = p.d >> 3;  // 8 bf16 per 16-byte vector
     const __nv_bfloat16* xr = p.x + row * p.x_stride;
+    constexpr int kStride = 32 * WPR;
+    const int lane = tl;  // vector index base
 
     uint4 raw[MAXV];
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
-        const int v = lane + 32 * i;
+        const int v = lane + kStride * i;
         if (v < nvec) raw[i] = ld_nc_v4(xr + 8 * v);
     }
     float sum = 0.f;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
-        if (lane + 32 * i < nvec) {
+        if (lane + kStride * i < nvec) {
             const uint32_t* u = reinterpret_cast<const uint32_t*>(&raw[i]);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -51,11 +60,19 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (MAXV <= 20) ? 2 : 1) ada
             }
         }
     }
-    const float mean = warp_sum(sum) / static_cast<float>(p.d);
+    sum = warp_sum(sum);
+    if constexpr (WPR > 1) {
+        if ((threadIdx.x & 31) == 0) red[0][warp] = sum;
+        named_bar_sync(1 + group, 32 * WPR);
+        sum = 0.f;
+#pragma unroll
+        for (int w = 0; w < WPR; ++w) sum += red[0][group * WPR + w];
+    }
+    const float mean = sum / static_cast<float>(p.d);
     float sq = 0.f;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
-        if (lane + 32 * i < nvec) {
+        if (lane + kStride * i < nvec) {
             const uint32_t* u = reinterpret_cast<const uint32_t*>(&raw[i]);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -65,7 +82,15 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (MAXV <= 20) ? 2 : 1) ada
             }
         }
     }
-    const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(p.d) + p.eps);
+    sq = warp_sum(sq);
+    if constexpr (WPR > 1) {
+        if ((threadIdx.x & 31) == 0) red[1][warp] = sq;
+        named_bar_sync(1 + group, 32 * WPR);
+        sq = 0.f;
+#pragma unroll
+        for (int w = 0; w < WPR; ++w) sq += red[1][group * WPR + w];
+    }
+    const float rstd = rsqrtf(sq / static_cast<float>(p.d) + p.eps);
 
     const int64_t batch = p.rows_per_batch > 0 ? row / p.rows_per_batch : 0;
     const float* s1p = p.scale1p ? p.scale1p + batch * p.mod_stride : nullptr;
@@ -73,7 +98,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (MAXV <= 20) ? 2 : 1) ada
     __nv_bfloat16* orow = p.out + row * p.out_stride;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
-        const int v = lane + 32 * i;
+        const int v = lane + kStride * i;
         if (v < nvec) {
             const uint32_t* u = reinterpret_cast<const uint32_t*>(&raw[i]);
             float y[8];
@@ -126,16 +151,23 @@ int launch_adaln_layernorm(const LnParams& p, cudaStream_t stream) {
     VAP_REQUIRE((p.scale1p == nullptr) == (p.shift == nullptr), "adaln_layernorm: scale1p and shift must both be given or both null");
     if (p.rows == 0) return 0;
     const int nvec = p.d / 8;
-    const unsigned grid = static_cast<unsigned>((p.rows + kWarpsPerBlock - 1) / kWarpsPerBlock);
     const dim3 block(kWarpsPerBlock * 32);
-    if (nvec <= 32 * 4)
-        adaln_layernorm_kernel<4><<<grid, block, 0, stream>>>(p);
-    else if (nvec <= 32 * 12)
-        adaln_layernorm_kernel<12><<<grid, block, 0, stream>>>(p);
-    else if (nvec <= 32 * 20)
-        adaln_layernorm_kernel<20><<<grid, block, 0, stream>>>(p);
-    else
-        adaln_layernorm_kernel<32><<<grid, block, 0, stream>>>(p);
+    if (nvec <= 32 * 8) {  // d <= 2048: one warp per row
+        const unsigned grid = static_cast<unsigned>((p.rows + kWarpsPerBlock - 1) / kWarpsPerBlock);
+        if (nvec <= 32 * 2)
+            adaln_layernorm_kernel<2, 1><<<grid, block, 0, stream>>>(p);
+        else
+            adaln_layernorm_kernel<8, 1><<<grid, block, 0, stream>>>(p);
+    } else {  // four warps per row
+        constexpr int kRowsPerBlock = kWarpsPerBlock / 4;
+        const unsigned grid = static_cast<unsigned>((p.rows + kRowsPerBlock - 1) / kRowsPerBlock);
+        if (nvec <= 128 * 3)
+            adaln_layernorm_kernel<3, 4><<<grid, block, 0, stream>>>(p);
+        else if (nvec <= 128 * 5)
+            adaln_layernorm_kernel<5, 4><<<grid, block, 0, stream>>>(p);
+        else
+            adaln_layernorm_kernel<8, 4><<<grid, block, 0, stream>>>(p);
+    }
     VAP_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
