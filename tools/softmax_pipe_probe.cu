@@ -14,7 +14,7 @@ namespace vap { void set_error(const char*, ...) {} }
 
 constexpr int REPS = 512;
 
-enum { V_EMPTY, V_FFMA, V_FFMA2, V_FADD2, V_FMNMX, V_FMNMX3, V_F2FP, V_MUFU, V_IMAD, V_SCALE_MUFU_PACK, V_SOFTMAX, V_SOFTMAX_NOSUM, V_POLY_NOCLAMP };
+enum { V_MUFU_BF16X2, V_MUFU_F16X2, V_EMPTY, V_FFMA, V_FFMA2, V_FADD2, V_FMNMX, V_FMNMX3, V_F2FP, V_MUFU, V_IMAD, V_SCALE_MUFU_PACK, V_SOFTMAX, V_SOFTMAX_NOSUM, V_POLY_NOCLAMP };
 
 template <int VARIANT, int POLY>
 __global__ void __launch_bounds__(512, 1) probe(const float* in, uint32_t* out, long long* cycles) {
@@ -61,6 +61,20 @@ __global__ void __launch_bounds__(512, 1) probe(const float* in, uint32_t* out, 
         } else if (VARIANT == V_MUFU) {
 #pragma unroll
             for (int e = 0; e < 64; ++e) s[e] = ex2_approx(s[e]);
+        } else if (VARIANT == V_MUFU_BF16X2) {
+#pragma unroll
+            for (int g = 0; g < 32; ++g) {  // 64 elements as 32 packed pairs -> 64 MUFU.EX2.BF16
+                uint32_t x = __float_as_uint(s[g]), y;
+                asm volatile("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(y) : "r"(x));
+                s[g] = __uint_as_float(y);
+            }
+        } else if (VARIANT == V_MUFU_F16X2) {
+#pragma unroll
+            for (int g = 0; g < 32; ++g) {
+                uint32_t x = __float_as_uint(s[g]), y;
+                asm volatile("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
+                s[g] = __uint_as_float(y);
+            }
         } else if (VARIANT == V_IMAD) {
 #pragma unroll
             for (int e = 0; e < 64; ++e) s[e] = __int_as_float(__float_as_int(s[e]) * 0x800000 + __float_as_int(nm));
@@ -151,6 +165,8 @@ int main() {
     run<V_F2FP, 0>("32 F2FP.BF16 + 32 LOP3", in, out, cyc);
     run<V_MUFU, 0>("64 MUFU.EX2", in, out, cyc);
     run<V_IMAD, 0>("64 IMAD", in, out, cyc);
+    run<V_MUFU_BF16X2, 0>("32 ex2.bf16x2 (64 MUFU.EX2.BF16)", in, out, cyc);
+    run<V_MUFU_F16X2, 0>("32 ex2.f16x2 (64 MUFU.EX2.F16)", in, out, cyc);
     run<V_SOFTMAX_NOSUM, 0>("scale + MUFU + pack (no sum)", in, out, cyc);
     run<V_SOFTMAX, 0>("softmax poly 0/8", in, out, cyc);
     run<V_SOFTMAX, 2>("softmax poly 2/8", in, out, cyc);

@@ -94,6 +94,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 #endif
     return ok != 0;
 }
+// non-blocking probe of a phase
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU box.
 #ifndef VAP_MBAR_SPIN_LIMIT
 #define VAP_MBAR_SPIN_LIMIT (1u << 21)
@@ -369,6 +379,16 @@ __device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
 // named barrier over a subset of warps
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// named barrier + OR-reduction of a predicate over its participants (every participant gets the result)
+__device__ __forceinline__ bool named_bar_red_or(uint32_t id, uint32_t nthreads, bool pred) {
+    uint32_t out;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %3, 0;\n\tbarrier.cta.red.or.pred p, %1, %2, q;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(out)
+        : "r"(id), "r"(nthreads), "r"(static_cast<uint32_t>(pred))
+        : "memory");
+    return out != 0;
 }
 __device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads) {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
