@@ -176,18 +176,28 @@ int launch_adaln_layernorm(const LnParams& p, cudaStream_t stream) {
 // q/k norm + RoPE (in place)
 // ------------------------------------------------------------------------------------------
 
-// One warp per token row; processes q then k.  Every lane always owns the same 8 channels of a head
-// (vector v = lane + 32*i  ->  channel-in-head 8*(v % (D/8)) = 8*(lane % (D/8)) because 32 % (D/8) == 0),
-// so its 4 RoPE (cos,sin) pairs and (Cog) its per-head LN affine values are loaded once.
-template <int MAXV, bool COG>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, (MAXV <= 20) ? 2 : 1) qk_norm_rope_kernel(QkParams p) {
-    const int lane = threadIdx.x & 31;
-    const int64_t row = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
-    if (row >= p.rows) return;
+// One work item = (token row, q or k); WPR warps share an item (WPR = 1 for d <= 2048, 4 above) so a thread holds at most
+// 8 16-byte vectors and nothing spills (the one-warp-per-row version held 20 per lane at d = 5120 and did q then k serially).
+// Every thread always owns the same 8 channels of a head (vector v = tl + 32*WPR*i -> channel-in-head 8*(v % (D/8)) =
+// 8*(tl % (D/8)) because 32*WPR % (D/8) == 0), so its 4 RoPE (cos,sin) pairs and (Cog) its per-head LN affine values are
+// loaded once; a head's D/8 vectors sit in consecutive lanes of ONE warp (D/8 divides 32), so the per-head statistics of
+// the CogVideoX mode stay shuffle-only.
+template <int MAXV, int WPR, bool COG>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, (MAXV <= 5) ? 4 : 3) qk_norm_rope_kernel(QkParams p) {
+    __shared__ float red[kWarpsPerBlock];
+    const int warp = threadIdx.x >> 5;
+    const int tl = threadIdx.x & (32 * WPR - 1);
+    const int group = warp / WPR;
+    constexpr int kStride = 32 * WPR;
+    const int n_which = p.k ? 2 : 1;  // k == null: normalise q only (cross-attention queries)
+    const int64_t item = static_cast<int64_t>(blockIdx.x) * (kWarpsPerBlock / WPR) + group;
+    if (item >= p.rows * n_which) return;  // whole groups leave together (the named barrier below is per group)
+    const int64_t row = item / n_which;
+    const int which = static_cast<int>(item - row * n_which);
     const int d = p.heads * p.head_dim;
     const int nvec = d >> 3;
     const int vec_per_head = p.head_dim >> 3;
-    const int ch = 8 * (lane % vec_per_head);  // channel offset inside the head
+    const int ch = 8 * (tl % vec_per_head);  // channel offset inside the head
 
     const int64_t pos = p.rows_per_batch > 0 ? row % p.rows_per_batch : row;
     const bool rotate = (p.cos != nullptr) && pos >= p.rope_row0 && (pos - p.rope_row0) < p.rope_rows;
@@ -200,16 +210,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (MAXV <= 20) ? 2 : 1) qk_
         sn[0] = s4.x, sn[1] = s4.y, sn[2] = s4.z, sn[3] = s4.w;
     }
 
-    const int n_which = p.k ? 2 : 1;  // k == null: normalise q only (cross-attention queries)
-#pragma unroll 1
-    for (int which = 0; which < n_which; ++which) {
+    {
         __nv_bfloat16* xr = (which == 0 ? p.q : p.k) + row * p.row_stride;
         const float* w = which == 0 ? p.wq : p.wk;
         const float* b = which == 0 ? p.bq : p.bk;
         uint4 raw[MAXV];
 #pragma unroll
         for (int i = 0; i < MAXV; ++i) {
-            const int v = lane + 32 * i;
+            const int v = tl + kStride * i;
             if (v < nvec) raw[i] = *reinterpret_cast<const uint4*>(xr + 8 * v);
         }
         float rs = 0.f;  // Wan: rsqrt(mean(x^2) + eps) over the whole row
@@ -217,7 +225,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (MAXV <= 20) ? 2 : 1) qk_
             float sq = 0.f;
 #pragma unroll
             for (int i = 0; i < MAXV; ++i) {
-                if (lane + 32 * i < nvec) {
+                if (tl + kStride * i < nvec) {
                     const uint32_t* u = reinterpret_cast<const uint32_t*>(&raw[i]);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -226,7 +234,15 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (MAXV <= 20) ? 2 : 1) qk_
                     }
                 }
             }
-            rs = rsqrtf(warp_sum(sq) / static_cast<float>(d) + p.eps);
+            sq = warp_sum(sq);
+            if constexpr (WPR > 1) {
+                if ((threadIdx.x & 31) == 0) red[warp] = sq;
+                named_bar_sync(1 + group, 32 * WPR);
+                sq = 0.f;
+#pragma unroll
+                for (int ww = 0; ww < WPR; ++ww) sq += red[group * WPR + ww];
+            }
+            rs = rsqrtf(sq / static_cast<float>(d) + p.eps);
         }
         float wl[8], bl[8];
         if (COG) {
@@ -238,7 +254,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (MAXV <= 20) ? 2 : 1) qk_
         }
 #pragma unroll
         for (int i = 0; i < MAXV; ++i) {
-            const int v = lane + 32 * i;
+            const int v = tl + kStride * i;
             // NOTE: the shuffles below need all lanes of a head group; nvec is a multiple of vec_per_head and
             // vec_per_head divides 32, so a head is never split between an active and an inactive lane.
             const bool active = v < nvec;
@@ -308,23 +324,26 @@ int launch_qk_norm_rope(const QkParams& p, int cog_mode, cudaStream_t stream) {
     if (cog_mode) VAP_REQUIRE(p.bq && (p.bk || !p.k), "qk_norm_rope: per-head LayerNorm needs biases");
     if (p.rows == 0) return 0;
     const int nvec = d / 8;
-    const unsigned grid = static_cast<unsigned>((p.rows + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    const int64_t items = p.rows * (p.k ? 2 : 1);
     const dim3 block(kWarpsPerBlock * 32);
-#define VAP_QK_LAUNCH(MV)                                                              \
-    do {                                                                               \
-        if (cog_mode)                                                                  \
-            qk_norm_rope_kernel<MV, true><<<grid, block, 0, stream>>>(p);              \
-        else                                                                           \
-            qk_norm_rope_kernel<MV, false><<<grid, block, 0, stream>>>(p);             \
+#define VAP_QK_LAUNCH(MV, WPR)                                                                                   \
+    do {                                                                                                         \
+        const unsigned grid = static_cast<unsigned>((items + kWarpsPerBlock / WPR - 1) / (kWarpsPerBlock / WPR)); \
+        if (cog_mode)                                                                                            \
+            qk_norm_rope_kernel<MV, WPR, true><<<grid, block, 0, stream>>>(p);                                   \
+        else                                                                                                     \
+            qk_norm_rope_kernel<MV, WPR, false><<<grid, block, 0, stream>>>(p);                                  \
     } while (0)
-    if (nvec <= 32 * 4)
-        VAP_QK_LAUNCH(4);
-    else if (nvec <= 32 * 12)
-        VAP_QK_LAUNCH(12);
-    else if (nvec <= 32 * 20)
-        VAP_QK_LAUNCH(20);
+    if (nvec <= 32 * 2)
+        VAP_QK_LAUNCH(2, 1);
+    else if (nvec <= 32 * 8)
+        VAP_QK_LAUNCH(8, 1);
+    else if (nvec <= 128 * 3)
+        VAP_QK_LAUNCH(3, 4);
+    else if (nvec <= 128 * 5)
+        VAP_QK_LAUNCH(5, 4);
     else
-        VAP_QK_LAUNCH(32);
+        VAP_QK_LAUNCH(8, 4);
 #undef VAP_QK_LAUNCH
     VAP_CHECK_CUDA(cudaGetLastError());
     return 0;
