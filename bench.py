@@ -189,6 +189,7 @@ def main():
     ap.add_argument("--impl", default="vap")
     ap.add_argument("--config", default="wan14b")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sp-mode", default=None, choices=["p2p", "nccl"], help="Ulysses transport for N > 1 (default p2p: exchange fused into the kernels over NVLink peer memory)")
     ap.add_argument("--profile", action="store_true", help="bracket the device-timed steps with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     a = ap.parse_args()
 
@@ -200,7 +201,7 @@ def main():
     f, h, wd = w["latent"]
     S = f * (h // 2) * (wd // 2)
     config = dict(workload=w["name"], tokens_per_stream=S, joint_tokens=2 * S + (452 if w["family"] == "cog" else 0), batch=1,
-                  parallelism=f"ulysses-sp{world}" if world > 1 else "single-gpu",
+                  parallelism=f"ulysses-sp{world}-{a.sp_mode or os.environ.get('VAP_ULYSSES') or 'p2p'}" if world > 1 else "single-gpu",
                   l2="working set (65 GB of weights + activations per step) >> 126 MB L2: no flush needed")
 
     if a.impl == "reference":
@@ -227,7 +228,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-        vap.ulysses.enable()
+        sp = vap.ulysses.enable(mode=a.sp_mode)
     model = build_model(vap, w, dev)
     inp = make_inputs(vap, w, dev)
     host = {k: (v.cpu().pin_memory() if torch.is_tensor(v) else v) for k, v in inp.items()}

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define VAP_B200_VERSION 100 /* major*10000 + minor*100 + patch */
+#define VAP_B200_VERSION 200 /* major*10000 + minor*100 + patch */
 
 /* Library version (VAP_B200_VERSION of the build). */
 int vap_version(void);
@@ -95,6 +95,26 @@ int vap_ulysses_pack(const void* src, void* dst, int64_t L, int nsplit, int64_t 
                      int64_t dst_row_stride, int64_t dst_split_stride, void* stream);
 int vap_ulysses_unpack(const void* src, void* dst, int64_t L, int nsplit, int64_t chunk, int64_t src_row_stride,
                        int64_t src_split_stride, int64_t dst_row_stride, void* stream);
+
+/* (5b) Ulysses exchange FUSED into the producing kernels, over NVLink peer memory (the pointer tables hold device pointers of
+ *      every rank's symmetric buffer, mapped into this process; `dst` / `o_peers` are HOST arrays of nsplit / npeers entries).
+ *   vap_qkv_scatter: vap_qk_norm_rope (same arguments) on the q and k columns of the local QKV projection output plus an
+ *      unchanged copy of the v columns, with every 16-byte result vector of head h stored straight into rank
+ *      s = h / (heads/nsplit)'s receive buffer  dst[s][dst_slot][dst_row0 + row][q|k|v][(heads/nsplit)*head_dim]
+ *      (slot_rows rows per slot) — all-to-all #1 without a pack kernel or a collective call.  q/k/v are not modified.
+ *   vap_attention_fwd_scatter: vap_attention_fwd whose epilogue stores query row `row` into
+ *      o_peers[row / o_rows_per_peer] at local row `row % o_rows_per_peer` (strides o_sb/o_sh/o_sl apply inside each peer
+ *      buffer; the caller offsets every peer pointer to this rank's head columns) — all-to-all #2 and the unpack fused
+ *      into the attention kernel.
+ *   The caller orders the exchange with a device-side barrier between the ranks (e.g. torch symmetric-memory barrier). */
+int vap_qkv_scatter(const void* q, const void* k, const void* v, int64_t rows, int heads, int head_dim, int64_t row_stride, const float* wq,
+                    const float* bq, const float* wk, const float* bk, const float* cos, const float* sin, int64_t rows_per_batch,
+                    int64_t rope_row0, int64_t rope_rows, float eps, int mode, void* const* dst, int nsplit, int64_t dst_slot,
+                    int64_t slot_rows, int64_t dst_row0, void* stream);
+int vap_attention_fwd_scatter(const void* q, const void* k, const void* v, void* const* o_peers, int npeers, int o_rows_per_peer, float* lse,
+                              int B, int H, int Lq, int Lkv, int D, int64_t q_sb, int64_t q_sh, int64_t q_sl, int64_t k_sb, int64_t k_sh,
+                              int64_t k_sl, int64_t v_sb, int64_t v_sh, int64_t v_sl, int64_t o_sb, int64_t o_sh, int64_t o_sl, float scale,
+                              void* stream);
 
 /* (6) Bring-up probe for the tcgen05 descriptors: one CTA computes D[128,N] = A[128,K] * B, fp32 out.
  *     a_in_tmem: bit 0: 0 = A from shared memory (K-major, SWIZZLE_128B), 1 = A staged to TMEM as packed bf16;

@@ -426,6 +426,50 @@ def check_ulysses_relayout():
     return dict(ok=True)
 
 
+def check_ulysses_p2p_emulated(P=4, L=96, H=8, D=128, mode=0):
+    """The fused Ulysses exchange (vap_qkv_scatter + vap_attention_fwd_scatter) with P ranks EMULATED on one device: rank r's
+    kernels get the other ranks' buffers as "peer" pointers.  Must reproduce — bit for bit — q/k-norm + RoPE in place followed
+    by one attention over the whole sequence, because every rank computes the same per-head arithmetic on the same rows."""
+    d = H * D
+    J = P * L
+    qkv = _randn((J, 3 * d), 60).to(DEV)
+    g = torch.Generator().manual_seed(61)
+    wq, wk = (torch.rand(d if mode == 0 else D, generator=g) + 0.5).to(DEV), (torch.rand(d if mode == 0 else D, generator=g) + 0.5).to(DEV)
+    bq = bk = None
+    if mode == 1:
+        bq, bk = (torch.randn(D, generator=g) * 0.1).to(DEV), (torch.randn(D, generator=g) * 0.1).to(DEV)
+    ang = torch.rand((J, D // 2), generator=g) * 6.28
+    cos, sin = torch.cos(ang).to(DEV).contiguous(), torch.sin(ang).to(DEV).contiguous()
+    # reference: one device, no exchange
+    ref_qkv = qkv.clone()
+    ops.qk_norm_rope_(ref_qkv[:, :d], ref_qkv[:, d:2 * d], heads=H, head_dim=D, wq=wq, wk=wk, bq=bq, bk=bk, cos=cos, sin=sin, rows_per_batch=J, eps=1e-6,
+                      mode=mode)
+    q, k, v = (ref_qkv[None, :, i * d:(i + 1) * d].unflatten(2, (H, D)).transpose(1, 2) for i in range(3))
+    o_ref = ops.attention(q, k, v).transpose(1, 2).flatten(2, 3)[0]  # [J, d]
+    # emulated ranks
+    hp = d // P
+    recv = [torch.zeros((P, L, 3, hp), dtype=torch.bfloat16, device=DEV) for _ in range(P)]
+    out = [torch.zeros((L, d), dtype=torch.bfloat16, device=DEV) for _ in range(P)]
+    half = L // 2
+    for r in range(P):
+        loc = qkv[r * L:(r + 1) * L]
+        for row0, n in ((0, half), (half, L - half)):  # two "streams" per rank, as the MoT block dispatches them
+            sl = slice(row0, row0 + n)
+            ops.qkv_scatter(loc[sl, :d], loc[sl, d:2 * d], loc[sl, 2 * d:], heads=H, head_dim=D, wq=wq, wk=wk, bq=bq, bk=bk,
+                            cos=cos[r * L + row0:r * L + row0 + n].contiguous(), sin=sin[r * L + row0:r * L + row0 + n].contiguous(), rows_per_batch=n,
+                            eps=1e-6, mode=mode, dst_ptrs=[t.data_ptr() for t in recv], dst_slot=r, slot_rows=L, dst_row0=row0)
+    assert torch.equal(qkv, _randn((J, 3 * d), 60).to(DEV)), "scatter mode must not modify its inputs"
+    for s_ in range(P):
+        joint = recv[s_].view(1, J, 3, H // P, D)
+        qs, ks, vs = (joint[:, :, w].transpose(1, 2) for w in range(3))
+        ops.attention_scatter(qs, ks, vs, o_ptrs=[t.data_ptr() + s_ * hp * 2 for t in out], rows_per_peer=L, o_strides=(0, D, d))
+    o = torch.cat(out, dim=0)
+    exact = torch.equal(o, o_ref)
+    err = rel_err(o, o_ref)
+    assert err < 1e-6, f"emulated p2p Ulysses differs from the single-device path: {err}"
+    return dict(err=err, bit_exact=exact)
+
+
 CHECKS = {
     "probe_ss": lambda: check_probe(False, False, 128, 128),
     "probe_ss_n256": lambda: check_probe(False, False, 256, 64),
@@ -458,6 +502,9 @@ CHECKS = {
     "attn_one_tile": lambda: check_attention(1, 1, 64, 100, 128, joint_layout=False),
     "attn_peaky": lambda: check_attention_peaky(),
     "ulysses_relayout": check_ulysses_relayout,
+    "ulysses_p2p_emulated_wan": lambda: check_ulysses_p2p_emulated(P=4, L=96, H=8, D=128, mode=0),
+    "ulysses_p2p_emulated_p8": lambda: check_ulysses_p2p_emulated(P=8, L=300, H=40, D=128, mode=0),
+    "ulysses_p2p_emulated_cog": lambda: check_ulysses_p2p_emulated(P=2, L=130, H=6, D=64, mode=1),
     "wan_blocks": check_wan_blocks,
     "wan_model": check_wan_model,
     "wan_denoise": check_wan_denoise,

@@ -1,0 +1,36 @@
+"""Multi-GPU parity of Ulysses sequence parallelism (torchrun, N ranks): the tiny Wan VAP model (one MoT + one plain block, or
+more heads with --heads) run token-sharded over N GPUs — in both transports, "p2p" (exchange fused into the kernels over NVLink
+peer memory) and "nccl" — must match the same model run on one GPU.  Prints one JSON line on rank 0; exit code != 0 on mismatch.
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 tools/ulysses_multi_gpu_check.py
+"""
+import argparse, importlib, json, os, sys
+import torch, torch.distributed as dist
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+vap = importlib.import_module("video-as-prompt_b200")
+ap = argparse.ArgumentParser(); ap.add_argument("--heads", type=int, default=8); ap.add_argument("--frames", type=int, default=4)
+a = ap.parse_args()
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local); dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+cfg = dict(vap.synth.WAN_TINY, num_attention_heads=a.heads, added_kv_proj_dim=a.heads * 128, num_layers=3, block_idx_with_mot_ref=[0, 2])
+with torch.device("meta"):
+    model = vap.WanTransformer3DMOTModel(**cfg)
+model = model.to(torch.bfloat16).to_empty(device=dev)
+vap.synth.fill_module_(model, seed=1234, num_layers=cfg["num_layers"])
+model.eval()
+inp = vap.synth.wan_inputs(cfg, a.frames, 16, 8 * world, seed=0, device=dev)  # tokens per stream = frames * 8 * 4 * world
+res = {}
+with torch.no_grad():
+    ref = model(**inp, return_dict=False)[0].float()
+    for mode in ("p2p", "nccl"):
+        vap.ulysses.enable(mode=mode)
+        outs = [model(**inp, return_dict=False)[0].float() for _ in range(3)]  # 3 forwards: exercises the alternating buffer sets
+        vap.ulysses.disable()
+        err = max(((o - ref).abs().max() / ref.abs().max()).item() for o in outs)
+        res[mode] = err
+ok = all(e < 2e-2 for e in res.values())
+t = torch.tensor([0 if ok else 1], device=dev); dist.all_reduce(t)
+if rank == 0:
+    print(json.dumps(dict(world=world, heads=a.heads, rel_err_vs_single_gpu=res, ok=bool(t.item() == 0))), flush=True)
+dist.destroy_process_group()
+sys.exit(0 if t.item() == 0 else 1)

@@ -402,7 +402,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             tc_fence_after();
             const float inv_l[2] = {1.f / l[0], 1.f / l[1]};
             const int row[2] = {q0 + i * kBlockM + row0_in_tile, q0 + i * kBlockM + row0_in_tile + 8};
-            __nv_bfloat16* obase = p.o + batch * p.o_sb + head * p.o_sh + 2 * cp;
+            // plain mode: one output tensor; peer mode (Ulysses exchange #2 fused into the epilogue): the query rows of rank r are
+            // stored straight into rank r's output buffer over NVLink
+            __nv_bfloat16* obase[2];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                if (p.o_rows_per_peer > 0) {
+                    const int peer = row[r] / p.o_rows_per_peer;
+                    obase[r] = (peer < 8 ? p.o_peer[peer] : p.o_peer[0]) + batch * p.o_sb + head * p.o_sh + 2 * cp +
+                               static_cast<int64_t>(row[r] - peer * p.o_rows_per_peer) * p.o_sl;
+                } else {
+                    obase[r] = p.o + batch * p.o_sb + head * p.o_sh + 2 * cp + static_cast<int64_t>(row[r]) * p.o_sl;
+                }
+            }
 #pragma unroll 1
             for (int g4 = 0; g4 < D / 32; ++g4) {
                 uint32_t ov[16];
@@ -411,7 +423,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
                 for (int r = 0; r < 2; ++r) {
                     if (row[r] < p.Lq) {
-                        __nv_bfloat16* orow = obase + static_cast<int64_t>(row[r]) * p.o_sl + 32 * g4;
+                        __nv_bfloat16* orow = obase[r] + 32 * g4;
 #pragma unroll
                         for (int g = 0; g < 4; ++g)
                             *reinterpret_cast<uint32_t*>(orow + 8 * g) =
@@ -467,8 +479,15 @@ int launch_attention_fwd(const AttnTensor& q, const AttnTensor& k, const AttnTen
     VAP_REQUIRE(D == 64 || D == 128, "attention: head_dim=%d must be 64 or 128", D);
     VAP_REQUIRE(p.B > 0 && p.H > 0 && p.Lq >= 0 && p.Lkv > 0, "attention: bad shape B=%d H=%d Lq=%d Lkv=%d", p.B, p.H, p.Lq, p.Lkv);
     VAP_REQUIRE(p.H <= 65535 && p.B <= 65535, "attention: H and B must be <= 65535");
-    VAP_REQUIRE((reinterpret_cast<uintptr_t>(p.o) & 15) == 0 && p.o_sl % 8 == 0 && p.o_sh % 8 == 0 && p.o_sb % 8 == 0,
-                "attention: output must be 16-byte aligned with strides that are multiples of 8 elements");
+    if (p.o_rows_per_peer > 0) {
+        const int npeer = (p.Lq + p.o_rows_per_peer - 1) / p.o_rows_per_peer;
+        VAP_REQUIRE(npeer <= 8, "attention: at most 8 output peers");
+        for (int r = 0; r < npeer; ++r) VAP_REQUIRE(p.o_peer[r] && (reinterpret_cast<uintptr_t>(p.o_peer[r]) & 15) == 0, "attention: bad output peer %d", r);
+        VAP_REQUIRE(p.o_sl % 8 == 0 && p.o_sh % 8 == 0 && p.o_sb % 8 == 0, "attention: output strides must be multiples of 8 elements");
+    } else {
+        VAP_REQUIRE((reinterpret_cast<uintptr_t>(p.o) & 15) == 0 && p.o_sl % 8 == 0 && p.o_sh % 8 == 0 && p.o_sb % 8 == 0,
+                    "attention: output must be 16-byte aligned with strides that are multiples of 8 elements");
+    }
     if (p.Lq == 0) return 0;
     CUtensorMap tmQ, tmK, tmV;
     if (make_attn_tmap(&tmQ, q, p.B, p.H, p.Lq, D, "q")) return -3;

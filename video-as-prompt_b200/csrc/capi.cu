@@ -150,8 +150,32 @@ int vap_qk_norm_rope(void* q, void* k, int64_t rows, int heads, int head_dim, in
     VAP_REQUIRE(q, "vap_qk_norm_rope: null tensor");
     VAP_REQUIRE(rows >= 0 && heads > 0, "vap_qk_norm_rope: bad shape");
     VAP_REQUIRE(mode == 0 || mode == 1, "vap_qk_norm_rope: mode must be 0 (Wan) or 1 (CogVideoX)");
-    QkParams p{static_cast<__nv_bfloat16*>(q), static_cast<__nv_bfloat16*>(k), rows, heads, head_dim, row_stride, wq, bq, wk, bk, cos, sin,
-               rows_per_batch, rope_row0, rope_rows, eps};
+    QkParams p{};
+    p.q = static_cast<__nv_bfloat16*>(q), p.k = static_cast<__nv_bfloat16*>(k);
+    p.rows = rows, p.heads = heads, p.head_dim = head_dim, p.row_stride = row_stride;
+    p.wq = wq, p.bq = bq, p.wk = wk, p.bk = bk, p.cos = cos, p.sin = sin;
+    p.rows_per_batch = rows_per_batch, p.rope_row0 = rope_row0, p.rope_rows = rope_rows, p.eps = eps;
+    return launch_qk_norm_rope(p, mode, static_cast<cudaStream_t>(stream));
+}
+
+int vap_qkv_scatter(const void* q, const void* k, const void* v, int64_t rows, int heads, int head_dim, int64_t row_stride, const float* wq,
+                    const float* bq, const float* wk, const float* bk, const float* cos, const float* sin, int64_t rows_per_batch,
+                    int64_t rope_row0, int64_t rope_rows, float eps, int mode, void* const* dst, int nsplit, int64_t dst_slot,
+                    int64_t slot_rows, int64_t dst_row0, void* stream) {
+    VAP_REQUIRE(q && k && v && dst, "vap_qkv_scatter: null tensor");
+    VAP_REQUIRE(rows >= 0 && heads > 0, "vap_qkv_scatter: bad shape");
+    VAP_REQUIRE(mode == 0 || mode == 1, "vap_qkv_scatter: mode must be 0 (Wan) or 1 (CogVideoX)");
+    VAP_REQUIRE(nsplit >= 1 && nsplit <= 8, "vap_qkv_scatter: nsplit=%d must be in [1, 8]", nsplit);
+    VAP_REQUIRE(dst_slot >= 0 && slot_rows > 0 && dst_row0 >= 0 && dst_row0 + rows <= slot_rows, "vap_qkv_scatter: rows do not fit the slot");
+    QkParams p{};
+    // q and k are only READ in scatter mode (the kernel stores to dst)
+    p.q = static_cast<__nv_bfloat16*>(const_cast<void*>(q)), p.k = static_cast<__nv_bfloat16*>(const_cast<void*>(k));
+    p.v = static_cast<const __nv_bfloat16*>(v);
+    p.rows = rows, p.heads = heads, p.head_dim = head_dim, p.row_stride = row_stride;
+    p.wq = wq, p.bq = bq, p.wk = wk, p.bk = bk, p.cos = cos, p.sin = sin;
+    p.rows_per_batch = rows_per_batch, p.rope_row0 = rope_row0, p.rope_rows = rope_rows, p.eps = eps;
+    for (int s = 0; s < nsplit; ++s) p.dst[s] = static_cast<__nv_bfloat16*>(dst[s]);
+    p.nsplit = nsplit, p.dst_slot = dst_slot, p.slot_rows = slot_rows, p.dst_row0 = dst_row0;
     return launch_qk_norm_rope(p, mode, static_cast<cudaStream_t>(stream));
 }
 
@@ -162,6 +186,29 @@ int vap_attention_fwd(const void* q, const void* k, const void* v, void* o, floa
     AttnParams p{};
     p.B = B, p.H = H, p.Lq = Lq, p.Lkv = Lkv;
     p.o = static_cast<__nv_bfloat16*>(o);
+    p.o_sb = o_sb, p.o_sh = o_sh, p.o_sl = o_sl;
+    p.lse = lse;
+    p.scale = scale;
+    p.scale_log2 = scale * 1.4426950408889634f;
+    p.trace = g_attn_trace;
+    const AttnTensor tq{static_cast<const __nv_bfloat16*>(q), q_sb, q_sh, q_sl};
+    const AttnTensor tk{static_cast<const __nv_bfloat16*>(k), k_sb, k_sh, k_sl};
+    const AttnTensor tv{static_cast<const __nv_bfloat16*>(v), v_sb, v_sh, v_sl};
+    return launch_attention_fwd(tq, tk, tv, p, D, static_cast<cudaStream_t>(stream));
+}
+
+int vap_attention_fwd_scatter(const void* q, const void* k, const void* v, void* const* o_peers, int npeers, int o_rows_per_peer, float* lse,
+                              int B, int H, int Lq, int Lkv, int D, int64_t q_sb, int64_t q_sh, int64_t q_sl, int64_t k_sb, int64_t k_sh,
+                              int64_t k_sl, int64_t v_sb, int64_t v_sh, int64_t v_sl, int64_t o_sb, int64_t o_sh, int64_t o_sl, float scale,
+                              void* stream) {
+    VAP_REQUIRE(q && k && v && o_peers, "vap_attention_fwd_scatter: null tensor");
+    VAP_REQUIRE(npeers >= 1 && npeers <= 8 && o_rows_per_peer > 0 && static_cast<int64_t>(npeers) * o_rows_per_peer >= Lq,
+                "vap_attention_fwd_scatter: %d peers x %d rows do not cover Lq=%d", npeers, o_rows_per_peer, Lq);
+    AttnParams p{};
+    p.B = B, p.H = H, p.Lq = Lq, p.Lkv = Lkv;
+    p.o = nullptr;
+    for (int r = 0; r < npeers; ++r) p.o_peer[r] = static_cast<__nv_bfloat16*>(o_peers[r]);
+    p.o_rows_per_peer = o_rows_per_peer;
     p.o_sb = o_sb, p.o_sh = o_sh, p.o_sl = o_sl;
     p.lse = lse;
     p.scale = scale;

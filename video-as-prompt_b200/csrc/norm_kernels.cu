@@ -189,7 +189,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (MAXV <= 5) ? 4 : 3) qk_n
     const int tl = threadIdx.x & (32 * WPR - 1);
     const int group = warp / WPR;
     constexpr int kStride = 32 * WPR;
-    const int n_which = p.k ? 2 : 1;  // k == null: normalise q only (cross-attention queries)
+    const bool scatter = p.nsplit > 0;
+    const int n_which = scatter ? 3 : (p.k ? 2 : 1);  // k == null: normalise q only (cross-attention queries)
     const int64_t item = static_cast<int64_t>(blockIdx.x) * (kWarpsPerBlock / WPR) + group;
     if (item >= p.rows * n_which) return;  // whole groups leave together (the named barrier below is per group)
     const int64_t row = item / n_which;
@@ -210,6 +211,24 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (MAXV <= 5) ? 4 : 3) qk_n
         sn[0] = s4.x, sn[1] = s4.y, sn[2] = s4.z, sn[3] = s4.w;
     }
 
+    // Scatter mode (Ulysses exchange #1 fused into this kernel): the result vector of head h goes to rank s = h / (H/P), into
+    // its receive buffer [slot = this rank][slot row][q|k|v][(H/P) * D] — a 16-byte store over NVLink instead of a store into
+    // the local buffer followed by a pack kernel and an NCCL all-to-all.  The V item is a pure copy.
+    const int hp = scatter ? d / p.nsplit : d;  // channels per destination rank
+    auto dst_of = [&](int v) -> __nv_bfloat16* {
+        const int c0 = 8 * v;
+        const int s = c0 / hp;
+        return p.dst[s] + ((p.dst_slot * p.slot_rows + p.dst_row0 + row) * 3 + which) * hp + (c0 - s * hp);
+    };
+    if (which == 2) {
+        const __nv_bfloat16* vr = p.v + row * p.row_stride;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int v = tl + kStride * i;
+            if (v < nvec) *reinterpret_cast<uint4*>(dst_of(v)) = ld_nc_v4(vr + 8 * v);
+        }
+        return;
+    }
     {
         __nv_bfloat16* xr = (which == 0 ? p.q : p.k) + row * p.row_stride;
         const float* w = which == 0 ? p.wq : p.wk;
@@ -307,7 +326,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (MAXV <= 5) ? 4 : 3) qk_n
                 o.y = pack_bf16x2(y[2], y[3]);
                 o.z = pack_bf16x2(y[4], y[5]);
                 o.w = pack_bf16x2(y[6], y[7]);
-                *reinterpret_cast<uint4*>(xr + 8 * v) = o;
+                *reinterpret_cast<uint4*>(scatter ? dst_of(v) : xr + 8 * v) = o;
             }
         }
     }
@@ -324,7 +343,12 @@ int launch_qk_norm_rope(const QkParams& p, int cog_mode, cudaStream_t stream) {
     if (cog_mode) VAP_REQUIRE(p.bq && (p.bk || !p.k), "qk_norm_rope: per-head LayerNorm needs biases");
     if (p.rows == 0) return 0;
     const int nvec = d / 8;
-    const int64_t items = p.rows * (p.k ? 2 : 1);
+    if (p.nsplit > 0) {
+        VAP_REQUIRE(p.nsplit <= 8 && p.heads % p.nsplit == 0, "qkv_scatter: %d heads are not divisible by %d ranks (max 8)", p.heads, p.nsplit);
+        VAP_REQUIRE(p.k && p.v, "qkv_scatter: q, k and v are required");
+        for (int s = 0; s < p.nsplit; ++s) VAP_REQUIRE(p.dst[s] && (reinterpret_cast<uintptr_t>(p.dst[s]) & 15) == 0, "qkv_scatter: bad destination %d", s);
+    }
+    const int64_t items = p.rows * (p.nsplit > 0 ? 3 : (p.k ? 2 : 1));
     const dim3 block(kWarpsPerBlock * 32);
 #define VAP_QK_LAUNCH(MV, WPR)                                                                                   \
     do {                                                                                                         \

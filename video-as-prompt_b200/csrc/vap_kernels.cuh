@@ -37,6 +37,13 @@ struct QkParams {
     int64_t rope_row0;       // positions < rope_row0 inside a batch are not rotated (Cog text tokens)
     int64_t rope_rows;       // rows in the table
     float eps;
+    // --- fused all-to-all dispatch (Ulysses exchange #1 by peer stores); nsplit == 0: plain in-place mode ---
+    const __nv_bfloat16* v;    // third item per row: copied unchanged (the V columns of the QKV projection)
+    __nv_bfloat16* dst[8];     // dst[s]: rank s's receive buffer [slots, slot_rows, 3, (heads/nsplit)*head_dim]
+    int nsplit;                // ranks
+    int64_t dst_slot;          // slot (= this rank) inside every receive buffer
+    int64_t slot_rows;         // rows per slot (local rows of both streams)
+    int64_t dst_row0;          // first row of this call inside the slot (stream offset)
 };
 int launch_qk_norm_rope(const QkParams& p, int cog_mode, cudaStream_t stream);
 
@@ -48,6 +55,9 @@ struct AttnParams {
     float scale_log2;          // softmax scale * log2(e)
     float scale;
     long long* trace;          // optional clock64() trace of CTA (0,0,0): [3 roles][64 iterations][8 stamps], or null
+    // --- fused all-to-all combine (Ulysses exchange #2 by peer stores); o_rows_per_peer == 0: plain mode (o above) ---
+    __nv_bfloat16* o_peer[8];  // query rows [r*rpp, (r+1)*rpp) belong to rank r and are written to o_peer[r] + (row - r*rpp)*o_sl
+    int o_rows_per_peer;
 };
 struct AttnTensor {
     const __nv_bfloat16* ptr;

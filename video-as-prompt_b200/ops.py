@@ -158,6 +158,64 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: Optio
     return (out, lse) if return_lse else out
 
 
+def _ptr_table(ptrs):
+    """Host array of device pointers (void* const*) for the peer-table entry points."""
+    import ctypes
+    arr = (ctypes.c_void_p * len(ptrs))(*[int(p) for p in ptrs])
+    return arr
+
+
+def qkv_scatter(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, heads: int, head_dim: int, wq: torch.Tensor, wk: torch.Tensor,
+                bq: Optional[torch.Tensor] = None, bk: Optional[torch.Tensor] = None, cos: Optional[torch.Tensor] = None,
+                sin: Optional[torch.Tensor] = None, rows_per_batch: int, rope_row0: int = 0, eps: float, mode: int, dst_ptrs, dst_slot: int,
+                slot_rows: int, dst_row0: int) -> None:
+    """q/k normalisation + RoPE + the Ulysses all-to-all #1 dispatch in ONE kernel (see vap_qkv_scatter): q, k, v are column
+    views [rows, heads*head_dim] of the local QKV projection (left untouched); the results go to the receive buffers of the
+    len(dst_ptrs) ranks (device pointers, peer memory), layout [slot, slot_rows, 3, heads/P*head_dim] each."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _need_cuda_bf16(t, n)
+    rows, d, rs = _rows_view(q, "q")
+    if d != heads * head_dim or _rows_view(k, "k") != (rows, d, rs) or _rows_view(v, "v") != (rows, d, rs):
+        raise ValueError("q, k and v must be [rows, heads*head_dim] views with one common row stride")
+    rope_rows = 0
+    if cos is not None:
+        if cos.shape != sin.shape or cos.dim() != 2 or cos.shape[1] != head_dim // 2 or not cos.is_contiguous() or not sin.is_contiguous():
+            raise ValueError(f"cos/sin must be contiguous [rope_rows, {head_dim // 2}] tables, got {tuple(cos.shape)}")
+        rope_rows = cos.shape[0]
+        if rows_per_batch - rope_row0 > rope_rows:
+            raise ValueError(f"RoPE table has {rope_rows} rows but {rows_per_batch - rope_row0} tokens per batch need rotating")
+    lib = _lib.load()
+    table = _ptr_table(dst_ptrs)
+    rc = lib.vap_qkv_scatter(q.data_ptr(), k.data_ptr(), v.data_ptr(), rows, heads, head_dim, rs, _need_cuda_f32(wq, "wq"), _need_cuda_f32(bq, "bq"),
+                             _need_cuda_f32(wk, "wk"), _need_cuda_f32(bk, "bk"), _need_cuda_f32(cos, "cos"), _need_cuda_f32(sin, "sin"),
+                             int(rows_per_batch), int(rope_row0), int(rope_rows), float(eps), int(mode), table, len(dst_ptrs), int(dst_slot),
+                             int(slot_rows), int(dst_row0), _stream())
+    _lib.check(rc, "vap_qkv_scatter")
+
+
+def attention_scatter(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, o_ptrs, rows_per_peer: int, o_strides, scale: Optional[float] = None) -> None:
+    """Attention whose epilogue stores query row r into peer r // rows_per_peer's output buffer (device pointers o_ptrs, element
+    strides o_strides = (batch, head, row) inside each peer buffer) — the Ulysses all-to-all #2 fused into the kernel."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _need_cuda_bf16(t, n)
+        if t.dim() != 4 or t.stride(-1) != 1:
+            raise ValueError(f"{n} must be [B,H,L,D] with contiguous D, got shape {tuple(t.shape)} strides {t.stride()}")
+    B, H, Lq, D = q.shape
+    Lkv = k.shape[2]
+    if k.shape != (B, H, Lkv, D) or v.shape != (B, H, Lkv, D):
+        raise ValueError(f"q {tuple(q.shape)}, k {tuple(k.shape)}, v {tuple(v.shape)} are inconsistent")
+    if len(o_ptrs) * rows_per_peer < Lq:
+        raise ValueError(f"{len(o_ptrs)} peers x {rows_per_peer} rows do not cover Lq={Lq}")
+    if scale is None:
+        scale = D ** -0.5
+    lib = _lib.load()
+    table = _ptr_table(o_ptrs)
+    rc = lib.vap_attention_fwd_scatter(q.data_ptr(), k.data_ptr(), v.data_ptr(), table, len(o_ptrs), int(rows_per_peer), 0, B, H, Lq, Lkv, D,
+                                       q.stride(0), q.stride(1), q.stride(2), k.stride(0), k.stride(1), k.stride(2), v.stride(0), v.stride(1),
+                                       v.stride(2), int(o_strides[0]), int(o_strides[1]), int(o_strides[2]), float(scale), _stream())
+    _lib.check(rc, "vap_attention_fwd_scatter")
+
+
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, *, epilogue: int = EPI_BIAS,
            residual: Optional[torch.Tensor] = None, gate: Optional[torch.Tensor] = None, rows_per_batch: Optional[int] = None,
            out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -10,8 +10,15 @@ After exchange #1 the joint sequence is ordered rank-major ([tgt_0|ref_0|tgt_1|r
 reference's [target|ref] order, which is irrelevant for unmasked attention as long as O rows map back to their tokens,
 which exchange #2 does by construction.
 
-The re-layout (pack / unpack) functions are injectable so the partitioning logic is testable on CPU with gloo; the
-product path uses the CUDA kernels vap_ulysses_pack / vap_ulysses_unpack.
+Two transports:
+  mode "p2p" (default on CUDA): both exchanges are FUSED into the producing kernels over NVLink peer memory (torch symmetric
+      memory gives every rank the device pointers of all ranks' buffers).  The q/k-norm + RoPE kernel stores its results — and a
+      copy of V — straight into the receive buffer of the rank that owns the head (vap_qkv_scatter: no local write, no pack
+      kernel, no collective call), and the attention kernel's epilogue stores every O row straight into the output buffer of
+      the rank that owns the row (vap_attention_fwd_scatter: no all-to-all, no unpack).  Ordering between ranks: one 7 us
+      device-side barrier per exchange and two alternating buffer sets (see PeerExchange).
+  mode "nccl": pack kernel -> dist.all_to_all_single -> attention -> all_to_all_single -> unpack kernel (the baseline; also the
+      path the CPU/gloo tests drive with injected pack/unpack functions).
 """
 from __future__ import annotations
 
@@ -29,15 +36,23 @@ class SequenceParallel:
     group: Optional[dist.ProcessGroup]
     rank: int
     world: int
+    mode: str = "nccl"  # "p2p" | "nccl"
+    _exchanges: Optional[dict] = None
 
 
 _CURRENT: Optional[SequenceParallel] = None
 
 
-def enable(group: Optional[dist.ProcessGroup] = None) -> SequenceParallel:
-    """Activate Ulysses over `group` (default: the world group).  world == 1 is a no-op context."""
+def enable(group: Optional[dist.ProcessGroup] = None, mode: Optional[str] = None) -> SequenceParallel:
+    """Activate Ulysses over `group` (default: the world group).  world == 1 is a no-op context.
+    mode: "p2p" (fused peer-memory exchange, default when the group runs on NCCL) or "nccl"; env VAP_ULYSSES overrides the default."""
     global _CURRENT
-    _CURRENT = SequenceParallel(group, dist.get_rank(group), dist.get_world_size(group))
+    import os
+    if mode is None:
+        mode = os.environ.get("VAP_ULYSSES") or ("p2p" if dist.get_backend(group) == "nccl" else "nccl")
+    if mode not in ("p2p", "nccl"):
+        raise ValueError(f"Ulysses mode must be 'p2p' or 'nccl', got {mode!r}")
+    _CURRENT = SequenceParallel(group, dist.get_rank(group), dist.get_world_size(group), mode, {})
     return _CURRENT
 
 
@@ -110,3 +125,70 @@ def exchange_out(o: torch.Tensor, sp: SequenceParallel, unpack: Callable = _unpa
     out = torch.empty((L, P * hp), dtype=o.dtype, device=o.device)
     unpack(recv, out)
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# fused exchange over NVLink peer memory
+# ----------------------------------------------------------------------------------------------
+class PeerExchange:
+    """Symmetric (peer-mapped) buffers of one joint-attention shape, shared by all MoT blocks.
+
+      recv[f] [P, rows, 3, (H/P)*D]   slot s = what rank s dispatched to this rank (its local rows of both streams, q|k|v of this
+                                      rank's heads); rows = local joint rows.  Viewed as [1, P*rows, 3, H/P, D] it is the
+                                      rank-major joint sequence the attention kernel reads through strided TMA descriptors.
+      out[f]  [rows, H*D]             this rank's rows of O for ALL heads; rank r's attention kernel fills columns
+                                      [r*(H/P)*D, (r+1)*(H/P)*D).
+
+    f alternates per block.  Why two sets suffice: block b writes set b%2 on the peers; a peer's last read of that set (block b-2's
+    attention for recv, block b-2's output projections for out) is stream-ordered before the barrier that peer entered in
+    block b-1, which this rank has passed before it launches block b's kernels."""
+
+    def __init__(self, sp: SequenceParallel, rows: int, heads: int, head_dim: int, device: torch.device):
+        import torch.distributed._symmetric_memory as symm
+        P = sp.world
+        self.sp, self.rows, self.heads, self.head_dim = sp, rows, heads, head_dim
+        self.hp = heads // P * head_dim
+        group = sp.group if sp.group is not None else dist.group.WORLD
+        self.recv, self.out, self.recv_ptrs, self.out_ptrs = [], [], [], []
+        self._handles = []
+        for _ in range(2):
+            r = symm.empty((P, rows, 3, self.hp), dtype=torch.bfloat16, device=device)
+            h = symm.rendezvous(r, group)
+            self.recv.append(r), self.recv_ptrs.append([int(p) for p in h.buffer_ptrs]), self._handles.append(h)
+            o = symm.empty((rows, heads * head_dim), dtype=torch.bfloat16, device=device)
+            h = symm.rendezvous(o, group)
+            # every rank writes its own head columns of the owner's rows
+            self.out.append(o), self.out_ptrs.append([int(p) + sp.rank * self.hp * 2 for p in h.buffer_ptrs]), self._handles.append(h)
+        self.flip = 1
+
+    def next_block(self) -> None:
+        self.flip ^= 1
+
+    def barrier(self) -> None:
+        self._handles[0].barrier(channel=0)  # stream-ordered: signals every peer and waits for every peer
+
+    def dispatch(self, qkv: torch.Tensor, row0: int, **norm_rope) -> None:
+        """Exchange #1 for one stream: qkv [L, 3*H*D] = this rank's rows of the stream's QKV projection (pre-norm)."""
+        inner = qkv.shape[-1] // 3
+        ops.qkv_scatter(qkv[:, :inner], qkv[:, inner:2 * inner], qkv[:, 2 * inner:], heads=self.heads, head_dim=self.head_dim,
+                        dst_ptrs=self.recv_ptrs[self.flip], dst_slot=self.sp.rank, slot_rows=self.rows, dst_row0=row0, **norm_rope)
+
+    def attention(self) -> torch.Tensor:
+        """barrier -> joint attention of this rank's heads over the full sequence, O rows stored to their owners -> barrier.
+        Returns this rank's rows of O for all heads, [rows, H*D]."""
+        P, hp, D = self.sp.world, self.hp, self.head_dim
+        self.barrier()
+        joint = self.recv[self.flip].view(1, P * self.rows, 3, self.heads // P, D)
+        q, k, v = (joint[:, :, w].transpose(1, 2) for w in range(3))
+        ops.attention_scatter(q, k, v, o_ptrs=self.out_ptrs[self.flip], rows_per_peer=self.rows, o_strides=(0, D, self.heads * D))
+        self.barrier()
+        return self.out[self.flip]
+
+
+def peer_exchange(sp: SequenceParallel, rows: int, heads: int, head_dim: int, device: torch.device) -> PeerExchange:
+    """The (cached) PeerExchange of this shape.  Creating one is collective: every rank must get here in the same order."""
+    key = (rows, heads, head_dim)
+    if key not in sp._exchanges:
+        check_divisible(rows * sp.world, heads, sp.world)
+        sp._exchanges[key] = PeerExchange(sp, rows, heads, head_dim, device)
+    return sp._exchanges[key]

@@ -86,21 +86,25 @@ def _token_major(o: torch.Tensor) -> torch.Tensor:
 # ----------------------------------------------------------------------------------------------
 # attention halves shared by the block forward and the processors
 # ----------------------------------------------------------------------------------------------
-def _self_attn_qkv(attn: nn.Module, x: torch.Tensor, tables: Optional[Tables], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def _self_attn_qkv(attn: nn.Module, x: torch.Tensor, tables: Optional[Tables], out: Optional[torch.Tensor] = None, scatter=None) -> torch.Tensor:
     """Fused QKV projection + RMSNorm-across-heads + RoPE of one stream (:214-236).  x [B, L, d] -> qkv [B, L, 3*inner]
-    (written into `out` if given, which may be a row-slice of the joint buffer)."""
+    (written into `out` if given, which may be a row-slice of the joint buffer).
+    scatter = (PeerExchange, row0): Ulysses peer-memory mode — the norm + RoPE kernel stores its results (and V) straight into
+    the receive buffers of the ranks owning the heads; `out` then only holds the raw projection."""
     W, bvec = _packed(attn, "qkv", [attn.to_q, attn.to_k, attn.to_v])
     inner = W.shape[0] // 3
     B, L, _ = x.shape
     if out is None:
         out = torch.empty((B, L, 3 * inner), dtype=torch.bfloat16, device=x.device)
     heads = attn.heads
+    norm_rope = dict(wq=_f32(attn.norm_q, "w", attn.norm_q.weight), wk=_f32(attn.norm_k, "w", attn.norm_k.weight),
+                     cos=tables[0] if tables else None, sin=tables[1] if tables else None, rows_per_batch=L, eps=attn.norm_q.eps, mode=ops.QK_WAN)
     for b in range(B):  # rows of one batch are uniformly strided inside the joint buffer
         ops.linear(x[b], W, bvec, out=out[b])
-        q, k = out[b, :, :inner], out[b, :, inner:2 * inner]
-        ops.qk_norm_rope_(q, k, heads=heads, head_dim=inner // heads, wq=_f32(attn.norm_q, "w", attn.norm_q.weight),
-                          wk=_f32(attn.norm_k, "w", attn.norm_k.weight), cos=tables[0] if tables else None,
-                          sin=tables[1] if tables else None, rows_per_batch=L, eps=attn.norm_q.eps, mode=ops.QK_WAN)
+        if scatter is not None:
+            scatter[0].dispatch(out[b], scatter[1], **norm_rope)
+        else:
+            ops.qk_norm_rope_(out[b, :, :inner], out[b, :, inner:2 * inner], heads=heads, head_dim=inner // heads, **norm_rope)
     return out
 
 
@@ -143,8 +147,9 @@ def _joint_attention(qkv: torch.Tensor, heads: int) -> torch.Tensor:
     """Joint attention over the rows of `qkv` [B, J, 3*inner] -> O [B, J, inner] (token-major).
 
     Single GPU: the kernel reads q/k/v as strided views of the joint buffer.  Under Ulysses sequence parallelism
-    (ulysses.enable()) the rows are this rank's token shard of both streams: all-to-all #1 trades them for all rows of
-    H/P heads, the kernel runs on those heads over the full joint sequence, all-to-all #2 brings O back."""
+    (ulysses.enable(), mode "nccl") the rows are this rank's token shard of both streams: all-to-all #1 trades them for all
+    rows of H/P heads, the kernel runs on those heads over the full joint sequence, all-to-all #2 brings O back.  (Mode "p2p"
+    does not come through here: see _sp_p2p.)"""
     sp = ulysses.current()
     if sp is None:
         q, k, v = _split_qkv(qkv, heads)
@@ -154,6 +159,18 @@ def _joint_attention(qkv: torch.Tensor, heads: int) -> torch.Tensor:
     q, k, v = ulysses.exchange_qkv(qkv[0], heads, sp)
     o = _token_major(ops.attention(q, k, v))[0]  # [P*L_loc, (H/P)*D]
     return ulysses.exchange_out(o, sp).unsqueeze(0)
+
+
+def _sp_p2p(x: torch.Tensor, rows: int, heads: int, head_dim: int):
+    """The PeerExchange for a joint attention over `rows` local rows when Ulysses runs in peer-memory mode, else None."""
+    sp = ulysses.current()
+    if sp is None or sp.mode != "p2p":
+        return None
+    if x.shape[0] != 1:
+        raise NotImplementedError("Ulysses sequence parallelism expects batch 1 per forward (the Wan pipeline's CFG passes are B=1)")
+    px = ulysses.peer_exchange(sp, rows, heads, head_dim, x.device)
+    px.next_block()
+    return px
 
 
 # ----------------------------------------------------------------------------------------------
@@ -201,7 +218,12 @@ def wan_block_forward(self: nn.Module, hidden_states: torch.Tensor, encoder_hidd
 
     if not self.with_mot_ref:  # :580-601
         xn = ops.adaln_layernorm(x, eps=eps, rounding=ops.ROUND_WAN, scale1p=scale1p, shift=shift)
-        o = _joint_attention(_self_attn_qkv(attn1, xn, tables), heads)
+        px = _sp_p2p(x, x.shape[1], heads, hd)
+        if px is not None:
+            _self_attn_qkv(attn1, xn, tables, scatter=(px, 0))
+            o = px.attention().unsqueeze(0)
+        else:
+            o = _joint_attention(_self_attn_qkv(attn1, xn, tables), heads)
         x = _linear(attn1.to_out[0], o, epilogue=ops.EPI_GATE_RES_F32, residual=x, gate=gate)
         x = _stream_tail(self, "", x, encoder_hidden_states, c_shift, c_scale1p, c_gate, eps, 1)
         return x, hidden_states_mot_ref
@@ -220,9 +242,15 @@ def wan_block_forward(self: nn.Module, hidden_states: torch.Tensor, encoder_hidd
     xn = ops.adaln_layernorm(x, eps=eps, rounding=ops.ROUND_WAN, scale1p=scale1p, shift=shift)
     xn_r = ops.adaln_layernorm(xr, eps=self.norm1_mot_ref.eps, rounding=ops.ROUND_WAN, scale1p=scale1p_r, shift=shift_r)
     qkv = torch.empty((B, S + Sr, 3 * inner), dtype=torch.bfloat16, device=x.device)
-    _self_attn_qkv(attn1, xn, tables, out=qkv[:, :S])
-    _self_attn_qkv(attn1_r, xn_r, tables_r, out=qkv[:, S:])
-    o = _joint_attention(qkv, heads)  # [B, J, inner], rows [target | ref]
+    px = _sp_p2p(x, S + Sr, heads, hd)
+    if px is not None:  # Ulysses over peer memory: both exchanges are fused into the norm/RoPE and attention kernels
+        _self_attn_qkv(attn1, xn, tables, out=qkv[:, :S], scatter=(px, 0))
+        _self_attn_qkv(attn1_r, xn_r, tables_r, out=qkv[:, S:], scatter=(px, S))
+        o = px.attention().unsqueeze(0)
+    else:
+        _self_attn_qkv(attn1, xn, tables, out=qkv[:, :S])
+        _self_attn_qkv(attn1_r, xn_r, tables_r, out=qkv[:, S:])
+        o = _joint_attention(qkv, heads)  # [B, J, inner], rows [target | ref]
     x = _linear(attn1.to_out[0], o[:, :S], epilogue=ops.EPI_GATE_RES_F32, residual=x, gate=gate)
     xr = _linear(attn1_r.to_out[0], o[:, S:], epilogue=ops.EPI_GATE_RES_F32, residual=xr, gate=gate_r)
 
