@@ -237,22 +237,25 @@ def main():
     # per-launch timing of the dominant kernel (joint attention) with CUDA events on the launching stream
     attn_events = []
     launches = [0]
-    orig_attention = vap.ops.attention
-
-    def timed_attention(q, k, v, **kw):
-        if q.shape[2] == k.shape[2] and record[0]:  # joint self-attention (cross-attention has Lkv = 512 / 257)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            out = orig_attention(q, k, v, **kw)
-            e1.record()
-            attn_events.append((e0, e1, q.shape))
-            return out
-        return orig_attention(q, k, v, **kw)
-
     record = [False]
-    vap.ops.attention = timed_attention
+
+    def timed_attn(orig):
+        def wrapper(q, k, v, **kw):
+            if q.shape[2] == k.shape[2] and record[0]:  # joint self-attention (cross-attention has Lkv = 512 / 257)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                out = orig(q, k, v, **kw)
+                e1.record()
+                attn_events.append((e0, e1, q.shape))
+                return out
+            return orig(q, k, v, **kw)
+        return wrapper
+
+    vap.ops.attention = timed_attn(vap.ops.attention)
+    vap.ops.attention_scatter = timed_attn(vap.ops.attention_scatter)  # Ulysses peer-memory mode: the same kernel with a fused exchange epilogue
     lib = vap._lib.load()
-    for name in ("vap_adaln_layernorm", "vap_qk_norm_rope", "vap_attention_fwd", "vap_gemm_bf16", "vap_ulysses_pack", "vap_ulysses_unpack"):
+    for name in ("vap_adaln_layernorm", "vap_qk_norm_rope", "vap_qkv_scatter", "vap_attention_fwd", "vap_attention_fwd_scatter", "vap_gemm_bf16",
+                 "vap_ulysses_pack", "vap_ulysses_unpack"):
         fn = getattr(lib, name)
 
         def counted(*args, _fn=fn):
@@ -332,9 +335,18 @@ def main():
             B_, H_, J_, D_ = attn_events[0][2]
             fl = 4.0 * B_ * H_ * J_ * J_ * D_
             avg = sum(times) / len(times)
+            traffic, traffic_src = None, None
+            try:  # DRAM bytes of this launch from the committed ncu --set full capture of the same shape (profiles/)
+                prof = json.load(open(os.path.join(ROOT, "profiles", "r01_attn_v5_in_step.json")))["launches"][0]
+                if (H_, J_, D_) == (40, 40560, 128):
+                    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+                    traffic = sum(prof[k]["value"] * scale[prof[k]["unit"]] for k in ("dram_read", "dram_write"))
+                    traffic_src = "profiles/r01_attn_v5_in_step.json (ncu dram__bytes_read.sum + dram__bytes_write.sum of this launch)"
+            except Exception:
+                pass
             roof = dict(bound="tensor", kernel="attn_fwd_kernel (joint attention)", achieved=fl / (avg * 1e-3) / 1e12, peak=peak, unit="TFLOP/s",
-                        frac=fl / (avg * 1e-3) / 1e12 / peak, traffic=None, launches=len(times), avg_ms=avg, flop_per_launch=fl, peak_source=peak_src,
-                        shape=dict(B=B_, H=H_, J=J_, D=D_))
+                        frac=fl / (avg * 1e-3) / 1e12 / peak, traffic=traffic, traffic_source=traffic_src, algorithmic_bytes=4.0 * B_ * H_ * J_ * D_ * 2,
+                        launches=len(times), avg_ms=avg, flop_per_launch=fl, peak_source=peak_src, shape=dict(B=B_, H=H_, J=J_, D=D_))
         total_flops, _ = wan_flops(w["cfg"], S // world * world, S) if w["family"] == "wan" else (None, None)
         line = {"metric": METRIC if a.config == "wan14b" else f"DiT denoise steps/s ({w['name']})", "value": a.steps / (ms_dev * 1e-3), "unit": UNIT,
                 "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "strong",
