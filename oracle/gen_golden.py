@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import importlib
 import json
+import math
 import os
 import sys
 
@@ -171,6 +172,37 @@ def gen_cog():
     ref_out = model(**inp, return_dict=False)[0]
     _eq(cog_oracle.cog_forward(sd, cfg, **inp), ref_out, "cog config#1 final")
     fixtures["config1"] = dict(latent=(4, 60, 90), num_mot_ref=1, multi=False, input_seed=6, final=ref_out)
+    # 4-step denoise with classifier-free guidance (one B=2 forward per step), dynamic guidance scale and the reference's own
+    # CogVideoXDPMScheduler in the configuration convert_cogvideox_to_diffusers.py:312-326 writes for the 5B model
+    from diffusers.schedulers import CogVideoXDPMScheduler
+    sched = CogVideoXDPMScheduler(snr_shift_scale=1.0, beta_end=0.012, beta_schedule="scaled_linear", beta_start=0.00085, clip_sample=False,
+                                  num_train_timesteps=1000, prediction_type="v_prediction", rescale_betas_zero_snr=True, set_alpha_to_one=True,
+                                  timestep_spacing="trailing")
+    steps, gscale, noise_seed = 4, 6.0, 21
+    sched.set_timesteps(steps)
+    ac_o, ts_o = denoise.cog_dpm_tables(steps)
+    _eq(ts_o, sched.timesteps, "cog dpm timesteps"), _eq(ac_o, sched.alphas_cumprod, "cog dpm alphas_cumprod")
+    frames, h, w = 3, 12, 16
+    inp = synth.cog_inputs(cfg, frames, h, w, seed=7, batch=2, rope_fn=rope_fn)  # batch 0 = negative prompt, 1 = prompt
+    kw2 = {k: inp[k] for k in ("encoder_hidden_states", "encoder_hidden_states_mot_ref", "image_rotary_emb", "image_rotary_emb_mot_ref", "num_mot_ref")}
+    g = torch.Generator().manual_seed(12)
+    lat0, img, lat_ref, img_ref = (torch.randn((1, frames, 16, h, w), generator=g) for _ in range(4))
+    lat, old = lat0.to(torch.bfloat16), None
+    gen = torch.Generator().manual_seed(noise_seed)
+    for i, t in enumerate(sched.timesteps):  # the reference pipeline's loop body (pipeline_cogvideox_image2video_mot.py:964-1057)
+        x = torch.cat([torch.cat([lat] * 2), torch.cat([img] * 2)], dim=2).to(torch.bfloat16)
+        xr = torch.cat([torch.cat([lat_ref] * 2), torch.cat([img_ref] * 2)], dim=2).to(torch.bfloat16)
+        noise = model(hidden_states=x, hidden_states_mot_ref=xr, timestep=t.expand(2), return_dict=False, **kw2)[0].float()
+        gs = 1 + gscale * ((1 - math.cos(math.pi * ((steps - t.item()) / steps) ** 5.0)) / 2)
+        n_u, n_c = noise.chunk(2)
+        noise = n_u + gs * (n_c - n_u)
+        lat, old = sched.step(noise, old, t, sched.timesteps[i - 1] if i > 0 else None, lat, generator=gen, return_dict=False)
+        lat = lat.to(torch.bfloat16)
+    fwd = lambda **k: cog_oracle.cog_forward(sd, cfg, **k)  # noqa: E731
+    lat_o, _ = denoise.cog_denoise(fwd, lat0.clone(), img, lat_ref, img_ref, kw2, steps, gscale, True, noise_seed)
+    _eq(lat_o, lat, "cog 4-step latents")
+    fixtures["denoise"] = dict(latent=(frames, h, w), input_seed=7, latent_seed=12, noise_seed=noise_seed, steps=steps, guidance=gscale, dynamic_cfg=True,
+                               final_latents=lat)
     torch.save(dict(cfg=cfg, weight_seed=2, cases=fixtures), os.path.join(GOLD, "cog_tiny.pt"))
     print("cog_tiny.pt ok")
 

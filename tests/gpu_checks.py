@@ -387,6 +387,23 @@ def check_cog_model(case="config1", tol=2e-2):
     return dict(err=err, cosine=cos)
 
 
+def check_cog_denoise():
+    """north_star: final denoised latents cosine >= 0.999 after 4 steps — CogVideoX loop: CFG as one B=2 forward per step, dynamic
+    guidance, CogVideoXDPMScheduler (fixture recorded from the reference scheduler + reference transformer on CPU)."""
+    g = _golden("cog_tiny.pt")
+    cfg, dn = g["cfg"], g["cases"]["denoise"]
+    model = build_cog(cfg, g["weight_seed"])
+    f, h, w = dn["latent"]
+    inp = synth.cog_inputs(cfg, f, h, w, seed=dn["input_seed"], batch=2)
+    kw2 = _to_dev({k: inp[k] for k in ("encoder_hidden_states", "encoder_hidden_states_mot_ref", "image_rotary_emb", "image_rotary_emb_mot_ref", "num_mot_ref")})
+    gen = torch.Generator().manual_seed(dn["latent_seed"])
+    lat0, img, lat_ref, img_ref = (torch.randn((1, f, 16, h, w), generator=gen).to(DEV) for _ in range(4))
+    lat = vap.denoise.cog_denoise(model, lat0, img, lat_ref, img_ref, kw2, dn["steps"], dn["guidance"], dn["dynamic_cfg"], dn["noise_seed"])
+    cos, err = cosine(lat, dn["final_latents"]), rel_err(lat, dn["final_latents"])
+    assert cos >= 0.999, f"cog 4-step DPM denoise: cosine {cos} (rel err {err})"
+    return dict(cosine=cos, err=err)
+
+
 def check_processor_level():
     """Boundary B1/B2: the drop-in processors + joint_sdpa reproduce the fused block (same kernels, reference-shaped calls)."""
     g = _golden("wan_tiny.pt")
@@ -511,6 +528,7 @@ CHECKS = {
     "cog_blocks_small": lambda: check_cog_blocks("small"),
     "cog_blocks_multi": lambda: check_cog_blocks("multi"),
     "cog_model_config1": lambda: check_cog_model("config1"),
+    "cog_denoise": check_cog_denoise,
     "processor_level": check_processor_level,
     "gemm_large": check_gemm_large,
     "attn_full_size": check_attention_full_size,

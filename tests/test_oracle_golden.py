@@ -125,3 +125,41 @@ def test_cog_ref_rope_negative_positions():
     assert torch.equal(cos_t[:, 16:], cos_r[:, 16:])
     assert torch.allclose(sin_r[0, 0], torch.sin(torch.tensor(-3.0)))
     assert torch.allclose(sin_r[-1, 0], torch.sin(torch.tensor(-1.0)))
+
+
+def test_cog_four_step_dpm_denoise(cog_golden):
+    """CogVideoXDPMScheduler loop restatement (oracle/denoise.py) against the latents recorded from the reference scheduler +
+    reference transformer (4 steps, CFG as one B=2 forward, dynamic guidance, two noise draws per 2nd-order step)."""
+    g = cog_golden
+    sd, cfg, dn = _cog_sd(g), g["cfg"], g["cases"]["denoise"]
+    f, h, w = dn["latent"]
+    inp = synth.cog_inputs(cfg, f, h, w, seed=dn["input_seed"], batch=2)
+    kw2 = {k: inp[k] for k in ("encoder_hidden_states", "encoder_hidden_states_mot_ref", "image_rotary_emb", "image_rotary_emb_mot_ref", "num_mot_ref")}
+    gen = torch.Generator().manual_seed(dn["latent_seed"])
+    lat0, img, lat_ref, img_ref = (torch.randn((1, f, 16, h, w), generator=gen) for _ in range(4))
+    with torch.no_grad():
+        lat, preds = denoise.cog_denoise(lambda **k: cog_oracle.cog_forward(sd, cfg, **k), lat0, img, lat_ref, img_ref, kw2, dn["steps"], dn["guidance"],
+                                         dn["dynamic_cfg"], dn["noise_seed"])
+    assert len(preds) == dn["steps"]
+    assert rel_err(lat, dn["final_latents"]) <= TOL
+
+
+def test_cog_dpm_schedule_matches_product():
+    """The product-side schedule / step (video-as-prompt_b200/denoise.py) and the oracle's are independent restatements."""
+    vd = importlib.import_module("video-as-prompt_b200.denoise")
+    for n in (4, 10, 50):
+        ac_o, ts_o = denoise.cog_dpm_tables(n)
+        ac_p, ts_p = vd.cog_dpm_schedule(n)
+        assert torch.equal(ts_o, ts_p) and torch.allclose(ac_o, ac_p, rtol=0, atol=0)
+    ac, ts = denoise.cog_dpm_tables(4)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn((1, 2, 16, 4, 4), generator=g).to(torch.bfloat16)
+    v = torch.randn((1, 2, 16, 4, 4), generator=g)
+    old = None
+    xo, xp, oo, op = x, x, None, None
+    for i, t in enumerate(ts.tolist()):
+        go, gp = torch.Generator().manual_seed(5 + i), torch.Generator().manual_seed(5 + i)
+        xo, oo = denoise.cog_dpm_step(ac, 4, v, oo, t, ts[i - 1].item() if i > 0 else None, xo, go)
+        xp, op = vd.cog_dpm_step(ac, 4, v, op, t, ts[i - 1].item() if i > 0 else None, xp, gp)
+        assert torch.equal(xo, xp) and torch.equal(oo, op)
+        xo, xp = xo.to(torch.bfloat16), xp.to(torch.bfloat16)
