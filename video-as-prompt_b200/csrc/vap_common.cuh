@@ -119,6 +119,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 
+// mbar_wait that returns 0 through an asm output: make a computation depend on the returned value to keep the compiler
+// from hoisting (non-volatile) work above the wait.
+__device__ __forceinline__ uint32_t mbar_wait_dep(uint32_t bar, uint32_t parity) {
+    mbar_wait(bar, parity);
+    uint32_t z;
+    asm volatile("mov.u32 %0, 0;" : "=r"(z)::"memory");
+    return z;
+}
+
 // ------------------------------------------------------------------------------------------
 // TMA
 // ------------------------------------------------------------------------------------------
