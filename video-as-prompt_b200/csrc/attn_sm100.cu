@@ -47,6 +47,9 @@ constexpr float kSumTrigger = 256.0f;  // 2^kRescaleThreshold
 #ifndef VAP_ATTN_POLY_PAIRS_D64
 #define VAP_ATTN_POLY_PAIRS_D64 1
 #endif
+#ifndef VAP_ATTN_LEADER_WAIT
+#define VAP_ATTN_LEADER_WAIT 1
+#endif
 #ifndef VAP_ATTN_TRACE
 #define VAP_ATTN_TRACE 0  // 1: clock64() stamps of CTA (0,0,0) when a trace buffer is installed (tools/attn_trace.py)
 #endif
@@ -274,7 +277,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             TR(0);
             // s_full(i) phase j: QK_i(j) is complete, and with it PV_i(j-1) (issued earlier by the same thread), so O_i is
             // quiescent until the first p_full arrive below
+#if VAP_ATTN_LEADER_WAIT
+            // Only ONE warp of the tile's eight polls the mbarrier; the others block on a named barrier, which costs no issue
+            // slots.  (Eight polling warps executed 39 % of the kernel's instructions and competed with the other tile's
+            // softmax for the same schedulers, profiles/r01_attn_v5_in_step.json.)
+            if ((sw & 7) == 0) mbar_wait(s_full(i), j & 1);
+            named_bar_sync(1 + i, 256);
+#else
             mbar_wait(s_full(i), j & 1);
+#endif
             tc_fence_after();
             TR(1);
 #pragma unroll

@@ -104,19 +104,29 @@ __device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU box.
+// Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU box.  The bound is a spin counter and a bare
+// trap: a printf in the timeout path costs a stack frame and registers in every kernel that waits, and in the attention kernel
+// (whose softmax warps spend a third of their time in this loop) 5 % of its throughput.  -DVAP_MBAR_VERBOSE brings the message
+// back for bring-up.
 #ifndef VAP_MBAR_SPIN_LIMIT
-#define VAP_MBAR_SPIN_LIMIT (1u << 21)
+#define VAP_MBAR_SPIN_LIMIT (1u << 24)
 #endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#if defined(VAP_MBAR_UNBOUNDED)
+    while (!mbar_try_wait(bar, parity)) {
+    }
+#else
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         if (++spins > VAP_MBAR_SPIN_LIMIT) {
+#if defined(VAP_MBAR_VERBOSE)
             printf("vap: mbarrier timeout block=(%d,%d,%d) thread=%d bar=0x%x parity=%u\n", blockIdx.x, blockIdx.y, blockIdx.z,
                    threadIdx.x, bar, parity);
+#endif
             __trap();
         }
     }
+#endif
 }
 
 // mbar_wait that returns 0 through an asm output: make a computation depend on the returned value to keep the compiler
