@@ -5,6 +5,7 @@ import importlib
 import json
 import os
 import re
+import sys
 
 import pytest
 import torch
@@ -165,3 +166,22 @@ def test_flow_match_schedule_matches_oracle():
         t1, s1 = vap.denoise.flow_match_schedule(n, sh)
         t2, s2 = od.flow_match_schedule(n, sh)
         assert torch.allclose(t1, t2, rtol=1e-6) and torch.allclose(s1, s2, rtol=1e-6)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU oracle timed on the host cores) prints ONE JSON line with the contract's keys; run here on
+    the tiny workload so it takes seconds."""
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--config", "wan_tiny", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+                "config", "impl", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["unit"] == "steps/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and "sample" in line["cpu_baseline"]
+    assert line["e2e"] == {"value": line["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"]
