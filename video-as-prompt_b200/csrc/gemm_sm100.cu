@@ -11,6 +11,7 @@
 //   warp 2   : TMEM allocator (2 accumulator stages x BN fp32 columns)
 //   warps 4-7: epilogue      (tcgen05.ld -> bias / GELU / gated residual with the reference's bf16 rounding
 //                             points -> 16-byte global stores), overlapped with the next tile's main loop.
+#include <cstdlib>
 #include "vap_kernels.cuh"
 
 namespace vap {
@@ -29,14 +30,18 @@ constexpr int kBK = 64;
 constexpr int kGemmThreads = 256;
 constexpr int kGroupM = 16;
 
-template <int BN>
+// MT = M-tiles (128 rows each) per CTA tile.  MT = 2 (256 x 256 tile, two MMAs per k-step sharing one W tile) streams a third less
+// operand data from L2 per FLOP than MT = 1 (128 x 256) but its two accumulators fill all 512 TMEM columns (the epilogue of a
+// tile is not overlapped with the next tile's main loop) and only three 64 KB stages fit: measured slower, kept as an experiment.
+template <int BN, int MT>
 struct GemmCfg {
-    static constexpr int kStages = (BN == 256) ? 4 : 6;
-    static constexpr int kABytes = kBM * kBK * 2;
+    static constexpr int kABytes = MT * kBM * kBK * 2;
     static constexpr int kBBytes = BN * kBK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStages = (MT == 2) ? 3 : ((BN == 256) ? 4 : 6);
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
-    static constexpr int kTmemCols = 2 * BN;  // 512 (BN=256) or 256 (BN=128): powers of two
+    static constexpr int kAccStages = (MT == 2) ? 1 : 2;
+    static constexpr int kTmemCols = (MT * BN * kAccStages >= 512) ? 512 : 256;  // powers of two
 };
 
 __device__ __forceinline__ void tile_coords(int tile, int m_blocks, int n_blocks, int& mb, int& nb) {
@@ -57,10 +62,10 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
     return 0.5f * x * (1.f + tanhf(inner));
 }
 
-template <int BN>
+template <int BN, int MT>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, MT>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
@@ -114,7 +119,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     const uint32_t a_dst = smem_base + stage * Cfg::kStageBytes;
                     const uint32_t b_dst = a_dst + Cfg::kABytes;
                     mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
-                    tma_load_2d(a_dst, &tmA, full_bar(stage), kb * kBK, mb * kBM);
+                    tma_load_2d(a_dst, &tmA, full_bar(stage), kb * kBK, mb * (kBM * MT));
                     tma_load_2d(b_dst, &tmB, full_bar(stage), kb * kBK, nb * BN);
                     if (++stage == Cfg::kStages) {
                         stage = 0;
@@ -134,7 +139,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
+                const uint32_t d_tmem = tmem_base + acc * (MT * BN);
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
@@ -142,9 +147,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     const uint32_t b_addr = a_addr + Cfg::kABytes;
 #pragma unroll
                     for (int k = 0; k < kBK / 16; ++k) {
-                        const uint64_t da = make_smem_desc(a_addr + k * 32, 0, 1024, kLayoutSw128);
                         const uint64_t db = make_smem_desc(b_addr + k * 32, 0, 1024, kLayoutSw128);
-                        umma_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt) {  // the M-tiles share the W operand
+                            const uint64_t da = make_smem_desc(a_addr + mt * (kBM * kBK * 2) + k * 32, 0, 1024, kLayoutSw128);
+                            umma_ss(d_tmem + mt * BN, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
                     }
                     umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs have read it
                     if (++stage == Cfg::kStages) {
@@ -153,7 +161,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
                 }
                 umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
-                if (++acc == 2) {
+                if (++acc == Cfg::kAccStages) {
                     acc = 0;
                     acc_phase ^= 1;
                 }
@@ -169,75 +177,78 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tile_coords(tile, p.m_blocks, p.n_blocks, mb, nb);
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
-            const int row = mb * kBM + q * 32 + lane;
-            const bool row_ok = row < p.M;
-            const float* gate = nullptr;
-            if (p.gate) gate = p.gate + (p.rows_per_batch > 0 ? (row_ok ? row / p.rows_per_batch : 0) : 0) * p.gate_stride;
-            __nv_bfloat16* crow = p.C + static_cast<int64_t>(row) * p.ldc;
-            const __nv_bfloat16* rrow = p.R ? p.R + static_cast<int64_t>(row) * p.ldr : nullptr;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c0, v);
-                tmem_ld_wait();
-                const int n0 = nb * BN + c0;
-                if (row_ok && n0 < p.N) {
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {  // 4 groups of 8 columns = 16-byte stores
-                        const int n = n0 + 8 * g;
-                        if (n < p.N) {
-                            float y[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) y[j] = __uint_as_float(v[8 * g + j]);
-                            if (p.bias) {
-                                const uint4 bb = *reinterpret_cast<const uint4*>(p.bias + n);
-                                const uint32_t* bu = reinterpret_cast<const uint32_t*>(&bb);
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const float2 f = bf16x2_to_float2(bu[j]);
-                                    y[2 * j] += f.x;
-                                    y[2 * j + 1] += f.y;
-                                }
-                            }
-                            if (p.epilogue != kEpiBias) {
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) y[j] = bf16_round(y[j]);
-                                if (p.epilogue == kEpiBiasGelu) {
-#pragma unroll
-                                    for (int j = 0; j < 8; ++j) y[j] = gelu_tanh_f(y[j]);
-                                } else {
-                                    const uint4 rr = *reinterpret_cast<const uint4*>(rrow + n);
-                                    const uint32_t* ru = reinterpret_cast<const uint32_t*>(&rr);
-                                    float r[8];
-#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                const int row = (mb * MT + mt) * kBM + q * 32 + lane;
+                const bool row_ok = row < p.M;
+                const float* gate = nullptr;
+                if (p.gate) gate = p.gate + (p.rows_per_batch > 0 ? (row_ok ? row / p.rows_per_batch : 0) : 0) * p.gate_stride;
+                __nv_bfloat16* crow = p.C + static_cast<int64_t>(row) * p.ldc;
+                const __nv_bfloat16* rrow = p.R ? p.R + static_cast<int64_t>(row) * p.ldr : nullptr;
+    #pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * (MT * BN) + mt * BN + c0, v);
+                    tmem_ld_wait();
+                    const int n0 = nb * BN + c0;
+                    if (row_ok && n0 < p.N) {
+    #pragma unroll
+                        for (int g = 0; g < 4; ++g) {  // 4 groups of 8 columns = 16-byte stores
+                            const int n = n0 + 8 * g;
+                            if (n < p.N) {
+                                float y[8];
+    #pragma unroll
+                                for (int j = 0; j < 8; ++j) y[j] = __uint_as_float(v[8 * g + j]);
+                                if (p.bias) {
+                                    const uint4 bb = *reinterpret_cast<const uint4*>(p.bias + n);
+                                    const uint32_t* bu = reinterpret_cast<const uint32_t*>(&bb);
+    #pragma unroll
                                     for (int j = 0; j < 4; ++j) {
-                                        const float2 f = bf16x2_to_float2(ru[j]);
-                                        r[2 * j] = f.x;
-                                        r[2 * j + 1] = f.y;
+                                        const float2 f = bf16x2_to_float2(bu[j]);
+                                        y[2 * j] += f.x;
+                                        y[2 * j + 1] += f.y;
                                     }
-                                    if (p.epilogue == kEpiResAdd) {
-#pragma unroll
-                                        for (int j = 0; j < 8; ++j) y[j] = r[j] + y[j];
+                                }
+                                if (p.epilogue != kEpiBias) {
+    #pragma unroll
+                                    for (int j = 0; j < 8; ++j) y[j] = bf16_round(y[j]);
+                                    if (p.epilogue == kEpiBiasGelu) {
+    #pragma unroll
+                                        for (int j = 0; j < 8; ++j) y[j] = gelu_tanh_f(y[j]);
                                     } else {
-                                        const float4 g0 = *reinterpret_cast<const float4*>(gate + n);
-                                        const float4 g1 = *reinterpret_cast<const float4*>(gate + n + 4);
-                                        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-                                        if (p.epilogue == kEpiGateResF32) {
-#pragma unroll
-                                            for (int j = 0; j < 8; ++j) y[j] = r[j] + y[j] * gg[j];
+                                        const uint4 rr = *reinterpret_cast<const uint4*>(rrow + n);
+                                        const uint32_t* ru = reinterpret_cast<const uint32_t*>(&rr);
+                                        float r[8];
+    #pragma unroll
+                                        for (int j = 0; j < 4; ++j) {
+                                            const float2 f = bf16x2_to_float2(ru[j]);
+                                            r[2 * j] = f.x;
+                                            r[2 * j + 1] = f.y;
+                                        }
+                                        if (p.epilogue == kEpiResAdd) {
+    #pragma unroll
+                                            for (int j = 0; j < 8; ++j) y[j] = r[j] + y[j];
                                         } else {
-#pragma unroll
-                                            for (int j = 0; j < 8; ++j) y[j] = r[j] + bf16_round(gg[j] * y[j]);
+                                            const float4 g0 = *reinterpret_cast<const float4*>(gate + n);
+                                            const float4 g1 = *reinterpret_cast<const float4*>(gate + n + 4);
+                                            const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                                            if (p.epilogue == kEpiGateResF32) {
+    #pragma unroll
+                                                for (int j = 0; j < 8; ++j) y[j] = r[j] + y[j] * gg[j];
+                                            } else {
+    #pragma unroll
+                                                for (int j = 0; j < 8; ++j) y[j] = r[j] + bf16_round(gg[j] * y[j]);
+                                            }
                                         }
                                     }
                                 }
+                                uint4 o;
+                                o.x = pack_bf16x2(y[0], y[1]);
+                                o.y = pack_bf16x2(y[2], y[3]);
+                                o.z = pack_bf16x2(y[4], y[5]);
+                                o.w = pack_bf16x2(y[6], y[7]);
+                                *reinterpret_cast<uint4*>(crow + n) = o;
                             }
-                            uint4 o;
-                            o.x = pack_bf16x2(y[0], y[1]);
-                            o.y = pack_bf16x2(y[2], y[3]);
-                            o.z = pack_bf16x2(y[4], y[5]);
-                            o.w = pack_bf16x2(y[6], y[7]);
-                            *reinterpret_cast<uint4*>(crow + n) = o;
                         }
                     }
                 }
@@ -246,7 +257,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));
-            if (++acc == 2) {
+            if (++acc == Cfg::kAccStages) {
                 acc = 0;
                 acc_phase ^= 1;
             }
@@ -261,21 +272,34 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
 }
 
-template <int BN>
+template <int BN, int MT>
 static int launch_gemm_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams p, cudaStream_t stream) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, MT>;
+    static_assert(Cfg::kSmemBytes <= 232448, "shared memory budget");
     static bool attr_set = false;
     if (!attr_set) {
-        VAP_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        VAP_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         attr_set = true;
     }
-    p.m_blocks = (p.M + kBM - 1) / kBM;
+    p.m_blocks = (p.M + kBM * MT - 1) / (kBM * MT);
     p.n_blocks = (p.N + BN - 1) / BN;
     const int tiles = p.m_blocks * p.n_blocks;
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    gemm_bf16_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+    gemm_bf16_kernel<BN, MT><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
     VAP_CHECK_CUDA(cudaGetLastError());
     return 0;
+}
+
+// M-tiles per CTA tile.  Measured on the MoT shapes (tools/gemm_ab.sh): the 256 x 256 tile (MT = 2) loses to 128 x 256 (1330-1350 vs
+// 1460-1520 TFLOP/s; only three pipeline stages fit and the epilogue is exposed), so it stays an experiment: VAP_GEMM_MT=2.
+static int gemm_m_tiles(int M, int N) {
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("VAP_GEMM_MT");
+        forced = e ? atoi(e) : 0;
+    }
+    (void)M;
+    return (forced == 2 && N >= 256) ? 2 : 1;
 }
 
 int launch_gemm_bf16(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, GemmParams p, cudaStream_t stream) {
@@ -295,11 +319,12 @@ int launch_gemm_bf16(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W
     if (p.M == 0) return 0;
     const bool wide = p.N >= 256;
     const int BN = wide ? 256 : 128;
+    const int MT = gemm_m_tiles(p.M, p.N);
     CUtensorMap tmA, tmB;
     {
         const uint64_t dims[2] = {static_cast<uint64_t>(p.K), static_cast<uint64_t>(p.M)};
         const uint64_t strides[1] = {static_cast<uint64_t>(lda)};
-        const uint32_t box[2] = {kBK, kBM};
+        const uint32_t box[2] = {kBK, static_cast<uint32_t>(kBM * MT)};
         if (make_tmap_bf16(&tmA, A, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return -3;
     }
     {
@@ -308,7 +333,8 @@ int launch_gemm_bf16(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W
         const uint32_t box[2] = {kBK, static_cast<uint32_t>(BN)};
         if (make_tmap_bf16(&tmB, W, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return -3;
     }
-    return wide ? launch_gemm_bn<256>(tmA, tmB, p, stream) : launch_gemm_bn<128>(tmA, tmB, p, stream);
+    if (MT == 2) return launch_gemm_bn<256, 2>(tmA, tmB, p, stream);
+    return wide ? launch_gemm_bn<256, 1>(tmA, tmB, p, stream) : launch_gemm_bn<128, 1>(tmA, tmB, p, stream);
 }
 
 }  // namespace vap
