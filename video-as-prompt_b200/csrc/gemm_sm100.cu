@@ -62,10 +62,20 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
     return 0.5f * x * (1.f + tanhf(inner));
 }
 
-template <int BN, int MT>
+// CL = 2: the kernel runs as clusters of two CTAs that work on vertically adjacent M-blocks of the SAME N-block: each CTA fetches
+// half of the W tile and TMA multicasts it into both CTAs' shared memory, so the W operand crosses the L2 -> SM fabric once per
+// pair (a third less operand traffic per FLOP, same tile shape / pipeline depth / accumulator double-buffering).  A shared-memory
+// slot is reusable when BOTH CTAs' MMAs have read it: every CTA's tcgen05.commit arrives on both CTAs' empty barriers.
+template <int BN, int MT, int CL>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
     using Cfg = GemmCfg<BN, MT>;
+    static_assert(CL == 1 || (CL == 2 && MT == 1 && BN == 256), "the cluster variant is the 128 x 256 tile");
+    const int cta_rank = (CL == 2) ? static_cast<int>(cluster_ctarank()) : 0;
+    // persistent loop: work unit u = one N-block x CL M-blocks; this CTA takes M-block CL * mbu + cta_rank of its cluster's units
+    const int unit0 = (CL == 2) ? static_cast<int>(cluster_id_x()) : static_cast<int>(blockIdx.x);
+    const int unit_stride = (CL == 2) ? static_cast<int>(cluster_nctaid_x()) : static_cast<int>(gridDim.x);
+    const int m_units = (p.m_blocks + CL - 1) / CL;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
@@ -78,7 +88,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int num_tiles = p.m_blocks * p.n_blocks;
+    const int num_tiles = m_units * p.n_blocks;
     const int k_blocks = (p.K + kBK - 1) / kBK;
 
     if (warp == 0 && lane == 0) {
@@ -88,7 +98,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < Cfg::kStages; ++s) {
             mbar_init(full_bar(s), 1);
-            mbar_init(empty_bar(s), 1);
+            mbar_init(empty_bar(s), CL);  // one tcgen05.commit per CTA of the cluster
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(tfull_bar(s), 1);
@@ -102,6 +112,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     tc_fence_before();
     __syncthreads();
+    if (CL == 2) cluster_sync_all();  // the peer's barriers are initialised before anything of ours can reach them
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
@@ -111,16 +122,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             // ===== TMA producer =====
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
                 int mb, nb;
-                tile_coords(tile, p.m_blocks, p.n_blocks, mb, nb);
+                tile_coords(tile, m_units, p.n_blocks, mb, nb);
+                mb = mb * CL + cta_rank;
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t a_dst = smem_base + stage * Cfg::kStageBytes;
                     const uint32_t b_dst = a_dst + Cfg::kABytes;
                     mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
                     tma_load_2d(a_dst, &tmA, full_bar(stage), kb * kBK, mb * (kBM * MT));
-                    tma_load_2d(b_dst, &tmB, full_bar(stage), kb * kBK, nb * BN);
+                    if (CL == 2)  // my half of the W tile, into both CTAs
+                        tma_load_2d_multicast(b_dst + cta_rank * (BN / 2) * kBK * 2, &tmB, full_bar(stage), kb * kBK, nb * BN + cta_rank * (BN / 2), 3);
+                    else
+                        tma_load_2d(b_dst, &tmB, full_bar(stage), kb * kBK, nb * BN);
                     if (++stage == Cfg::kStages) {
                         stage = 0;
                         phase ^= 1;
@@ -136,7 +151,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * (MT * BN);
@@ -154,7 +169,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             umma_ss(d_tmem + mt * BN, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
                         }
                     }
-                    umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs have read it
+                    if (CL == 2) umma_commit_multicast(empty_bar(stage), 3);  // frees the slot in both CTAs once these MMAs have read it
+                    else umma_commit(empty_bar(stage));
                     if (++stage == Cfg::kStages) {
                         stage = 0;
                         phase ^= 1;
@@ -172,9 +188,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int q = warp & 3;  // TMEM lane quarter owned by this warp
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
             int mb, nb;
-            tile_coords(tile, p.m_blocks, p.n_blocks, mb, nb);
+            tile_coords(tile, m_units, p.n_blocks, mb, nb);
+            mb = mb * CL + cta_rank;
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
 #pragma unroll 1
@@ -266,6 +283,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     tc_fence_before();
     __syncthreads();
+    if (CL == 2) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it or signal its barriers
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc(tmem_base, Cfg::kTmemCols);
@@ -278,16 +296,61 @@ static int launch_gemm_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmPa
     static_assert(Cfg::kSmemBytes <= 232448, "shared memory budget");
     static bool attr_set = false;
     if (!attr_set) {
-        VAP_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        VAP_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, MT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         attr_set = true;
     }
     p.m_blocks = (p.M + kBM * MT - 1) / (kBM * MT);
     p.n_blocks = (p.N + BN - 1) / BN;
     const int tiles = p.m_blocks * p.n_blocks;
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    gemm_bf16_kernel<BN, MT><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+    gemm_bf16_kernel<BN, MT, 1><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
     VAP_CHECK_CUDA(cudaGetLastError());
     return 0;
+}
+
+// 128 x 256 tiles in clusters of two CTAs sharing the W tile by TMA multicast
+static int launch_gemm_cluster(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams p, cudaStream_t stream) {
+    using Cfg = GemmCfg<256, 1>;
+    static int max_clusters = -1;
+    if (max_clusters < 0) {
+        VAP_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<256, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        cudaLaunchConfig_t probe{};
+        probe.gridDim = dim3(static_cast<unsigned>(sm_count() / 2 * 2));
+        probe.blockDim = dim3(kGemmThreads);
+        probe.dynamicSmemBytes = Cfg::kSmemBytes;
+        cudaLaunchAttribute attr{};
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = 2, attr.val.clusterDim.y = 1, attr.val.clusterDim.z = 1;
+        probe.attrs = &attr, probe.numAttrs = 1;
+        int n = 0;
+        VAP_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm_bf16_kernel<256, 1, 2>, &probe));
+        max_clusters = n;
+    }
+    VAP_REQUIRE(max_clusters > 0, "gemm_bf16: no 2-CTA cluster fits on this device");
+    p.m_blocks = (p.M + kBM - 1) / kBM;
+    p.n_blocks = (p.N + 255) / 256;
+    const int units = ((p.m_blocks + 1) / 2) * p.n_blocks;
+    const int clusters = units < max_clusters ? units : max_clusters;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(2 * clusters));
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2, attr.val.clusterDim.y = 1, attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr, cfg.numAttrs = 1;
+    VAP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<256, 1, 2>, tmA, tmB, p));
+    return 0;
+}
+
+static int gemm_cluster_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("VAP_GEMM_CLUSTER");
+        mode = e ? atoi(e) : 0;
+    }
+    return mode;
 }
 
 // M-tiles per CTA tile.  Measured on the MoT shapes (tools/gemm_ab.sh): the 256 x 256 tile (MT = 2) loses to 128 x 256 (1330-1350 vs
@@ -320,6 +383,7 @@ int launch_gemm_bf16(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W
     const bool wide = p.N >= 256;
     const int BN = wide ? 256 : 128;
     const int MT = gemm_m_tiles(p.M, p.N);
+    const bool cluster = wide && MT == 1 && gemm_cluster_mode() == 2 && p.M > 2 * kBM;
     CUtensorMap tmA, tmB;
     {
         const uint64_t dims[2] = {static_cast<uint64_t>(p.K), static_cast<uint64_t>(p.M)};
@@ -330,9 +394,10 @@ int launch_gemm_bf16(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W
     {
         const uint64_t dims[2] = {static_cast<uint64_t>(p.K), static_cast<uint64_t>(p.N)};
         const uint64_t strides[1] = {static_cast<uint64_t>(ldw)};
-        const uint32_t box[2] = {kBK, static_cast<uint32_t>(BN)};
+        const uint32_t box[2] = {kBK, static_cast<uint32_t>(cluster ? BN / 2 : BN)};
         if (make_tmap_bf16(&tmB, W, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return -3;
     }
+    if (cluster) return launch_gemm_cluster(tmA, tmB, p, stream);
     if (MT == 2) return launch_gemm_bn<256, 2>(tmA, tmB, p, stream);
     return wide ? launch_gemm_bn<256, 1>(tmA, tmB, p, stream) : launch_gemm_bn<128, 1>(tmA, tmB, p, stream);
 }
