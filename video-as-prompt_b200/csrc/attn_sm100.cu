@@ -27,6 +27,7 @@
 //   * P is published in two 64-column halves (p_full(i, 0/1)), so the first four PV MMAs of a step overlap the second
 //     half of the softmax.
 // The last KV tile is masked against Lkv (TMA zero-fills out-of-range K/V rows).
+#include <cstdlib>
 #include "vap_kernels.cuh"
 
 namespace vap {
@@ -66,7 +67,10 @@ struct AttnCfg {
     static constexpr int kColS0 = 0, kColS1 = 128, kColO0 = 256, kColO1 = 256 + D;
 };
 
-template <int D>
+// CL = 2: clusters of two CTAs (adjacent 256-row query blocks of the same head) share every K / V tile: each CTA fetches half of
+// the tile's rows and TMA multicasts them into both CTAs' shared memory, so K / V cross the L2 -> SM fabric once per 512 query
+// rows; a ring slot is reusable when BOTH CTAs' MMAs have read it (multicast tcgen05.commit on the empty barriers).
+template <int D, int CL>
 __global__ void __launch_bounds__(kAttnThreads, 1)  // registers are granted per 4 warps: 18 warps cost 20 -> 96 per thread
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -101,7 +105,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < Cfg::kKvStages; ++s) {
             mbar_init(kv_full(s), 1);
-            mbar_init(kv_empty(s), 1);
+            mbar_init(kv_empty(s), CL);  // one tcgen05.commit per CTA of the cluster
         }
         mbar_init(q_full, 1);
         for (int i = 0; i < 2; ++i) {
@@ -119,9 +123,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     tc_fence_before();
     __syncthreads();
+    if (CL == 2) cluster_sync_all();  // the peer's barriers are initialised before anything of ours can reach them
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+    const int cta_rank = (CL == 2) ? static_cast<int>(cluster_ctarank()) : 0;
 
     // The producer and MMA warps run their loops warp-wide (all lanes wait on the mbarriers, one elected lane issues):
     // control flow and descriptors stay warp-uniform, so ptxas keeps them in uniform registers instead of wrapping
@@ -144,8 +150,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     if (elect_one()) {
                         mbar_arrive_expect_tx(kv_full(stage), Cfg::kTileBytes);
                         const uint32_t dst = kv_smem + stage * Cfg::kTileBytes;
-                        for (int h = 0; h < Cfg::kHalves; ++h)
-                            tma_load_4d(dst + h * Cfg::kHalfBytes, kv == 0 ? &tmK : &tmV, kv_full(stage), h * 64, j * kBlockN, head, batch);
+                        for (int h = 0; h < Cfg::kHalves; ++h) {
+                            if (CL == 2)  // my 64 rows of the tile, into both CTAs
+                                tma_load_4d_multicast(dst + h * Cfg::kHalfBytes + cta_rank * (kBlockN / 2) * 128, kv == 0 ? &tmK : &tmV, kv_full(stage), h * 64,
+                                                      j * kBlockN + cta_rank * (kBlockN / 2), head, batch, 3);
+                            else
+                                tma_load_4d(dst + h * Cfg::kHalfBytes, kv == 0 ? &tmK : &tmV, kv_full(stage), h * 64, j * kBlockN, head, batch);
+                        }
                     }
                     __syncwarp();
                     if (++stage == Cfg::kKvStages) {
@@ -190,6 +201,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 if (elect_one()) umma_commit(bar);
                 __syncwarp();
             };
+            auto release = [&](uint32_t bar) {  // a K / V ring slot: in a cluster the arrive goes to both CTAs' empty barriers
+                if (elect_one()) {
+                    if (CL == 2) umma_commit_multicast(bar, 3);
+                    else umma_commit(bar);
+                }
+                __syncwarp();
+            };
 
             int stage = 0;
             uint32_t phase = 0;
@@ -206,7 +224,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             commit(s_full(0));
             issue_qk(1, kv_smem + stage * Cfg::kTileBytes);
             commit(s_full(1));
-            commit(kv_empty(stage));
+            release(kv_empty(stage));
             advance();
             long long* trm = (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) ? p.trace + 1024 : nullptr;
 #if VAP_ATTN_TRACE
@@ -245,8 +263,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     }
                     TRM(3 + 2 * i);
                 }
-                commit(kv_empty(v_stage));
-                if (has_next) commit(kv_empty(k_stage));
+                release(kv_empty(v_stage));
+                if (has_next) release(kv_empty(k_stage));
             }
         }
     } else {
@@ -452,6 +470,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
     tc_fence_before();
     __syncthreads();
+    if (CL == 2) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it or signal its barriers
     if (warp == 0) {
         tc_fence_after();
         tmem_dealloc(tmem_base, Cfg::kTmemCols);
@@ -459,30 +478,53 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 }
 
 
-static int make_attn_tmap(CUtensorMap* tm, const AttnTensor& t, int B, int H, int L, int D, const char* name) {
+static int make_attn_tmap(CUtensorMap* tm, const AttnTensor& t, int B, int H, int L, int D, int box_rows, const char* name) {
     VAP_REQUIRE((reinterpret_cast<uintptr_t>(t.ptr) & 15) == 0, "attention: %s must be 16-byte aligned", name);
     VAP_REQUIRE(t.sl % 8 == 0 && t.sh % 8 == 0 && t.sb % 8 == 0, "attention: %s strides must be multiples of 8 elements", name);
     const uint64_t dims[4] = {static_cast<uint64_t>(D), static_cast<uint64_t>(L), static_cast<uint64_t>(H), static_cast<uint64_t>(B)};
     // a size-1 dim may come with stride 0 from the caller; TMA wants a positive multiple of 16 bytes
     const uint64_t strides[3] = {static_cast<uint64_t>(t.sl > 0 ? t.sl : D), static_cast<uint64_t>(t.sh > 0 ? t.sh : D),
                                  static_cast<uint64_t>(t.sb > 0 ? t.sb : D)};
-    const uint32_t box[4] = {64, 128, 1, 1};
+    const uint32_t box[4] = {64, static_cast<uint32_t>(box_rows), 1, 1};
     return make_tmap_bf16(tm, t.ptr, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-template <int D>
+static int attn_cluster_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("VAP_ATTN_CLUSTER");
+        mode = e ? atoi(e) : 0;
+    }
+    return mode;
+}
+
+template <int D, int CL>
 static int launch_attn_d(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const AttnParams& p, cudaStream_t stream) {
     using Cfg = AttnCfg<D>;
     static_assert(Cfg::kSmemBytes <= 232448, "shared memory budget");
     static_assert(2 * Cfg::kKvStages + 12 <= Cfg::kBarBytes / 8, "barrier area");
     static bool attr_set = false;
     if (!attr_set) {
-        VAP_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        VAP_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<D, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         attr_set = true;
     }
-    const dim3 grid((p.Lq + 2 * kBlockM - 1) / (2 * kBlockM), p.H, p.B);
-    attn_fwd_kernel<D><<<grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(tmQ, tmK, tmV, p);
-    VAP_CHECK_CUDA(cudaGetLastError());
+    const unsigned q_blocks = static_cast<unsigned>((p.Lq + 2 * kBlockM - 1) / (2 * kBlockM));
+    if (CL == 1) {
+        const dim3 grid(q_blocks, p.H, p.B);
+        attn_fwd_kernel<D, CL><<<grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(tmQ, tmK, tmV, p);
+        VAP_CHECK_CUDA(cudaGetLastError());
+        return 0;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((q_blocks + 1) / 2 * 2, p.H, p.B);  // a trailing CTA without query rows still loads and consumes its share of K / V
+    cfg.blockDim = dim3(kAttnThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2, attr.val.clusterDim.y = 1, attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr, cfg.numAttrs = 1;
+    VAP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, attn_fwd_kernel<D, CL>, tmQ, tmK, tmV, p));
     return 0;
 }
 
@@ -500,11 +542,13 @@ int launch_attention_fwd(const AttnTensor& q, const AttnTensor& k, const AttnTen
                     "attention: output must be 16-byte aligned with strides that are multiples of 8 elements");
     }
     if (p.Lq == 0) return 0;
+    const bool cluster = attn_cluster_mode() == 2 && p.Lq > 2 * kBlockM;
     CUtensorMap tmQ, tmK, tmV;
-    if (make_attn_tmap(&tmQ, q, p.B, p.H, p.Lq, D, "q")) return -3;
-    if (make_attn_tmap(&tmK, k, p.B, p.H, p.Lkv, D, "k")) return -3;
-    if (make_attn_tmap(&tmV, v, p.B, p.H, p.Lkv, D, "v")) return -3;
-    return D == 128 ? launch_attn_d<128>(tmQ, tmK, tmV, p, stream) : launch_attn_d<64>(tmQ, tmK, tmV, p, stream);
+    if (make_attn_tmap(&tmQ, q, p.B, p.H, p.Lq, D, kBlockM, "q")) return -3;
+    if (make_attn_tmap(&tmK, k, p.B, p.H, p.Lkv, D, cluster ? kBlockN / 2 : kBlockN, "k")) return -3;
+    if (make_attn_tmap(&tmV, v, p.B, p.H, p.Lkv, D, cluster ? kBlockN / 2 : kBlockN, "v")) return -3;
+    if (cluster) return D == 128 ? launch_attn_d<128, 2>(tmQ, tmK, tmV, p, stream) : launch_attn_d<64, 2>(tmQ, tmK, tmV, p, stream);
+    return D == 128 ? launch_attn_d<128, 1>(tmQ, tmK, tmV, p, stream) : launch_attn_d<64, 1>(tmQ, tmK, tmV, p, stream);
 }
 
 }  // namespace vap
