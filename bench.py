@@ -189,6 +189,9 @@ def main():
     ap.add_argument("--impl", default="vap")
     ap.add_argument("--config", default="wan14b")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", default="off", choices=["on", "off"],
+                    help="replay the forward as one CUDA graph (experimental: single GPU only measured; with N > 1 the process did not exit cleanly after "
+                         "the run, so it is off by default)")
     ap.add_argument("--sp-mode", default=None, choices=["p2p", "nccl"], help="Ulysses transport for N > 1 (default p2p: exchange fused into the kernels over NVLink peer memory)")
     ap.add_argument("--profile", action="store_true", help="bracket the device-timed steps with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     a = ap.parse_args()
@@ -265,13 +268,15 @@ def main():
 
     sigmas = vap.denoise.flow_match_schedule(max(a.steps + a.warmup, 2), 3.0, device=dev)[1]
 
+    fwd = [model]  # the callable a step uses: the model, or its CUDA-graph replay
+
     def step(i, x_latent, from_host):
         kw = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in host.items()} if from_host else inp
         if w["family"] == "wan":
-            noise = model(**kw, return_dict=False)[0]
+            noise = fwd[0](**kw, return_dict=False)[0]
             x_latent = vap.denoise.flow_match_step(noise, x_latent, sigmas[i], sigmas[i + 1])  # scheduler update (fp32 Euler)
         else:
-            noise = model(**kw, return_dict=False)[0]
+            noise = fwd[0](**kw, return_dict=False)[0]
         if from_host:
             noise_host.copy_(noise, non_blocking=True)
         return x_latent
@@ -316,9 +321,33 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item(), t0, t1, launches[0]
 
+    # Eager pass first: it yields the per-launch CUDA-event timing of the attention kernel (roofline) and the launch count, and
+    # is the reported number when no graph is used.  With --graph the same K steps are then timed again as CUDA-graph replays
+    # (identical kernels and data; only the launch path differs) and THAT is `value` / `e2e`.
+    use_graph = a.graph == "on"
     sampler = ClockSampler(local) if rank == 0 else None
     ms_dev, t0, t1, n_launch = timed(from_host=False)
     clocks = sampler.stop(t0, t1) if sampler else None
+    graph_note = None
+    if use_graph:
+        ok = torch.tensor([1], device=dev)
+        try:
+            graphed = vap.GraphedForward(model, inp)
+        except Exception as exc:  # capture is all-or-nothing across the ranks
+            ok.zero_()
+            graph_note = f"capture failed ({type(exc).__name__}: {str(exc)[:120]}), eager numbers reported"
+        if world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() == 1:
+            fwd[0] = graphed
+            config["launch"] = "CUDA graph replay of the forward (eager pass: %.1f ms/step)" % (ms_dev / a.steps)
+            sampler = ClockSampler(local) if rank == 0 else None
+            ms_dev, t0, t1, _ = timed(from_host=False)
+            clocks = sampler.stop(t0, t1) if sampler else None
+        else:
+            config["launch"] = "eager (" + (graph_note or "another rank failed to capture") + ")"
+    else:
+        config["launch"] = "eager"
     ms_e2e, _, _, _ = timed(from_host=True)
 
     if rank == 0:

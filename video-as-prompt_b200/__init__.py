@@ -3,7 +3,8 @@
 Import as ``import vap_b200`` (alias module at the repo root) or ``importlib.import_module("video-as-prompt_b200")``.
 The CUDA kernels live in ``libvap_b200.so`` (C ABI: ``include/vap_b200.h``), built in-tree by ``csrc/build.py``.
 """
-from . import _lib, cogvideox, denoise, install as _install_mod, modules, ops, rope, sdpa, synth, ulysses, wan  # noqa: F401
+from . import _lib, cogvideox, denoise, graphs, install as _install_mod, modules, ops, rope, sdpa, synth, ulysses, wan  # noqa: F401
+from .graphs import GraphedForward  # noqa: F401
 from ._lib import VapError  # noqa: F401
 from .cogvideox import CogVideoXAttnMOTProcessor2_0, CogVideoXAttnProcessor2_0, CogVideoXTransformer3DMOTModel, cog_block_forward  # noqa: F401
 from .install import install, uninstall  # noqa: F401
