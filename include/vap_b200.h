@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define VAP_B200_VERSION 200 /* major*10000 + minor*100 + patch */
+#define VAP_B200_VERSION 300 /* major*10000 + minor*100 + patch */
 
 /* Library version (VAP_B200_VERSION of the build). */
 int vap_version(void);
@@ -115,6 +115,19 @@ int vap_attention_fwd_scatter(const void* q, const void* k, const void* v, void*
                               int B, int H, int Lq, int Lkv, int D, int64_t q_sb, int64_t q_sh, int64_t q_sl, int64_t k_sb, int64_t k_sh,
                               int64_t k_sl, int64_t v_sb, int64_t v_sh, int64_t v_sl, int64_t o_sb, int64_t o_sh, int64_t o_sl, float scale,
                               void* stream);
+
+/* (3b) Split-KV joint attention: when B * H * ceil(Lq / 256) work items are a poor multiple of the SM count (e.g. 5 heads per
+ *      rank under 8-way Ulysses: 795 items = 5.4 waves on 148 SMs), the KV sequence is cut into kv_splits ranges; item
+ *      (batch, head, 256 query rows, range) writes a NORMALISED partial O and its log-sum-exp, and the combine kernel merges
+ *      them: O = sum_s exp(lse_s - lse) O_s — to a plain strided output (o) or, for the fused Ulysses exchange #2, straight into
+ *      the owning ranks' buffers (o_peers / o_rows_per_peer as in vap_attention_fwd_scatter; pass exactly one of o / o_peers).
+ *      o_part [kv_splits, B, Lq, H, D] bf16 and lse_part [kv_splits, B, H, Lq] fp32 are caller-allocated workspaces.
+ *      Same reference call sites as (3). */
+int vap_attention_fwd_splitkv(const void* q, const void* k, const void* v, void* o_part, float* lse_part, int kv_splits, int B, int H, int Lq,
+                              int Lkv, int D, int64_t q_sb, int64_t q_sh, int64_t q_sl, int64_t k_sb, int64_t k_sh, int64_t k_sl, int64_t v_sb,
+                              int64_t v_sh, int64_t v_sl, float scale, void* stream);
+int vap_attention_combine(const void* o_part, const float* lse_part, int kv_splits, int B, int H, int Lq, int D, void* o, void* const* o_peers,
+                          int npeers, int o_rows_per_peer, float* lse, int64_t o_sb, int64_t o_sh, int64_t o_sl, void* stream);
 
 /* (6) Bring-up probe for the tcgen05 descriptors: one CTA computes D[128,N] = A[128,K] * B, fp32 out.
  *     a_in_tmem: bit 0: 0 = A from shared memory (K-major, SWIZZLE_128B), 1 = A staged to TMEM as packed bf16;

@@ -263,6 +263,61 @@ def check_attention_full_size(J=40560, H=40, D=128, heads_checked=2):
     return dict(ones_err=p1, perm_err=p2, err_vs_torch_sdpa=p3)
 
 
+def check_attention_splitkv(B=1, H=2, Lq=300, Lkv=1000, D=128, splits=2, seed=33, tol=1e-2):
+    """Split-KV attention + merge (vap_attention_fwd_splitkv / vap_attention_combine) vs the definition-level fp32 oracle and vs
+    the unsplit kernel; the KV tail (Lkv not a multiple of 128) lands in the last range."""
+    q, k, v = _randn((B, H, Lq, D), seed), _randn((B, H, Lkv, D), seed + 1), _randn((B, H, Lkv, D), seed + 2)
+    gq, gk, gv = q.to(DEV), k.to(DEV), v.to(DEV)
+    ref = ocommon.sdpa_explicit_fp32(q, k, v)
+    out = ops.attention_splitkv(gq, gk, gv, splits)
+    base = ops.attention(gq, gk, gv)
+    torch.cuda.synchronize()
+    err, err_base = rel_err(out, ref), rel_err(out, base)
+    assert out.shape == (B, H, Lq, D) and out.transpose(1, 2).is_contiguous()
+    assert err < tol and err_base < tol, f"split-KV attention H={H} Lq={Lq} Lkv={Lkv} D={D} splits={splits}: rel err {err}, vs unsplit {err_base}"
+    return dict(err=err, err_vs_unsplit=err_base)
+
+
+def check_attention_splitkv_peers(P=4, L=64, H=2, D=128, splits=2):
+    """The merge kernel in peer mode (Ulysses exchange #2): rows scattered to P emulated ranks' buffers must equal — bit for bit —
+    the merge into one plain tensor."""
+    J = P * L
+    q, k, v = (_randn((1, H, J, D), 70 + i).to(DEV) for i in range(3))
+    plain = ops.attention_splitkv(q, k, v, splits).transpose(1, 2).flatten(2, 3)[0]  # [J, H*D]
+    out = [torch.zeros((L, H * D), dtype=torch.bfloat16, device=DEV) for _ in range(P)]
+    ops.attention_splitkv(q, k, v, splits, o_ptrs=[t.data_ptr() for t in out], rows_per_peer=L, o_strides=(0, D, H * D))
+    torch.cuda.synchronize()
+    assert torch.equal(torch.cat(out, 0), plain), "split-KV merge: peer scatter differs from the plain output"
+    return dict(bit_exact=True)
+
+
+def check_attention_splitkv_sp8_shape(J=40560, H=5, D=128):
+    """The shape one rank sees under 8-way Ulysses at BASELINE config #3 (5 heads, 795 work items = 5.37 waves on 148 SMs), where
+    ops.attention cuts the KV sequence by itself: the automatic path must agree with the unsplit kernel, and both are timed."""
+    g = torch.Generator(device=DEV).manual_seed(2)
+    qkv = torch.randn((1, J, 3 * H * D), generator=g, device=DEV, dtype=torch.float32).to(torch.bfloat16)
+    q, k, v = (qkv[..., i * H * D:(i + 1) * H * D].unflatten(2, (H, D)).transpose(1, 2) for i in range(3))
+    auto = ops.attention_kv_splits(1, H, J, J)
+    base, _ = ops.attention(q, k, v, return_lse=True)  # return_lse keeps the unsplit kernel
+    out = ops.attention(q, k, v)
+
+    def ms(fn, n=5):
+        fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    t_base, t_auto = ms(lambda: ops.attention(q, k, v, return_lse=True)), ms(lambda: ops.attention(q, k, v))
+    err = rel_err(out, base)
+    assert err < 1e-2, f"automatic split-KV ({auto} ranges) vs unsplit: rel err {err}"
+    flop = 4.0 * H * J * J * D
+    return dict(auto_splits=auto, err_vs_unsplit=err, unsplit_ms=t_base, auto_ms=t_auto, unsplit_tflops=flop / t_base / 1e9, auto_tflops=flop / t_auto / 1e9)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # block / model level against the golden fixtures recorded from the reference
 # ---------------------------------------------------------------------------------------------------------------
@@ -487,6 +542,22 @@ def check_ulysses_p2p_emulated(P=4, L=96, H=8, D=128, mode=0):
     return dict(err=err, bit_exact=exact)
 
 
+def check_ulysses_p2p_emulated_splitkv():
+    """The emulated fused exchange with the split-KV path forced on (what 8-way Ulysses uses at 480p: 5 heads per rank): the merge
+    kernel does the peer stores.  Still bit-exact against the single-device path, which splits the same way."""
+    old = os.environ.get("VAP_ATTN_SPLITKV")
+    os.environ["VAP_ATTN_SPLITKV"] = "2"
+    ops._SPLIT_CACHE.clear()
+    try:
+        return check_ulysses_p2p_emulated(P=4, L=96, H=8, D=128, mode=0)
+    finally:
+        if old is None:
+            del os.environ["VAP_ATTN_SPLITKV"]
+        else:
+            os.environ["VAP_ATTN_SPLITKV"] = old
+        ops._SPLIT_CACHE.clear()
+
+
 CHECKS = {
     "probe_ss": lambda: check_probe(False, False, 128, 128),
     "probe_ss_n256": lambda: check_probe(False, False, 256, 64),
@@ -518,9 +589,14 @@ CHECKS = {
     "attn_cross_512": lambda: check_attention(1, 2, 300, 512, 128, joint_layout=False),
     "attn_one_tile": lambda: check_attention(1, 1, 64, 100, 128, joint_layout=False),
     "attn_peaky": lambda: check_attention_peaky(),
+    "attn_splitkv_2": lambda: check_attention_splitkv(1, 2, 300, 1000, 128, 2),
+    "attn_splitkv_3_d64": lambda: check_attention_splitkv(2, 3, 452, 900, 64, 3),
+    "attn_splitkv_uneven": lambda: check_attention_splitkv(1, 1, 130, 128 * 5 + 7, 128, 4),
+    "attn_splitkv_peers": lambda: check_attention_splitkv_peers(),
     "ulysses_relayout": check_ulysses_relayout,
     "ulysses_p2p_emulated_wan": lambda: check_ulysses_p2p_emulated(P=4, L=96, H=8, D=128, mode=0),
     "ulysses_p2p_emulated_p8": lambda: check_ulysses_p2p_emulated(P=8, L=300, H=40, D=128, mode=0),
+    "ulysses_p2p_emulated_splitkv": check_ulysses_p2p_emulated_splitkv,
     "ulysses_p2p_emulated_cog": lambda: check_ulysses_p2p_emulated(P=2, L=130, H=6, D=64, mode=1),
     "wan_blocks": check_wan_blocks,
     "wan_model": check_wan_model,
@@ -532,4 +608,5 @@ CHECKS = {
     "processor_level": check_processor_level,
     "gemm_large": check_gemm_large,
     "attn_full_size": check_attention_full_size,
+    "attn_splitkv_sp8_shape": check_attention_splitkv_sp8_shape,
 }

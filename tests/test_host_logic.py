@@ -185,3 +185,34 @@ def test_bench_reference_arm_contract():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and "sample" in line["cpu_baseline"]
     assert line["e2e"] == {"value": line["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"]
+
+
+def test_attention_kv_split_heuristic(monkeypatch):
+    """The wave model behind the automatic split-KV attention: only shapes whose (batch, head, 256-row) work items are a poor
+    multiple of the 148 SMs are split — the 5-heads-per-rank shape of 8-way Ulysses at 480p — and never a short KV sequence."""
+    monkeypatch.setattr(vap.ops, "sm_count", lambda: 148)
+    ks = vap.ops.attention_kv_splits
+    J = 40560
+    assert ks(1, 5, J, J) == 2            # Ulysses 8 ranks: 795 items = 5.37 waves -> 6; two ranges -> 5.5
+    assert ks(1, 40, J, J) == 1           # single GPU: 42.97 waves
+    assert ks(1, 20, J, J) == 1 and ks(1, 10, J, J) == 1  # 2 and 4 ranks
+    assert ks(1, 5, 151200, 151200) == 1  # 720p at 8 ranks: 19.97 waves
+    assert ks(1, 48, 35552, 35552) == 1   # CogVideoX-5B
+    assert ks(1, 40, 20280, 512) == 1 and ks(1, 2, 300, 300) == 1  # cross-attention / tiny: too few KV tiles to cut
+    monkeypatch.setenv("VAP_ATTN_SPLITKV", "0")
+    vap.ops._SPLIT_CACHE.clear()
+    assert vap.ops._auto_kv_splits(1, 5, J, J) == 1
+    monkeypatch.setenv("VAP_ATTN_SPLITKV", "3")
+    vap.ops._SPLIT_CACHE.clear()
+    assert vap.ops._auto_kv_splits(1, 5, J, J) == 3 and vap.ops._auto_kv_splits(1, 1, 64, 200) == 2  # clamped to the KV tiles
+    vap.ops._SPLIT_CACHE.clear()
+
+
+def test_split_kv_entry_points_validate_arguments():
+    lib = vap._lib.load()
+    assert lib.vap_attention_fwd_splitkv(16, 16, 16, 16, 16, 9, 1, 1, 8, 8, 128, *([8] * 9), 1.0, 0) == -1
+    assert b"kv_splits" in lib.vap_last_error()
+    assert lib.vap_attention_fwd_splitkv(16, 16, 16, 16, 16, 4, 1, 1, 8, 300, 128, *([8] * 9), 1.0, 0) == -1  # 3 KV tiles < 4 ranges
+    assert b"KV tiles" in lib.vap_last_error()
+    assert lib.vap_attention_combine(16, 16, 2, 1, 1, 8, 128, 0, 0, 0, 0, 0, 128, 128, 128, 0) == -1  # neither o nor o_peers
+    assert b"either o or o_peers" in lib.vap_last_error()

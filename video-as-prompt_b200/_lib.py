@@ -36,6 +36,10 @@ SIGNATURES = {
                                 _FLOAT_P, c_int64, c_int64, c_int64, c_float, c_int, c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p]),
     "vap_attention_fwd_scatter": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, _FLOAT_P, c_int, c_int, c_int, c_int, c_int]
                                   + [c_int64] * 12 + [c_float, c_void_p]),
+    "vap_attention_fwd_splitkv": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, _FLOAT_P, c_int, c_int, c_int, c_int, c_int, c_int] + [c_int64] * 9
+                                  + [c_float, c_void_p]),
+    "vap_attention_combine": (c_int, [c_void_p, _FLOAT_P, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, _FLOAT_P, c_int64, c_int64,
+                                      c_int64, c_void_p]),
     "vap_gemm_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
                               c_int64, _FLOAT_P, c_int64, c_int64, c_void_p]),
     "vap_ulysses_pack": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int64, c_int64, c_int64, c_int64, c_void_p]),

@@ -94,8 +94,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * (2 * kBlockM);
     const int head = blockIdx.y;
-    const int batch = blockIdx.z;
-    const int n_kv = (p.Lkv + kBlockN - 1) / kBlockN;
+    // split-KV: grid z = batch * kv_splits + split; this CTA attends to KV tiles [j0, j0 + n_kv) (all of them when kv_splits == 1)
+    const int batch = static_cast<int>(blockIdx.z) / p.kv_splits;
+    const unsigned split = blockIdx.z - static_cast<unsigned>(batch * p.kv_splits);
+    const int n_kv_all = (p.Lkv + kBlockN - 1) / kBlockN;
+    const int j0 = static_cast<int>(split * static_cast<unsigned>(n_kv_all) / static_cast<unsigned>(p.kv_splits));
+    const int n_kv = static_cast<int>((split + 1u) * static_cast<unsigned>(n_kv_all) / static_cast<unsigned>(p.kv_splits)) - j0;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQ);
@@ -153,9 +157,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                         for (int h = 0; h < Cfg::kHalves; ++h) {
                             if (CL == 2)  // my 64 rows of the tile, into both CTAs
                                 tma_load_4d_multicast(dst + h * Cfg::kHalfBytes + cta_rank * (kBlockN / 2) * 128, kv == 0 ? &tmK : &tmV, kv_full(stage), h * 64,
-                                                      j * kBlockN + cta_rank * (kBlockN / 2), head, batch, 3);
+                                                      (j0 + j) * kBlockN + cta_rank * (kBlockN / 2), head, batch, 3);
                             else
-                                tma_load_4d(dst + h * Cfg::kHalfBytes, kv == 0 ? &tmK : &tmV, kv_full(stage), h * 64, j * kBlockN, head, batch);
+                                tma_load_4d(dst + h * Cfg::kHalfBytes, kv == 0 ? &tmK : &tmV, kv_full(stage), h * 64, (j0 + j) * kBlockN, head, batch);
                         }
                     }
                     __syncwarp();
@@ -312,7 +316,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 tmem_ld_16x256b_x8(s_col + 64 * ch, sr);
                 tmem_ld_wait();
                 if (ch == 0) TR(2);
-                const int valid = p.Lkv - j * kBlockN - 64 * ch - 2 * cp;  // this thread's column 8 g + e is inside the sequence iff 8 g + e < valid
+                const int valid = p.Lkv - (j0 + j) * kBlockN - 64 * ch - 2 * cp;  // this thread's column 8 g + e is inside the sequence iff 8 g + e < valid
                 if (valid < 58) {
 #pragma unroll
                     for (int g = 0; g < 8; ++g)
@@ -441,7 +445,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     obase[r] = (peer < 8 ? p.o_peer[peer] : p.o_peer[0]) + batch * p.o_sb + head * p.o_sh + 2 * cp +
                                static_cast<int64_t>(row[r] - peer * p.o_rows_per_peer) * p.o_sl;
                 } else {
-                    obase[r] = p.o + batch * p.o_sb + head * p.o_sh + 2 * cp + static_cast<int64_t>(row[r]) * p.o_sl;
+                    obase[r] = p.o + static_cast<uint64_t>(split) * static_cast<uint64_t>(p.o_split_stride) + batch * p.o_sb + head * p.o_sh + 2 * cp + static_cast<int64_t>(row[r]) * p.o_sl;
                 }
             }
 #pragma unroll 1
@@ -463,7 +467,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             if (p.lse && cp == 0) {
 #pragma unroll
                 for (int r = 0; r < 2; ++r)
-                    if (row[r] < p.Lq) p.lse[(static_cast<int64_t>(batch) * p.H + head) * p.Lq + row[r]] = m_used[r] * p.scale + logf(l[r]);
+                    if (row[r] < p.Lq)
+                        p.lse[static_cast<uint64_t>(split) * static_cast<uint64_t>(p.lse_split_stride) + (static_cast<int64_t>(batch) * p.H + head) * p.Lq + row[r]] = m_used[r] * p.scale + logf(l[r]);
             }
         }
     }
@@ -510,13 +515,13 @@ static int launch_attn_d(const CUtensorMap& tmQ, const CUtensorMap& tmK, const C
     }
     const unsigned q_blocks = static_cast<unsigned>((p.Lq + 2 * kBlockM - 1) / (2 * kBlockM));
     if (CL == 1) {
-        const dim3 grid(q_blocks, p.H, p.B);
+        const dim3 grid(q_blocks, p.H, p.B * p.kv_splits);
         attn_fwd_kernel<D, CL><<<grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(tmQ, tmK, tmV, p);
         VAP_CHECK_CUDA(cudaGetLastError());
         return 0;
     }
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((q_blocks + 1) / 2 * 2, p.H, p.B);  // a trailing CTA without query rows still loads and consumes its share of K / V
+    cfg.gridDim = dim3((q_blocks + 1) / 2 * 2, p.H, p.B * p.kv_splits);  // a trailing CTA without query rows still loads and consumes its share of K / V
     cfg.blockDim = dim3(kAttnThreads);
     cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     cfg.stream = stream;
@@ -531,7 +536,13 @@ static int launch_attn_d(const CUtensorMap& tmQ, const CUtensorMap& tmK, const C
 int launch_attention_fwd(const AttnTensor& q, const AttnTensor& k, const AttnTensor& v, AttnParams p, int D, cudaStream_t stream) {
     VAP_REQUIRE(D == 64 || D == 128, "attention: head_dim=%d must be 64 or 128", D);
     VAP_REQUIRE(p.B > 0 && p.H > 0 && p.Lq >= 0 && p.Lkv > 0, "attention: bad shape B=%d H=%d Lq=%d Lkv=%d", p.B, p.H, p.Lq, p.Lkv);
-    VAP_REQUIRE(p.H <= 65535 && p.B <= 65535, "attention: H and B must be <= 65535");
+    if (p.kv_splits < 1) p.kv_splits = 1;
+    VAP_REQUIRE(p.H <= 65535 && static_cast<int64_t>(p.B) * p.kv_splits <= 65535, "attention: H and B * kv_splits must be <= 65535");
+    if (p.kv_splits > 1) {
+        VAP_REQUIRE(p.kv_splits <= 8 && (p.Lkv + kBlockN - 1) / kBlockN >= p.kv_splits, "attention: kv_splits=%d needs at least that many %d-row KV tiles (Lkv=%d)",
+                    p.kv_splits, kBlockN, p.Lkv);
+        VAP_REQUIRE(p.lse != nullptr && p.o_rows_per_peer == 0, "attention: split-KV writes local partials and needs their log-sum-exp buffer");
+    }
     if (p.o_rows_per_peer > 0) {
         const int npeer = (p.Lq + p.o_rows_per_peer - 1) / p.o_rows_per_peer;
         VAP_REQUIRE(npeer <= 8, "attention: at most 8 output peers");
@@ -549,6 +560,97 @@ int launch_attention_fwd(const AttnTensor& q, const AttnTensor& k, const AttnTen
     if (make_attn_tmap(&tmV, v, p.B, p.H, p.Lkv, D, cluster ? kBlockN / 2 : kBlockN, "v")) return -3;
     if (cluster) return D == 128 ? launch_attn_d<128, 2>(tmQ, tmK, tmV, p, stream) : launch_attn_d<64, 2>(tmQ, tmK, tmV, p, stream);
     return D == 128 ? launch_attn_d<128, 1>(tmQ, tmK, tmV, p, stream) : launch_attn_d<64, 1>(tmQ, tmK, tmV, p, stream);
+}
+
+// ------------------------------------------------------------------------------------------------------------------------
+// split-KV merge: one thread per 8 output channels (16 bytes).  HBM-bound: reads `splits` partial rows + their log-sum-exps,
+// writes one row — to the plain output tensor or straight into the owning peer's buffer (Ulysses exchange #2), exactly like the
+// attention epilogue.
+// ------------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) attn_combine_kernel(const AttnCombineParams p) {
+    const AttnParams& d = p.dst;
+    const int vec_per_head = p.D / 8;
+    const int64_t vec_per_row = static_cast<int64_t>(d.H) * vec_per_head;
+    const int64_t total = static_cast<int64_t>(d.B) * d.Lq * vec_per_row;
+    const int64_t part_stride = static_cast<int64_t>(d.B) * d.Lq * d.H * p.D;  // elements between splits of o_part
+    const int64_t lse_stride = static_cast<int64_t>(d.B) * d.H * d.Lq;
+    for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int c8 = static_cast<int>(idx % vec_per_head);
+        const int head = static_cast<int>((idx / vec_per_head) % d.H);
+        const int64_t brow = idx / vec_per_row;  // batch * Lq + row
+        const int row = static_cast<int>(brow % d.Lq);
+        const int batch = static_cast<int>(brow / d.Lq);
+        const int64_t lse_idx = (static_cast<int64_t>(batch) * d.H + head) * d.Lq + row;
+        float ls[8];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+            if (s < p.splits) {
+                ls[s] = p.lse_part[s * lse_stride + lse_idx];
+                mx = fmaxf(mx, ls[s]);
+            }
+        float wsum = 0.f;
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+            if (s < p.splits) {
+                ls[s] = __expf(ls[s] - mx);
+                wsum += ls[s];
+            }
+        const float inv = 1.f / wsum;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const __nv_bfloat16* src = p.o_part + (brow * d.H + head) * p.D + 8 * c8;
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+            if (s < p.splits) {
+                const uint4 u = ld_nc_v4(src + s * part_stride);
+                const uint32_t* w = reinterpret_cast<const uint32_t*>(&u);
+                const float ws = ls[s] * inv;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = bf16x2_to_float2(w[j]);
+                    acc[2 * j] += ws * f.x;
+                    acc[2 * j + 1] += ws * f.y;
+                }
+            }
+        __nv_bfloat16* out;
+        if (d.o_rows_per_peer > 0) {
+            const int peer = row / d.o_rows_per_peer;
+            out = (peer < 8 ? d.o_peer[peer] : d.o_peer[0]) + batch * d.o_sb + head * d.o_sh + static_cast<int64_t>(row - peer * d.o_rows_per_peer) * d.o_sl;
+        } else {
+            out = d.o + batch * d.o_sb + head * d.o_sh + static_cast<int64_t>(row) * d.o_sl;
+        }
+        uint4 o;
+        o.x = pack_bf16x2(acc[0], acc[1]);
+        o.y = pack_bf16x2(acc[2], acc[3]);
+        o.z = pack_bf16x2(acc[4], acc[5]);
+        o.w = pack_bf16x2(acc[6], acc[7]);
+        st_v4(out + 8 * c8, o);
+        if (d.lse && c8 == 0) d.lse[lse_idx] = mx + __logf(wsum);
+    }
+}
+
+int launch_attention_combine(const AttnCombineParams& p, cudaStream_t stream) {
+    const AttnParams& d = p.dst;
+    VAP_REQUIRE(p.D == 64 || p.D == 128, "attention combine: head_dim=%d must be 64 or 128", p.D);
+    VAP_REQUIRE(p.splits >= 1 && p.splits <= 8, "attention combine: splits=%d must be in [1, 8]", p.splits);
+    VAP_REQUIRE(d.B > 0 && d.H > 0 && d.Lq >= 0, "attention combine: bad shape B=%d H=%d Lq=%d", d.B, d.H, d.Lq);
+    VAP_REQUIRE(p.o_part && p.lse_part && (reinterpret_cast<uintptr_t>(p.o_part) & 15) == 0, "attention combine: partials must be 16-byte aligned");
+    VAP_REQUIRE(d.o_sl % 8 == 0 && d.o_sh % 8 == 0 && d.o_sb % 8 == 0, "attention combine: output strides must be multiples of 8 elements");
+    if (d.o_rows_per_peer > 0) {
+        const int npeer = (d.Lq + d.o_rows_per_peer - 1) / d.o_rows_per_peer;
+        VAP_REQUIRE(npeer <= 8, "attention combine: at most 8 output peers");
+        for (int r = 0; r < npeer; ++r) VAP_REQUIRE(d.o_peer[r] && (reinterpret_cast<uintptr_t>(d.o_peer[r]) & 15) == 0, "attention combine: bad output peer %d", r);
+    } else {
+        VAP_REQUIRE(d.o && (reinterpret_cast<uintptr_t>(d.o) & 15) == 0, "attention combine: output must be 16-byte aligned");
+    }
+    const int64_t total = static_cast<int64_t>(d.B) * d.Lq * d.H * (p.D / 8);
+    if (total == 0) return 0;
+    int64_t blocks = (total + 255) / 256;
+    const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
+    if (blocks > cap) blocks = cap;
+    attn_combine_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(p);
+    VAP_CHECK_CUDA(cudaGetLastError());
+    return 0;
 }
 
 }  // namespace vap

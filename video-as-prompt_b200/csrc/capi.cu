@@ -220,6 +220,49 @@ int vap_attention_fwd_scatter(const void* q, const void* k, const void* v, void*
     return launch_attention_fwd(tq, tk, tv, p, D, static_cast<cudaStream_t>(stream));
 }
 
+int vap_attention_fwd_splitkv(const void* q, const void* k, const void* v, void* o_part, float* lse_part, int kv_splits, int B, int H, int Lq,
+                              int Lkv, int D, int64_t q_sb, int64_t q_sh, int64_t q_sl, int64_t k_sb, int64_t k_sh, int64_t k_sl, int64_t v_sb,
+                              int64_t v_sh, int64_t v_sl, float scale, void* stream) {
+    VAP_REQUIRE(q && k && v && o_part && lse_part, "vap_attention_fwd_splitkv: null tensor");
+    VAP_REQUIRE(kv_splits >= 1 && kv_splits <= 8, "vap_attention_fwd_splitkv: kv_splits=%d must be in [1, 8]", kv_splits);
+    AttnParams p{};
+    p.B = B, p.H = H, p.Lq = Lq, p.Lkv = Lkv;
+    p.o = static_cast<__nv_bfloat16*>(o_part);  // [kv_splits, B, Lq, H, D]
+    p.o_sl = static_cast<int64_t>(H) * D, p.o_sh = D, p.o_sb = static_cast<int64_t>(Lq) * H * D;
+    p.kv_splits = kv_splits;
+    p.o_split_stride = static_cast<int64_t>(B) * Lq * H * D;
+    p.lse = lse_part;  // [kv_splits, B, H, Lq]
+    p.lse_split_stride = static_cast<int64_t>(B) * H * Lq;
+    p.scale = scale;
+    p.scale_log2 = scale * 1.4426950408889634f;
+    p.trace = g_attn_trace;
+    const AttnTensor tq{static_cast<const __nv_bfloat16*>(q), q_sb, q_sh, q_sl};
+    const AttnTensor tk{static_cast<const __nv_bfloat16*>(k), k_sb, k_sh, k_sl};
+    const AttnTensor tv{static_cast<const __nv_bfloat16*>(v), v_sb, v_sh, v_sl};
+    return launch_attention_fwd(tq, tk, tv, p, D, static_cast<cudaStream_t>(stream));
+}
+
+int vap_attention_combine(const void* o_part, const float* lse_part, int kv_splits, int B, int H, int Lq, int D, void* o, void* const* o_peers,
+                          int npeers, int o_rows_per_peer, float* lse, int64_t o_sb, int64_t o_sh, int64_t o_sl, void* stream) {
+    VAP_REQUIRE(o_part && lse_part, "vap_attention_combine: null partials");
+    VAP_REQUIRE((o != nullptr) != (o_peers != nullptr), "vap_attention_combine: pass either o or o_peers");
+    AttnCombineParams p{};
+    p.o_part = static_cast<const __nv_bfloat16*>(o_part);
+    p.lse_part = lse_part;
+    p.splits = kv_splits, p.D = D;
+    p.dst.B = B, p.dst.H = H, p.dst.Lq = Lq;
+    p.dst.o = static_cast<__nv_bfloat16*>(o);
+    if (o_peers) {
+        VAP_REQUIRE(npeers >= 1 && npeers <= 8 && o_rows_per_peer > 0 && static_cast<int64_t>(npeers) * o_rows_per_peer >= Lq,
+                    "vap_attention_combine: %d peers x %d rows do not cover Lq=%d", npeers, o_rows_per_peer, Lq);
+        for (int r = 0; r < npeers; ++r) p.dst.o_peer[r] = static_cast<__nv_bfloat16*>(o_peers[r]);
+        p.dst.o_rows_per_peer = o_rows_per_peer;
+    }
+    p.dst.o_sb = o_sb, p.dst.o_sh = o_sh, p.dst.o_sl = o_sl;
+    p.dst.lse = lse;
+    return launch_attention_combine(p, static_cast<cudaStream_t>(stream));
+}
+
 int vap_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int M, int N, int K, const void* bias,
                   int epilogue, const void* R, int64_t ldr, const float* gate, int64_t gate_stride, int64_t rows_per_batch, void* stream) {
     VAP_REQUIRE(A && W && C, "vap_gemm_bf16: null tensor");

@@ -62,6 +62,84 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
     return 0.5f * x * (1.f + tanhf(inner));
 }
 
+// Epilogue of one accumulator row: thread `lane` of the warp that owns TMEM lane quarter q reads its row (BN fp32 columns at
+// `taddr`, 32 at a time), applies bias / GELU / gated residual with the reference's bf16 rounding points and stores 16-byte vectors.
+template <int BN>
+__device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t taddr, int row, int nb) {
+    const bool row_ok = row < p.M;
+    const float* gate = nullptr;
+    if (p.gate) gate = p.gate + (p.rows_per_batch > 0 ? (row_ok ? row / p.rows_per_batch : 0) : 0) * p.gate_stride;
+    __nv_bfloat16* crow = p.C + static_cast<int64_t>(row) * p.ldc;
+    const __nv_bfloat16* rrow = p.R ? p.R + static_cast<int64_t>(row) * p.ldr : nullptr;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_x32(taddr + c0, v);
+        tmem_ld_wait();
+        const int n0 = nb * BN + c0;
+        if (row_ok && n0 < p.N) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {  // 4 groups of 8 columns = 16-byte stores
+                const int n = n0 + 8 * g;
+                if (n < p.N) {
+                    float y[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) y[j] = __uint_as_float(v[8 * g + j]);
+                    if (p.bias) {
+                        const uint4 bb = *reinterpret_cast<const uint4*>(p.bias + n);
+                        const uint32_t* bu = reinterpret_cast<const uint32_t*>(&bb);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 f = bf16x2_to_float2(bu[j]);
+                            y[2 * j] += f.x;
+                            y[2 * j + 1] += f.y;
+                        }
+                    }
+                    if (p.epilogue != kEpiBias) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) y[j] = bf16_round(y[j]);
+                        if (p.epilogue == kEpiBiasGelu) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) y[j] = gelu_tanh_f(y[j]);
+                        } else {
+                            const uint4 rr = *reinterpret_cast<const uint4*>(rrow + n);
+                            const uint32_t* ru = reinterpret_cast<const uint32_t*>(&rr);
+                            float r[8];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float2 f = bf16x2_to_float2(ru[j]);
+                                r[2 * j] = f.x;
+                                r[2 * j + 1] = f.y;
+                            }
+                            if (p.epilogue == kEpiResAdd) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) y[j] = r[j] + y[j];
+                            } else {
+                                const float4 g0 = *reinterpret_cast<const float4*>(gate + n);
+                                const float4 g1 = *reinterpret_cast<const float4*>(gate + n + 4);
+                                const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                                if (p.epilogue == kEpiGateResF32) {
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) y[j] = r[j] + y[j] * gg[j];
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) y[j] = r[j] + bf16_round(gg[j] * y[j]);
+                                }
+                            }
+                        }
+                    }
+                    uint4 o;
+                    o.x = pack_bf16x2(y[0], y[1]);
+                    o.y = pack_bf16x2(y[2], y[3]);
+                    o.z = pack_bf16x2(y[4], y[5]);
+                    o.w = pack_bf16x2(y[6], y[7]);
+                    *reinterpret_cast<uint4*>(crow + n) = o;
+                }
+            }
+        }
+    }
+}
+
 // CL = 2: the kernel runs as clusters of two CTAs that work on vertically adjacent M-blocks of the SAME N-block: each CTA fetches
 // half of the W tile and TMA multicasts it into both CTAs' shared memory, so the W operand crosses the L2 -> SM fabric once per
 // pair (a third less operand traffic per FLOP, same tile shape / pipeline depth / accumulator double-buffering).  A shared-memory
@@ -195,81 +273,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
 #pragma unroll 1
-            for (int mt = 0; mt < MT; ++mt) {
-                const int row = (mb * MT + mt) * kBM + q * 32 + lane;
-                const bool row_ok = row < p.M;
-                const float* gate = nullptr;
-                if (p.gate) gate = p.gate + (p.rows_per_batch > 0 ? (row_ok ? row / p.rows_per_batch : 0) : 0) * p.gate_stride;
-                __nv_bfloat16* crow = p.C + static_cast<int64_t>(row) * p.ldc;
-                const __nv_bfloat16* rrow = p.R ? p.R + static_cast<int64_t>(row) * p.ldr : nullptr;
-    #pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 32) {
-                    uint32_t v[32];
-                    tmem_ld_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * (MT * BN) + mt * BN + c0, v);
-                    tmem_ld_wait();
-                    const int n0 = nb * BN + c0;
-                    if (row_ok && n0 < p.N) {
-    #pragma unroll
-                        for (int g = 0; g < 4; ++g) {  // 4 groups of 8 columns = 16-byte stores
-                            const int n = n0 + 8 * g;
-                            if (n < p.N) {
-                                float y[8];
-    #pragma unroll
-                                for (int j = 0; j < 8; ++j) y[j] = __uint_as_float(v[8 * g + j]);
-                                if (p.bias) {
-                                    const uint4 bb = *reinterpret_cast<const uint4*>(p.bias + n);
-                                    const uint32_t* bu = reinterpret_cast<const uint32_t*>(&bb);
-    #pragma unroll
-                                    for (int j = 0; j < 4; ++j) {
-                                        const float2 f = bf16x2_to_float2(bu[j]);
-                                        y[2 * j] += f.x;
-                                        y[2 * j + 1] += f.y;
-                                    }
-                                }
-                                if (p.epilogue != kEpiBias) {
-    #pragma unroll
-                                    for (int j = 0; j < 8; ++j) y[j] = bf16_round(y[j]);
-                                    if (p.epilogue == kEpiBiasGelu) {
-    #pragma unroll
-                                        for (int j = 0; j < 8; ++j) y[j] = gelu_tanh_f(y[j]);
-                                    } else {
-                                        const uint4 rr = *reinterpret_cast<const uint4*>(rrow + n);
-                                        const uint32_t* ru = reinterpret_cast<const uint32_t*>(&rr);
-                                        float r[8];
-    #pragma unroll
-                                        for (int j = 0; j < 4; ++j) {
-                                            const float2 f = bf16x2_to_float2(ru[j]);
-                                            r[2 * j] = f.x;
-                                            r[2 * j + 1] = f.y;
-                                        }
-                                        if (p.epilogue == kEpiResAdd) {
-    #pragma unroll
-                                            for (int j = 0; j < 8; ++j) y[j] = r[j] + y[j];
-                                        } else {
-                                            const float4 g0 = *reinterpret_cast<const float4*>(gate + n);
-                                            const float4 g1 = *reinterpret_cast<const float4*>(gate + n + 4);
-                                            const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-                                            if (p.epilogue == kEpiGateResF32) {
-    #pragma unroll
-                                                for (int j = 0; j < 8; ++j) y[j] = r[j] + y[j] * gg[j];
-                                            } else {
-    #pragma unroll
-                                                for (int j = 0; j < 8; ++j) y[j] = r[j] + bf16_round(gg[j] * y[j]);
-                                            }
-                                        }
-                                    }
-                                }
-                                uint4 o;
-                                o.x = pack_bf16x2(y[0], y[1]);
-                                o.y = pack_bf16x2(y[2], y[3]);
-                                o.z = pack_bf16x2(y[4], y[5]);
-                                o.w = pack_bf16x2(y[6], y[7]);
-                                *reinterpret_cast<uint4*>(crow + n) = o;
-                            }
-                        }
-                    }
-                }
-            }
+            for (int mt = 0; mt < MT; ++mt)
+                epilogue_rows<BN>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * (MT * BN) + mt * BN, (mb * MT + mt) * kBM + q * 32 + lane, nb);
             // all TMEM reads of this accumulator stage are complete (tmem_ld_wait) -> release it
             tc_fence_before();
             __syncwarp();
@@ -287,6 +292,164 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------------
+// CTA-pair variant: ONE 256 x 256 output tile per cluster of two CTAs, computed by tcgen05.mma cta_group::2 (M = 256).
+// CTA rank r of the pair stages its own 128 rows of A and HALF of the W tile (rows [128 r, 128 r + 128) of the 256) per k-step:
+// 32 KB per stage and CTA instead of 48 KB, so every byte of shared memory feeds twice the MMA work of the one-CTA kernel
+// (the operand read rate per FLOP halves for W), and seven stages fit.  Protocol (the CUTLASS 2-SM scheme):
+//   full[s]   lives in the LEADER (even CTA): its producer arms it with the bytes of BOTH CTAs' loads; the peer's TMA completes
+//             its transaction bytes there (cp.async.bulk.tensor.cta_group::2)
+//   empty[s]  per CTA; the leader's tcgen05.commit.cta_group::2 arrives on both (multicast)
+//   tfull[a]  per CTA; committed by the leader on both -> each CTA's epilogue warps read their own 128 accumulator rows
+//   tempty[a] lives in the leader, 8 arrivals: the four epilogue warps of BOTH CTAs (the peer's arrive remotely)
+// ------------------------------------------------------------------------------------------------------------------------
+struct GemmPairCfg {
+    static constexpr int BN = 256;
+    static constexpr int kABytes = kBM * kBK * 2;        // this CTA's 128 rows of A
+    static constexpr int kBBytes = (BN / 2) * kBK * 2;   // this CTA's half of the W tile
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStages = 7;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int kTmemCols = 512;  // two accumulator stages x 256 fp32 columns (x 128 lanes in each CTA)
+};
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+    using Cfg = GemmPairCfg;
+    constexpr int BN = Cfg::BN;
+    const int cta_rank = static_cast<int>(cluster_ctarank());
+    const bool leader = cta_rank == 0;
+    const int unit0 = static_cast<int>(cluster_id_x());
+    const int unit_stride = static_cast<int>(cluster_nctaid_x());
+    const int m_units = (p.m_blocks + 1) / 2;  // 256-row blocks
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + 2 + s); };
+    const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * Cfg::kStages + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_tiles = m_units * p.n_blocks;
+    const int k_blocks = (p.K + kBK - 1) / kBK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < Cfg::kStages; ++s) {
+            mbar_init(full_bar(s), 1);   // the leader's producer (arrive + expect_tx); unused in the peer
+            mbar_init(empty_bar(s), 1);  // the leader's commit
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(tfull_bar(s), 1);
+            mbar_init(tempty_bar(s), 8);  // four epilogue warps of each CTA; unused in the peer
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc_pair(tmem_ptr_addr, Cfg::kTmemCols);
+        tmem_relinquish_pair();
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // both CTAs' barriers and TMEM exist before anything crosses the pair
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer (both CTAs) =====
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
+                int mu, nb;
+                tile_coords(tile, m_units, p.n_blocks, mu, nb);
+                const int row0 = (2 * mu + cta_rank) * kBM;
+                const int col0 = nb * BN + cta_rank * (BN / 2);
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    const uint32_t a_dst = smem_base + stage * Cfg::kStageBytes;
+                    const uint32_t b_dst = a_dst + Cfg::kABytes;
+                    if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
+                    tma_load_2d_pair(a_dst, &tmA, full_bar(stage), kb * kBK, row0);
+                    tma_load_2d_pair(b_dst, &tmB, full_bar(stage), kb * kBK, col0);
+                    if (++stage == Cfg::kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader && lane == 0) {
+            // ===== MMA issuer (leader CTA only) =====
+            constexpr uint32_t idesc = make_idesc_bf16(2 * kBM, BN, 0, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_base + stage * Cfg::kStageBytes;
+                    const uint32_t b_addr = a_addr + Cfg::kABytes;
+#pragma unroll
+                    for (int k = 0; k < kBK / 16; ++k)
+                        umma_ss_pair(d_tmem, make_smem_desc(a_addr + k * 32, 0, 1024, kLayoutSw128), make_smem_desc(b_addr + k * 32, 0, 1024, kLayoutSw128), idesc,
+                                     (kb | k) != 0 ? 1u : 0u);
+                    umma_commit_pair(empty_bar(stage), 3);  // frees the slot in both CTAs once these MMAs have read it
+                    if (++stage == Cfg::kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit_pair(tfull_bar(acc), 3);  // accumulator complete -> both CTAs' epilogues
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue warps (both CTAs: each drains its own 128 rows of the accumulator) =====
+        const int q = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
+            int mu, nb;
+            tile_coords(tile, m_units, p.n_blocks, mu, nb);
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            epilogue_rows<BN>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN, (2 * mu + cta_rank) * kBM + q * 32 + lane, nb);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(tempty_bar(acc), 0);
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // no CTA leaves (or frees TMEM) while the pair's MMAs, loads or barrier arrivals may still touch it
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
     }
 }
 
@@ -344,6 +507,47 @@ static int launch_gemm_cluster(const CUtensorMap& tmA, const CUtensorMap& tmB, G
     return 0;
 }
 
+// 256 x 256 tiles on CTA pairs (tcgen05.mma cta_group::2)
+static int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams p, cudaStream_t stream) {
+    using Cfg = GemmPairCfg;
+    static_assert(Cfg::kSmemBytes <= 232448, "shared memory budget");
+    static_assert(2 * Cfg::kStages + 5 <= 32, "barrier area");
+    static int max_clusters = -1;
+    cudaLaunchConfig_t cfg{};
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2, attr.val.clusterDim.y = 1, attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr, cfg.numAttrs = 1;
+    if (max_clusters < 0) {
+        VAP_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        cfg.gridDim = dim3(static_cast<unsigned>(sm_count() / 2 * 2));
+        int n = 0;
+        VAP_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm_bf16_pair_kernel, &cfg));
+        max_clusters = n;
+    }
+    VAP_REQUIRE(max_clusters > 0, "gemm_bf16: no 2-CTA cluster fits on this device");
+    p.m_blocks = (p.M + kBM - 1) / kBM;
+    p.n_blocks = (p.N + 255) / 256;
+    const int units = ((p.m_blocks + 1) / 2) * p.n_blocks;
+    const int clusters = units < max_clusters ? units : max_clusters;
+    cfg.gridDim = dim3(static_cast<unsigned>(2 * clusters));
+    VAP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_pair_kernel, tmA, tmB, p));
+    return 0;
+}
+
+// VAP_GEMM_PAIR: 1 = CTA-pair kernel (cta_group::2) for the wide shapes, 0 = one-CTA kernel.
+static int gemm_pair_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("VAP_GEMM_PAIR");
+        mode = e ? atoi(e) : 0;
+    }
+    return mode;
+}
+
 static int gemm_cluster_mode() {
     static int mode = -1;
     if (mode < 0) {
@@ -383,7 +587,8 @@ int launch_gemm_bf16(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W
     const bool wide = p.N >= 256;
     const int BN = wide ? 256 : 128;
     const int MT = gemm_m_tiles(p.M, p.N);
-    const bool cluster = wide && MT == 1 && gemm_cluster_mode() == 2 && p.M > 2 * kBM;
+    const bool pair = wide && MT == 1 && gemm_pair_mode() == 1 && p.M > kBM;
+    const bool cluster = !pair && wide && MT == 1 && gemm_cluster_mode() == 2 && p.M > 2 * kBM;
     CUtensorMap tmA, tmB;
     {
         const uint64_t dims[2] = {static_cast<uint64_t>(p.K), static_cast<uint64_t>(p.M)};
@@ -394,9 +599,10 @@ int launch_gemm_bf16(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W
     {
         const uint64_t dims[2] = {static_cast<uint64_t>(p.K), static_cast<uint64_t>(p.N)};
         const uint64_t strides[1] = {static_cast<uint64_t>(ldw)};
-        const uint32_t box[2] = {kBK, static_cast<uint32_t>(cluster ? BN / 2 : BN)};
+        const uint32_t box[2] = {kBK, static_cast<uint32_t>((cluster || pair) ? BN / 2 : BN)};
         if (make_tmap_bf16(&tmB, W, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return -3;
     }
+    if (pair) return launch_gemm_pair(tmA, tmB, p, stream);
     if (cluster) return launch_gemm_cluster(tmA, tmB, p, stream);
     if (MT == 2) return launch_gemm_bn<256, 2>(tmA, tmB, p, stream);
     return wide ? launch_gemm_bn<256, 1>(tmA, tmB, p, stream) : launch_gemm_bn<128, 1>(tmA, tmB, p, stream);

@@ -228,6 +228,50 @@ __device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t cta
 }
 
 // ------------------------------------------------------------------------------------------
+// CTA pairs (cta_group::2): two CTAs of a cluster, on the two SMs of a TPC, execute ONE tcgen05.mma of M = 256.  CTA rank r holds
+// rows [128 r, 128 r + 128) of A and rows [N/2 r, N/2 r + N/2) of B in its own shared memory (same CTA-relative offsets) and
+// receives rows [128 r, +128) of D in its own TMEM.  Only the even (leader) CTA issues MMAs and commits; both CTAs issue TMA.
+// ------------------------------------------------------------------------------------------
+// shared::cta address of `bar` as seen in the pair's LEADER CTA (clears the CTA-rank bit of the shared::cluster window address)
+__device__ __forceinline__ uint32_t pair_leader_addr(uint32_t bar) { return bar & 0xFEFFFFFFu; }
+// TMA load into THIS CTA's shared memory whose transaction bytes complete on the LEADER CTA's mbarrier
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(tm)), "r"(pair_leader_addr(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst, uint32_t ncols) {  // one warp of EACH CTA of the pair
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[smem of both CTAs] * B[smem of both CTAs], M = 256; issued by one thread of the leader CTA
+__device__ __forceinline__ void umma_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on the mbarrier at this offset in every CTA of `cta_mask` once the pair's previously issued MMAs have completed
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(cta_mask)
+                 : "memory");
+}
+// arrive on the mbarrier at this offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\tmbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(bar),
+        "r"(cta)
+        : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
 // tcgen05 / TMEM
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {

@@ -58,12 +58,27 @@ struct AttnParams {
     // --- fused all-to-all combine (Ulysses exchange #2 by peer stores); o_rows_per_peer == 0: plain mode (o above) ---
     __nv_bfloat16* o_peer[8];  // query rows [r*rpp, (r+1)*rpp) belong to rank r and are written to o_peer[r] + (row - r*rpp)*o_sl
     int o_rows_per_peer;
+    // --- split-KV (kv_splits > 1): grid z = batch * kv_splits + split; split s attends to its share of the KV tiles and writes a
+    //     normalised partial O at o + s * o_split_stride and its log-sum-exp at lse + s * lse_split_stride (lse is then required);
+    //     launch_attention_combine merges the partials.  Fills the SMs when B * H * ceil(Lq / 256) is a poor multiple of their number.
+    int kv_splits;
+    int64_t o_split_stride, lse_split_stride;  // elements
 };
 struct AttnTensor {
     const __nv_bfloat16* ptr;
     int64_t sb, sh, sl;  // element strides (batch, head, token); the head_dim axis is contiguous
 };
 int launch_attention_fwd(const AttnTensor& q, const AttnTensor& k, const AttnTensor& v, AttnParams p, int D, cudaStream_t stream);
+
+// Merge of split-KV partials: O = sum_s w_s O_s, w_s = exp(lse_s - lse) ; the result goes to `dst` exactly as the attention
+// epilogue would have written it (plain strided tensor or rows scattered to their owning peers; dst.lse optional).
+struct AttnCombineParams {
+    const __nv_bfloat16* o_part;  // [splits, B, Lq, H, D] contiguous
+    const float* lse_part;        // [splits, B, H, Lq]
+    int splits, D;
+    AttnParams dst;               // B, H, Lq, o / o_peer / o_rows_per_peer / strides / lse of the destination
+};
+int launch_attention_combine(const AttnCombineParams& p, cudaStream_t stream);
 
 struct GemmParams {
     int M, N, K;

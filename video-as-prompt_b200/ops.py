@@ -142,6 +142,10 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: Optio
     Lkv = k.shape[2]
     if k.shape != (B, H, Lkv, D) or v.shape != (B, H, Lkv, D):
         raise ValueError(f"q {tuple(q.shape)}, k {tuple(k.shape)}, v {tuple(v.shape)} are inconsistent")
+    if not return_lse and Lq > 0:
+        splits = _auto_kv_splits(B, H, Lq, Lkv)
+        if splits > 1:  # the work items are a poor multiple of the SM count: cut the KV sequence and merge (see attention_kv_splits)
+            return attention_splitkv(q, k, v, splits, scale=scale, out=out)
     if out is None:
         out = torch.empty((B, Lq, H, D), dtype=torch.bfloat16, device=q.device).transpose(1, 2)
     _need_cuda_bf16(out, "out")
@@ -156,6 +160,86 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: Optio
                                v.stride(1), v.stride(2), out.stride(0), out.stride(1), out.stride(2), float(scale), _stream())
     _lib.check(rc, "vap_attention_fwd")
     return (out, lse) if return_lse else out
+
+
+_SPLIT_CACHE = {}
+
+
+def _auto_kv_splits(B: int, H: int, Lq: int, Lkv: int) -> int:
+    """Split count `attention` / `attention_scatter` use by themselves: VAP_ATTN_SPLITKV = "auto" (default: the wave model of
+    attention_kv_splits), "0" / "1" (never split) or a number in [2, 8] (always split, for testing)."""
+    import os
+    key = (B, H, Lq, Lkv)
+    s = _SPLIT_CACHE.get(key)
+    if s is None:
+        mode = os.environ.get("VAP_ATTN_SPLITKV", "auto")
+        if mode == "auto":
+            s = attention_kv_splits(B, H, Lq, Lkv)
+        else:
+            s = max(1, min(int(mode), 8, (Lkv + 127) // 128))
+        _SPLIT_CACHE[key] = s
+    return s
+
+
+def attention_kv_splits(B: int, H: int, Lq: int, Lkv: int, min_gain: float = 0.03) -> int:
+    """How many KV ranges to cut the attention into so that the (batch, head, 256 query rows) work items fill the SMs.
+    The kernel runs one item per SM at a time, so T ~ ceil(items / SMs); with s ranges T ~ ceil(s * items / SMs) / s plus ~1 % for
+    the extra prologues and the merge.  Returns 1 unless a split gains at least `min_gain` (e.g. 5 heads x 159 blocks = 795 items =
+    5.37 waves on 148 SMs -> 6; two ranges: 10.74 -> 11 half-waves = 5.5)."""
+    items = B * H * ((Lq + 255) // 256)
+    sms = sm_count()
+    kv_tiles = (Lkv + 127) // 128
+    best, best_t = 1, float(-(-items // sms))
+    for s in (2, 3, 4):
+        if kv_tiles < 16 * s:  # keep every range long enough to amortise its prologue / epilogue
+            break
+        t = -(-(items * s) // sms) / s * 1.01
+        if t < best_t * (1.0 - min_gain):
+            best, best_t = s, t
+    return best
+
+
+def attention_splitkv(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, kv_splits: int, *, scale: Optional[float] = None,
+                      out: Optional[torch.Tensor] = None, o_ptrs=None, rows_per_peer: int = 0, o_strides=None) -> Optional[torch.Tensor]:
+    """Attention with the KV sequence cut into `kv_splits` ranges (vap_attention_fwd_splitkv) followed by the merge kernel
+    (vap_attention_combine).  The merged result goes to `out` / a fresh token-major tensor like `attention`, or — with o_ptrs /
+    rows_per_peer / o_strides as in `attention_scatter` — straight into the owning ranks' buffers."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _need_cuda_bf16(t, n)
+        if t.dim() != 4 or t.stride(-1) != 1:
+            raise ValueError(f"{n} must be [B,H,L,D] with contiguous D, got shape {tuple(t.shape)} strides {t.stride()}")
+    B, H, Lq, D = q.shape
+    Lkv = k.shape[2]
+    if k.shape != (B, H, Lkv, D) or v.shape != (B, H, Lkv, D):
+        raise ValueError(f"q {tuple(q.shape)}, k {tuple(k.shape)}, v {tuple(v.shape)} are inconsistent")
+    if not 1 <= kv_splits <= 8:
+        raise ValueError(f"kv_splits={kv_splits} must be in [1, 8]")
+    if scale is None:
+        scale = D ** -0.5
+    o_part = torch.empty((kv_splits, B, Lq, H, D), dtype=torch.bfloat16, device=q.device)
+    lse_part = torch.empty((kv_splits, B, H, Lq), dtype=torch.float32, device=q.device)
+    lib = _lib.load()
+    rc = lib.vap_attention_fwd_splitkv(q.data_ptr(), k.data_ptr(), v.data_ptr(), o_part.data_ptr(), lse_part.data_ptr(), int(kv_splits), B, H, Lq,
+                                       Lkv, D, q.stride(0), q.stride(1), q.stride(2), k.stride(0), k.stride(1), k.stride(2), v.stride(0),
+                                       v.stride(1), v.stride(2), float(scale), _stream())
+    _lib.check(rc, "vap_attention_fwd_splitkv")
+    if o_ptrs is not None:
+        if len(o_ptrs) * rows_per_peer < Lq:
+            raise ValueError(f"{len(o_ptrs)} peers x {rows_per_peer} rows do not cover Lq={Lq}")
+        table = _ptr_table(o_ptrs)
+        rc = lib.vap_attention_combine(o_part.data_ptr(), lse_part.data_ptr(), int(kv_splits), B, H, Lq, D, 0, table, len(o_ptrs), int(rows_per_peer), 0,
+                                       int(o_strides[0]), int(o_strides[1]), int(o_strides[2]), _stream())
+        _lib.check(rc, "vap_attention_combine")
+        return None
+    if out is None:
+        out = torch.empty((B, Lq, H, D), dtype=torch.bfloat16, device=q.device).transpose(1, 2)
+    _need_cuda_bf16(out, "out")
+    if out.shape != (B, H, Lq, D) or out.stride(-1) != 1:
+        raise ValueError(f"out must be [B,H,Lq,D] with contiguous D, got {tuple(out.shape)}")
+    rc = lib.vap_attention_combine(o_part.data_ptr(), lse_part.data_ptr(), int(kv_splits), B, H, Lq, D, out.data_ptr(), 0, 0, 0, 0, out.stride(0),
+                                   out.stride(1), out.stride(2), _stream())
+    _lib.check(rc, "vap_attention_combine")
+    return out
 
 
 def _ptr_table(ptrs):
@@ -206,6 +290,10 @@ def attention_scatter(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, o_pt
         raise ValueError(f"q {tuple(q.shape)}, k {tuple(k.shape)}, v {tuple(v.shape)} are inconsistent")
     if len(o_ptrs) * rows_per_peer < Lq:
         raise ValueError(f"{len(o_ptrs)} peers x {rows_per_peer} rows do not cover Lq={Lq}")
+    splits = _auto_kv_splits(B, H, Lq, Lkv)
+    if splits > 1:  # e.g. 5 heads per rank under 8-way Ulysses: the merge kernel does the peer stores
+        attention_splitkv(q, k, v, splits, scale=scale, o_ptrs=o_ptrs, rows_per_peer=rows_per_peer, o_strides=o_strides)
+        return
     if scale is None:
         scale = D ** -0.5
     lib = _lib.load()
