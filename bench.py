@@ -257,7 +257,8 @@ def main():
     vap.ops.attention = timed_attn(vap.ops.attention)
     vap.ops.attention_scatter = timed_attn(vap.ops.attention_scatter)  # Ulysses peer-memory mode: the same kernel with a fused exchange epilogue
     lib = vap._lib.load()
-    for name in ("vap_adaln_layernorm", "vap_qk_norm_rope", "vap_qkv_scatter", "vap_attention_fwd", "vap_attention_fwd_scatter", "vap_gemm_bf16",
+    for name in ("vap_adaln_layernorm", "vap_qk_norm_rope", "vap_qkv_scatter", "vap_attention_fwd", "vap_attention_fwd_scatter", "vap_attention_fwd_splitkv",
+                 "vap_attention_combine", "vap_gemm_bf16",
                  "vap_ulysses_pack", "vap_ulysses_unpack"):
         fn = getattr(lib, name)
 

@@ -5,13 +5,18 @@
 // activations [M,K] row-major and weights [N,K] row-major, i.e. both operands K-major — exactly the
 // layout UMMA wants, so neither side is transposed or repacked.
 //
-// Persistent, warp-specialised kernel, one CTA per SM:
+// Two persistent, warp-specialised kernels; a per-shape wave model (gemm_use_pair) picks one:
+//   gemm_bf16_pair_kernel : 256 x 256 output tile per CLUSTER OF TWO CTAs on tcgen05.mma cta_group::2 (M = 256 across the SM pair:
+//                           each CTA stages its 128 rows of A and half of the W tile) — the large MoT projections
+//   gemm_bf16_kernel      : 128 x BN tile per CTA (cta_group::1) — small / narrow problems, described next
+// One-CTA kernel, one CTA per SM:
 //   warp 0   : TMA producer  (A tile 128x64, W tile BNx64 per stage, SWIZZLE_128B, kStages-deep mbarrier ring)
 //   warp 1   : MMA issuer    (one elected thread, tcgen05.mma cta_group::1 kind::f16, M=128 N=BN K=16)
 //   warp 2   : TMEM allocator (2 accumulator stages x BN fp32 columns)
 //   warps 4-7: epilogue      (tcgen05.ld -> bias / GELU / gated residual with the reference's bf16 rounding
 //                             points -> 16-byte global stores), overlapped with the next tile's main loop.
 #include <cstdlib>
+#include <cstring>
 #include "vap_kernels.cuh"
 
 namespace vap {
@@ -28,7 +33,13 @@ enum GemmEpilogue : int {
 constexpr int kBM = 128;
 constexpr int kBK = 64;
 constexpr int kGemmThreads = 256;
-constexpr int kGroupM = 16;
+#ifndef VAP_GEMM_GROUP_M
+#define VAP_GEMM_GROUP_M 16
+#endif
+#ifndef VAP_GEMM_PAIR_STAGES
+#define VAP_GEMM_PAIR_STAGES 7
+#endif
+constexpr int kGroupM = VAP_GEMM_GROUP_M;  // M-blocks (pair kernel: 256-row units) that share one sweep over N
 
 // MT = M-tiles (128 rows each) per CTA tile.  MT = 2 (256 x 256 tile, two MMAs per k-step sharing one W tile) streams a third less
 // operand data from L2 per FLOP than MT = 1 (128 x 256) but its two accumulators fill all 512 TMEM columns (the epilogue of a
@@ -311,7 +322,7 @@ struct GemmPairCfg {
     static constexpr int kABytes = kBM * kBK * 2;        // this CTA's 128 rows of A
     static constexpr int kBBytes = (BN / 2) * kBK * 2;   // this CTA's half of the W tile
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = 7;
+    static constexpr int kStages = VAP_GEMM_PAIR_STAGES;
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
     static constexpr int kTmemCols = 512;  // two accumulator stages x 256 fp32 columns (x 128 lanes in each CTA)
 };
@@ -538,14 +549,25 @@ static int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, Gemm
     return 0;
 }
 
-// VAP_GEMM_PAIR: 1 = CTA-pair kernel (cta_group::2) for the wide shapes, 0 = one-CTA kernel.
-static int gemm_pair_mode() {
-    static int mode = -1;
-    if (mode < 0) {
+// Which kernel runs a wide (N >= 256) shape.  Measured on the MoT shapes (tools/gemm_pair_ab.sh, B200): the CTA-pair kernel reaches
+// 1470-1545 TFLOP/s where the one-CTA kernel reaches 1405-1440 (cuBLAS 1460-1645), but its 256 x 256 units quantise worse on small
+// problems (M = 769: 673 vs 848).  So, per shape, a wave model decides: a pair unit (two tiles of work on two SMs) takes ~0.94 of a
+// one-CTA tile time.  VAP_GEMM_PAIR = "auto" (default) | 0 (never) | 1 (every eligible shape).
+static bool gemm_use_pair(int M, int N) {
+    static int mode = -2;
+    if (mode == -2) {
         const char* e = getenv("VAP_GEMM_PAIR");
-        mode = e ? atoi(e) : 0;
+        mode = (!e || !strcmp(e, "auto")) ? -1 : atoi(e);
     }
-    return mode;
+    if (M <= kBM || N < 256 || mode == 0) return false;
+    if (mode == 1) return true;
+    const int sms = sm_count();
+    const int n_blocks = (N + 255) / 256;
+    const int64_t tiles = static_cast<int64_t>((M + kBM - 1) / kBM) * n_blocks;
+    const int64_t units = static_cast<int64_t>((M + 2 * kBM - 1) / (2 * kBM)) * n_blocks;
+    const int64_t waves_one = (tiles + sms - 1) / sms;
+    const int64_t waves_pair = (units + sms / 2 - 1) / (sms / 2);
+    return 0.94 * static_cast<double>(waves_pair) < static_cast<double>(waves_one);
 }
 
 static int gemm_cluster_mode() {
@@ -587,7 +609,7 @@ int launch_gemm_bf16(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W
     const bool wide = p.N >= 256;
     const int BN = wide ? 256 : 128;
     const int MT = gemm_m_tiles(p.M, p.N);
-    const bool pair = wide && MT == 1 && gemm_pair_mode() == 1 && p.M > kBM;
+    const bool pair = wide && MT == 1 && gemm_cluster_mode() != 2 && gemm_use_pair(p.M, p.N);
     const bool cluster = !pair && wide && MT == 1 && gemm_cluster_mode() == 2 && p.M > 2 * kBM;
     CUtensorMap tmA, tmB;
     {
