@@ -22,10 +22,10 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops
+from . import ops, ulysses
 from .modules import AdaLayerNorm, Attention, CogVideoXLayerNormZero, FeedForward, TimestepEmbedding
 from .rope import Tables, as_tables
-from .wan import _f32, _heads_view, _linear, _Output, _packed, _token_major
+from .wan import _f32, _heads_view, _joint_attention, _linear, _Output, _packed, _sp_p2p, _token_major
 
 
 def _mods(norm: nn.Module, temb: torch.Tensor) -> torch.Tensor:
@@ -48,21 +48,27 @@ def _ln_zero(norm: nn.Module, x: torch.Tensor, mods: torch.Tensor, text: bool, r
                         ln_b=_f32(norm.norm, "b", norm.norm.bias), scale1p=mods[:, i + 1], shift=mods[:, i], rows_per_batch=rows_per_mod, out=out)
 
 
-def _qkv(attn: nn.Module, h: torch.Tensor, T: int, tables: Optional[Tables], out: torch.Tensor) -> None:
+def _qkv(attn: nn.Module, h: torch.Tensor, T: int, tables: Optional[Tables], out: torch.Tensor, scatter=None) -> None:
     """to_q/k/v + per-head LayerNorm + RoPE on the video tokens (attention_processor.py:2923-2945), one batch element.
-    h [L, d] -> out [L, 3*inner] (row-slice of the joint buffer)."""
+    h [L, d] -> out [L, 3*inner] (row-slice of the joint buffer).
+    scatter = (PeerExchange, row0): Ulysses peer-memory mode — the norm + RoPE kernel stores its results (and V) straight into the
+    receive buffers of the ranks owning the heads; `out` then only holds the raw projection."""
     W, bvec = _packed(attn, "qkv", [attn.to_q, attn.to_k, attn.to_v])
     inner = W.shape[0] // 3
     heads = attn.heads
     ops.linear(h, W, bvec, out=out)
-    if attn.norm_q is not None:
-        ops.qk_norm_rope_(out[:, :inner], out[:, inner:2 * inner], heads=heads, head_dim=inner // heads,
-                          wq=_f32(attn.norm_q, "w", attn.norm_q.weight), bq=_f32(attn.norm_q, "b", attn.norm_q.bias),
-                          wk=_f32(attn.norm_k, "w", attn.norm_k.weight), bk=_f32(attn.norm_k, "b", attn.norm_k.bias),
-                          cos=tables[0] if tables else None, sin=tables[1] if tables else None, rows_per_batch=h.shape[0], rope_row0=T,
-                          eps=attn.norm_q.eps, mode=ops.QK_COG)
-    elif tables is not None:
-        raise NotImplementedError("RoPE without qk LayerNorm is not a CogVideoX-VAP configuration")
+    if attn.norm_q is None:
+        if tables is not None or scatter is not None:
+            raise NotImplementedError("RoPE / sequence parallelism without qk LayerNorm is not a CogVideoX-VAP configuration")
+        return
+    norm_rope = dict(wq=_f32(attn.norm_q, "w", attn.norm_q.weight), bq=_f32(attn.norm_q, "b", attn.norm_q.bias),
+                     wk=_f32(attn.norm_k, "w", attn.norm_k.weight), bk=_f32(attn.norm_k, "b", attn.norm_k.bias),
+                     cos=tables[0] if tables else None, sin=tables[1] if tables else None, rows_per_batch=h.shape[0], rope_row0=T,
+                     eps=attn.norm_q.eps, mode=ops.QK_COG)
+    if scatter is not None:
+        scatter[0].dispatch(out, scatter[1], **norm_rope)
+    else:
+        ops.qk_norm_rope_(out[:, :inner], out[:, inner:2 * inner], heads=heads, head_dim=inner // heads, **norm_rope)
 
 
 def _gated(lin: nn.Linear, a: torch.Tensor, res: torch.Tensor, gate: torch.Tensor, rows_per_gate: int, out: torch.Tensor) -> None:
@@ -80,7 +86,7 @@ class _Stream:
         self.temb = temb                                  # [B * nmod, time_embed_dim]
         self.nmod = nmod                                  # modulation vectors per batch element (n refs, or 1)
         self.S, self.T = v.shape[1], e.shape[1]
-        self.sv, self.se = self.S // nmod, self.T // nmod  # tokens per modulation vector
+        self.sv, self.se = max(self.S // nmod, 1), max(self.T // nmod, 1)  # tokens per modulation vector
         self.tables = tables
         self.mods1 = _mods(self.norm1, temb)
 
@@ -106,9 +112,11 @@ def cog_block_forward(self: nn.Module, hidden_states: torch.Tensor, encoder_hidd
     streams = [_Stream(self, "", hidden_states, encoder_hidden_states, temb, 1, as_tables(image_rotary_emb, hd, dev))]
     if self.with_mot_ref:
         multi = temb_list_mot_ref is not None
+        if multi and ulysses.current() is not None:
+            raise NotImplementedError("Ulysses sequence parallelism with per-reference timesteps (temb_list_mot_ref) is not supported")
         if multi == (temb_mot_ref is not None):
             raise NotImplementedError("Not supprted for temb_list_mot_ref is not None and temb_mot_ref is not None or both are None")
-        n = hidden_states_mot_ref.shape[1] // S
+        n = hidden_states_mot_ref.shape[1] // S if multi else 1
         # multi-ref: the reference reshapes the ref stream to (B*n, S, d) against cat(temb_list) (:393-401), i.e. reshaped
         # row r = b*n + i takes modulation row r of the concatenation
         temb_r = torch.cat(temb_list_mot_ref, dim=0) if multi else temb_mot_ref
@@ -116,22 +124,29 @@ def cog_block_forward(self: nn.Module, hidden_states: torch.Tensor, encoder_hidd
                                as_tables(image_rotary_emb_mot_ref, hd, dev)))
 
     # ---- norm1 + fused QKV of every stream into the joint buffer [text | video | text_ref | video_ref] ------------
+    # Under Ulysses sequence parallelism the rows of every stream are this rank's shard of its [text | video] sequence (the shell
+    # shards them: rank 0 holds the text rows, st.T may be 0 elsewhere); the joint attention then does the two exchanges.
     J = sum(st.T + st.S for st in streams)
     qkv = torch.empty((B, J, 3 * inner), dtype=torch.bfloat16, device=dev)
+    px = _sp_p2p(hidden_states, J, heads, hd)  # PeerExchange in peer-memory mode (B == 1), else None
     for b in range(B):
         row = 0
         for st in streams:
             L = st.T + st.S
             h = torch.empty((L, d), dtype=torch.bfloat16, device=dev)
             m = st.mods_of(st.mods1, b)
-            _ln_zero(st.norm1, st.e[b], m, True, st.se, h[:st.T])
-            _ln_zero(st.norm1, st.v[b], m, False, st.sv, h[st.T:])
-            _qkv(st.attn, h, st.T, st.tables, qkv[b, row:row + L])
+            if st.T:
+                _ln_zero(st.norm1, st.e[b], m, True, st.se, h[:st.T])
+            if st.S:
+                _ln_zero(st.norm1, st.v[b], m, False, st.sv, h[st.T:])
+            _qkv(st.attn, h, st.T, st.tables, qkv[b, row:row + L], scatter=(px, row) if px is not None else None)
             row += L
 
     # ---- joint attention ---------------------------------------------------------------------------------------
-    q, k, vv = (_heads_view(qkv[..., i * inner:(i + 1) * inner], heads) for i in range(3))
-    o = _token_major(ops.attention(q, k, vv))  # [B, J, inner]
+    if px is not None:
+        o = px.attention().unsqueeze(0)     # exchanges fused into the kernels over NVLink peer memory
+    else:
+        o = _joint_attention(qkv, heads)    # [B, J, inner]; NCCL all-to-alls around the kernel when Ulysses runs in "nccl" mode
 
     # ---- per stream: to_out + gated residual, norm2, FFN + gated residual ------------------------------------------
     outs = []
@@ -144,17 +159,23 @@ def cog_block_forward(self: nn.Module, hidden_states: torch.Tensor, encoder_hidd
             m1 = st.mods_of(st.mods1, b)
             e1 = torch.empty((st.T, d), dtype=torch.bfloat16, device=dev)
             v1 = torch.empty((st.S, d), dtype=torch.bfloat16, device=dev)
-            _gated(st.attn.to_out[0], o[b, row:row + st.T], st.e[b], m1[:, 5], st.se, e1)
-            _gated(st.attn.to_out[0], o[b, row + st.T:row + L], st.v[b], m1[:, 2], st.sv, v1)
+            if st.T:
+                _gated(st.attn.to_out[0], o[b, row:row + st.T], st.e[b], m1[:, 5], st.se, e1)
+            if st.S:
+                _gated(st.attn.to_out[0], o[b, row + st.T:row + L], st.v[b], m1[:, 2], st.sv, v1)
             if mods2 is None:
                 mods2 = _mods(st.norm2, st.temb)
             m2 = st.mods_of(mods2, b)
             h2 = torch.empty((L, d), dtype=torch.bfloat16, device=dev)
-            _ln_zero(st.norm2, e1, m2, True, st.se, h2[:st.T])
-            _ln_zero(st.norm2, v1, m2, False, st.sv, h2[st.T:])
+            if st.T:
+                _ln_zero(st.norm2, e1, m2, True, st.se, h2[:st.T])
+            if st.S:
+                _ln_zero(st.norm2, v1, m2, False, st.sv, h2[st.T:])
             f1 = _linear(st.ff.net[0].proj, h2, epilogue=ops.EPI_BIAS_GELU)
-            _gated(st.ff.net[2], f1[:st.T], e1, m2[:, 5], st.se, e_out[b])
-            _gated(st.ff.net[2], f1[st.T:], v1, m2[:, 2], st.sv, v_out[b])
+            if st.T:
+                _gated(st.ff.net[2], f1[:st.T], e1, m2[:, 5], st.se, e_out[b])
+            if st.S:
+                _gated(st.ff.net[2], f1[st.T:], v1, m2[:, 2], st.sv, v_out[b])
         outs += [v_out, e_out]
         row += L
     if not self.with_mot_ref:
@@ -258,6 +279,23 @@ class CogVideoXPatchEmbed(nn.Module):
         return emb
 
 
+def _shard_stream(seq: torch.Tensor, text_len: int, rotary, head_dim: int, sp, heads: int):
+    """This rank's rows of one stream's [text | video] sequence [1, T + S, d] -> (text rows, video rows, RoPE tables of those video
+    rows).  Rows are cut uniformly over the concatenation, as the reference's context-parallel split hook cuts its inputs
+    (finetrainers/parallel/ptd.py:545-628)."""
+    L = seq.shape[1]
+    ulysses.check_divisible(L, heads, sp.world)
+    n = L // sp.world
+    r0 = sp.rank * n
+    t_loc = min(max(text_len - r0, 0), n)   # text rows on this rank
+    v0 = r0 + t_loc - text_len              # first video token on this rank
+    loc = seq[:, r0:r0 + n]
+    tables = as_tables(rotary, head_dim, seq.device)
+    if tables is not None:  # a rank holding text rows only rotates nothing
+        tables = tuple(t[v0:v0 + n - t_loc].contiguous() for t in tables) if n > t_loc else None
+    return loc[:, :t_loc].contiguous(), loc[:, t_loc:].contiguous(), tables
+
+
 class CogVideoXTransformer3DMOTModel(nn.Module):
     """Stand-alone mirror of the reference model (cogvideox_transformer_3d_mot.py:517-1106): same constructor kwargs (the
     subset the VAP checkpoints use), module names and forward signature."""
@@ -327,18 +365,42 @@ class CogVideoXTransformer3DMOTModel(nn.Module):
             emb_r, emb_list_r = self._time(self.time_embedding_mot_ref, timestep, inner, dt), None
         assert hidden_states_mot_ref.shape[1] // Fr == num_mot_ref, f"hidden_states_mot_ref.shape[1]: {hidden_states_mot_ref.shape}"
 
+        sp = ulysses.current()
+        if sp is not None and B > 1:
+            # classifier-free guidance hands the shell one B = 2 batch (pipeline_cogvideox_image2video_mot.py:972-1001); the exchange
+            # buffers are per sequence, so under sequence parallelism the batch elements run one after the other
+            outs = []
+            for b in range(B):
+                pick = lambda t: t[b:b + 1] if torch.is_tensor(t) and t.dim() > 0 and t.shape[0] == B else t  # noqa: E731
+                outs.append(self.forward(pick(hidden_states), pick(encoder_hidden_states), pick(timestep), timestep_cond, ofs, image_rotary_emb,
+                                         attention_kwargs, False, num_mot_ref, pick(hidden_states_mot_ref), pick(encoder_hidden_states_mot_ref),
+                                         image_rotary_emb_mot_ref, effect_types, reference_train_mode,
+                                         None if timestep_list_mot_ref is None else [pick(t) for t in timestep_list_mot_ref])[0])
+            out = torch.cat(outs, dim=0)
+            return (out,) if not return_dict else _Output(sample=out)
+
         h = self.patch_embed(encoder_hidden_states, hidden_states)
-        e, v = h[:, :Ttok], h[:, Ttok:]
         vs, es = [], []
         for i in range(num_mot_ref):
             hi = self.patch_embed_mot_ref(encoder_hidden_states_mot_ref[:, i * Ttok:(i + 1) * Ttok], hidden_states_mot_ref[:, i * Fr:(i + 1) * Fr])
             es.append(hi[:, :Ttok]), vs.append(hi[:, Ttok:])
-        v_r, e_r = torch.cat(vs, dim=1), torch.cat(es, dim=1)
+        rope, rope_r = image_rotary_emb, image_rotary_emb_mot_ref
+        if sp is None:
+            e, v = h[:, :Ttok], h[:, Ttok:]
+            v_r, e_r = torch.cat(vs, dim=1), torch.cat(es, dim=1)
+        else:
+            # Ulysses: rank r owns rows [r n, (r+1) n) of each stream's [text | video] sequence (17 776 / 8 = 2 222), so
+            # rank 0 holds the text rows in front of its video rows and the others hold video rows only; RoPE tables follow the rows
+            if num_mot_ref != 1:
+                raise NotImplementedError("Ulysses sequence parallelism supports one reference video (num_mot_ref == 1)")
+            hd = cfg["attention_head_dim"]
+            (e, v, rope), (e_r, v_r, rope_r) = (_shard_stream(t, Ttok, r, hd, sp, cfg["num_attention_heads"])
+                                                for t, r in ((h, image_rotary_emb), (torch.cat([es[0], vs[0]], dim=1), image_rotary_emb_mot_ref)))
 
         for block in self.transformer_blocks:
-            v, e, v_r, e_r = block(hidden_states=v, encoder_hidden_states=e, temb=emb, image_rotary_emb=image_rotary_emb,
+            v, e, v_r, e_r = block(hidden_states=v, encoder_hidden_states=e, temb=emb, image_rotary_emb=rope,
                                    attention_kwargs=attention_kwargs, hidden_states_mot_ref=v_r, encoder_hidden_states_mot_ref=e_r,
-                                   temb_mot_ref=emb_r, temb_list_mot_ref=emb_list_r, image_rotary_emb_mot_ref=image_rotary_emb_mot_ref)
+                                   temb_mot_ref=emb_r, temb_list_mot_ref=emb_list_r, image_rotary_emb_mot_ref=rope_r)
 
         v = ops.adaln_layernorm(v, eps=self.norm_final.eps, rounding=ops.ROUND_COG, ln_w=_f32(self.norm_final, "w", self.norm_final.weight),
                                 ln_b=_f32(self.norm_final, "b", self.norm_final.bias))
@@ -349,6 +411,9 @@ class CogVideoXTransformer3DMOTModel(nn.Module):
         v = ops.adaln_layernorm(v, eps=self.norm_out.norm.eps, rounding=ops.ROUND_COG, ln_w=_f32(self.norm_out.norm, "w", self.norm_out.norm.weight),
                                 ln_b=_f32(self.norm_out.norm, "b", self.norm_out.norm.bias), scale1p=m[:, 1], shift=m[:, 0])
         v = self.proj_out(v)
+        if sp is not None:  # all-gather the rank-local rows (rank 0's are preceded by its text rows, padded here) and drop the text rows
+            pad = v.new_zeros((B, e.shape[1], v.shape[-1]))
+            v = ulysses.gather_rows(torch.cat([pad, v], dim=1), sp)[:, Ttok:]
         p = cfg["patch_size"]
         out = v.reshape(B, Fr, H // p, W // p, -1, p, p).permute(0, 1, 4, 2, 5, 3, 6).flatten(5, 6).flatten(3, 4)
         if not return_dict:
