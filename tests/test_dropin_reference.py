@@ -1,0 +1,74 @@
+"""CPU, authoring container only (skipped where /root/reference does not exist, e.g. on the GPU box): the drop-in boundary on the
+REFERENCE's own classes.  The reference's WanTransformer3DMOTModel / CogVideoXTransformer3DMOTModel are imported from
+/root/reference, filled with synthetic weights and run on CPU as they are; then `vap_b200.install(model, level=...)` rebinds the
+block forwards (B3) or swaps the attention processors + the SDPA slot (B1 + B2) on those very instances — kernels replaced by the
+torch stand-ins of tests/cpu_standin_ops.py — and the SAME pipeline-facing call must give the same output within the bf16 gate, and
+`uninstall` must restore the reference's behaviour bit for bit.  This is the host-side half of the drop-in claim; the kernels' half
+is `-m gpu`."""
+import importlib
+import os
+import sys
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("VAP_REFERENCE", "/root/reference")
+
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "diffusers", "src")), reason="the reference tree is not present here")
+
+
+def _worker(family, q):
+    try:
+        sys.path.insert(0, ROOT)
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        sys.path.insert(0, os.path.join(REF, "diffusers", "src"))
+        os.environ.setdefault("PYTHONDONTWRITEBYTECODE", "1")
+        sys.dont_write_bytecode = True
+        torch.set_grad_enabled(False)
+        torch.set_num_threads(4)
+        vap = importlib.import_module("video-as-prompt_b200")
+        import cpu_standin_ops
+        cpu_standin_ops.install(vap)
+        if family == "wan":
+            from diffusers import WanTransformer3DMOTModel as RefModel
+            cfg = dict(vap.synth.WAN_TINY, num_layers=3, block_idx_with_mot_ref=[0, 2])
+            inp = vap.synth.wan_inputs(cfg, 3, 16, 24, seed=0)
+        else:
+            from diffusers import CogVideoXTransformer3DMOTModel as RefModel
+            cfg = dict(vap.synth.COG_TINY, num_layers=3, block_idx_with_mot_ref=[0, 2])
+            inp = vap.synth.cog_inputs(cfg, 2, 12, 20, seed=0, batch=2)
+        model = RefModel(**cfg).to(torch.bfloat16).eval()
+        vap.synth.fill_module_(model, seed=7, num_layers=cfg["num_layers"])
+        keys = list(model.state_dict())
+
+        def run():
+            return model(**inp, return_dict=False)[0].float()
+
+        ref = run()
+        res = {}
+        for level in ("block", "processor"):
+            vap.install(model, level=level)
+            out = run()
+            vap.uninstall(model)
+            res[level] = ((out - ref).abs().max() / ref.abs().max()).item()
+            res[level + "_restored"] = bool(torch.equal(run(), ref))
+        res["keys_unchanged"] = list(model.state_dict()) == keys
+        q.put(res)
+    except Exception:  # noqa: BLE001
+        import traceback
+        q.put({"error": traceback.format_exc()[-3000:]})
+
+
+@pytest.mark.parametrize("family", ["wan", "cog"])
+def test_install_on_the_reference_model_matches_the_reference(family):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    p = ctx.Process(target=_worker, args=(family, q))
+    p.start()
+    res = q.get(timeout=600)
+    p.join(60)
+    assert "error" not in res, res.get("error")
+    assert res["block"] < 2e-2 and res["processor"] < 2e-2, res
+    assert res["block_restored"] and res["processor_restored"] and res["keys_unchanged"], res

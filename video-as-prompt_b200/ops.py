@@ -94,6 +94,8 @@ def adaln_layernorm(x: torch.Tensor, *, eps: float, rounding: int, ln_w: Optiona
         raise ValueError("scale1p and shift must have the same batch stride")
     if rows_per_batch is None:
         rows_per_batch = x.shape[-2] if (x.dim() >= 3 and ms != 0) else rows
+    if rows == 0:  # e.g. a sequence-parallel rank that holds text rows only: nothing to launch (an empty tensor has no storage)
+        return out
     lib = _lib.load()
     rc = lib.vap_adaln_layernorm(x.data_ptr(), out.data_ptr(), rows, d, xs, os_, _need_cuda_f32(ln_w, "ln_w"), _need_cuda_f32(ln_b, "ln_b"),
                                  _need_cuda_f32(scale1p, "scale1p"), _need_cuda_f32(shift, "shift"), ms, max(int(rows_per_batch), 1),
@@ -121,6 +123,8 @@ def qk_norm_rope_(q: torch.Tensor, k: Optional[torch.Tensor], *, heads: int, hea
         rope_rows = cos.shape[0]
         if rows_per_batch - rope_row0 > rope_rows:
             raise ValueError(f"RoPE table has {rope_rows} rows but {rows_per_batch - rope_row0} tokens per batch need rotating")
+    if rows == 0:
+        return
     lib = _lib.load()
     rc = lib.vap_qk_norm_rope(q.data_ptr(), k.data_ptr() if k is not None else 0, rows, heads, head_dim, rs, _need_cuda_f32(wq, "wq"), _need_cuda_f32(bq, "bq"),
                               _need_cuda_f32(wk, "wk"), _need_cuda_f32(bk, "bk"), _need_cuda_f32(cos, "cos"), _need_cuda_f32(sin, "sin"),
@@ -268,6 +272,8 @@ def qkv_scatter(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, heads: int
         rope_rows = cos.shape[0]
         if rows_per_batch - rope_row0 > rope_rows:
             raise ValueError(f"RoPE table has {rope_rows} rows but {rows_per_batch - rope_row0} tokens per batch need rotating")
+    if rows == 0:
+        return
     lib = _lib.load()
     table = _ptr_table(dst_ptrs)
     rc = lib.vap_qkv_scatter(q.data_ptr(), k.data_ptr(), v.data_ptr(), rows, heads, head_dim, rs, _need_cuda_f32(wq, "wq"), _need_cuda_f32(bq, "bq"),
@@ -346,6 +352,8 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     gs = _mod_stride(gate, N, "gate") if gate is not None else 0
     if rows_per_batch is None:
         rows_per_batch = x.shape[-2] if (x.dim() >= 3 and gs != 0) else max(M, 1)
+    if M == 0:
+        return out
     lib = _lib.load()
     rc = lib.vap_gemm_bf16(x.data_ptr(), lda, weight.data_ptr(), weight.stride(0), out.data_ptr(), ldc, M, N, K,
                            bias.data_ptr() if bias is not None else 0, int(epilogue), r_ptr, ldr, _need_cuda_f32(gate, "gate"), gs,
