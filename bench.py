@@ -386,8 +386,17 @@ def main():
                 "roofline": roof, "model_tflops": (total_flops / (ms_dev / a.steps * 1e-3) / 1e12) if total_flops else None}
         if world == 1 and not a.no_cpu_baseline and w["family"] == "wan":
             line["cpu_baseline"] = cpu_baseline_entry(vap, w, S, S)
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
+    if use_graph:
+        # a captured graph holds the NCCL all-gather and the symmetric-memory barriers of the step: release it (and the replay
+        # callable) before the communicator is torn down, or the teardown waits on work that can no longer be retired
+        fwd[0] = model
+        graphed = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

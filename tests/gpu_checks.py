@@ -593,6 +593,7 @@ CHECKS = {
     "attn_splitkv_3_d64": lambda: check_attention_splitkv(2, 3, 452, 900, 64, 3),
     "attn_splitkv_uneven": lambda: check_attention_splitkv(1, 1, 130, 128 * 5 + 7, 128, 4),
     "attn_splitkv_peers": lambda: check_attention_splitkv_peers(),
+    "attn_splitkv_peers_p8": lambda: check_attention_splitkv_peers(P=8, L=40, H=5, D=128, splits=2),
     "ulysses_relayout": check_ulysses_relayout,
     "ulysses_p2p_emulated_wan": lambda: check_ulysses_p2p_emulated(P=4, L=96, H=8, D=128, mode=0),
     "ulysses_p2p_emulated_p8": lambda: check_ulysses_p2p_emulated(P=8, L=300, H=40, D=128, mode=0),
