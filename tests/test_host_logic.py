@@ -216,3 +216,57 @@ def test_split_kv_entry_points_validate_arguments():
     assert b"KV tiles" in lib.vap_last_error()
     assert lib.vap_attention_combine(16, 16, 2, 1, 1, 8, 128, 0, 0, 0, 0, 0, 128, 128, 128, 0) == -1  # neither o nor o_peers
     assert b"either o or o_peers" in lib.vap_last_error()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# launch sequence of the fused blocks: which C-ABI entry points one forward calls, in which order, on which shapes
+# (tools/host_path_profile.py swaps the library for a no-op stub in a SUBPROCESS; nothing is computed)
+# ------------------------------------------------------------------------------------------------------------------
+def _recorded_calls(family: str, blocks: int, tmp_path):
+    import subprocess
+    out = tmp_path / f"{family}_calls.json"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "host_path_profile.py"), "--family", family, "--blocks", str(blocks),
+                        "--iters", "1", "--record", str(out)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    summary = json.loads(r.stdout.strip().splitlines()[-1])
+    calls = json.load(open(out))
+    assert summary["c_abi_calls_per_forward"] == len(calls)
+    return calls
+
+
+def test_wan_mot_block_launch_sequence(tmp_path):
+    """One Wan MoT block = 35 launches (SURVEY §8a W1-W9 on both streams): per stream LN -> fused-QKV GEMM -> q/k norm + RoPE into the
+    JOINT buffer, ONE attention over [target | ref], per stream O-projection with the gated-residual epilogue, then per stream the
+    cross-attention (q / text kv / image kv projections, three norms, two attentions, ungated residual epilogue) and the FFN (GELU and
+    gated-residual epilogues); + the output head's LayerNorm.  No pack / cat / transpose kernels of ours in between."""
+    calls = _recorded_calls("wan", 1, tmp_path)
+    names = [c[0].replace("vap_", "") for c in calls]
+    ln, gemm, qk, att = "adaln_layernorm", "gemm_bf16", "qk_norm_rope", "attention_fwd"
+    tail = [ln, gemm, qk, gemm, qk, att, gemm, qk, att, gemm, ln, gemm, gemm]
+    assert names == [ln, ln, gemm, qk, gemm, qk, att, gemm, gemm] + tail + tail + [ln]
+    # the joint attention reads q, k, v of BOTH streams as strided views of one [J, 3d] buffer: J = 2 x 32 rows, row stride 3 * 256
+    joint = [c for c in calls if c[0] == "vap_attention_fwd"][0]
+    scal = [x for x in joint[1:] if x not in ("p", None)]
+    B, H, Lq, Lkv, D = scal[:5]
+    assert (B, H, Lq, Lkv, D) == (1, 2, 64, 64, 128)
+    q_strides, k_strides, v_strides, o_strides = scal[5:8], scal[8:11], scal[11:14], scal[14:17]
+    assert q_strides == k_strides == v_strides == [64 * 768, 128, 768] and o_strides == [64 * 256, 128, 256]
+    # GEMM epilogues in order: QKV x2 (bias), O-proj x2 (fp32 gated residual), then per stream q / kv / kv_img (bias), to_out (residual add),
+    # FFN up (GELU), FFN down (fp32 gated residual)
+    epi = [[x for x in c[1:] if x not in ("p", None)][6] for c in calls if c[0] == "vap_gemm_bf16"]
+    assert epi == [0, 0, 2, 2] + [0, 0, 0, 3, 1, 2] * 2
+
+
+def test_cog_mot_block_launch_sequence(tmp_path):
+    """CogVideoX: block 0 carries the expert (18 launches), block 1 is a plain block (9); each stream's LayerNormZero writes text and
+    video rows into ONE [T + S, d] buffer feeding the QKV / FFN GEMMs, the joint attention runs over [text | video | text_ref | video_ref]."""
+    calls = _recorded_calls("cog", 2, tmp_path)
+    names = [c[0].replace("vap_", "") for c in calls]
+    ln, gemm, qk, att = "adaln_layernorm", "gemm_bf16", "qk_norm_rope", "attention_fwd"
+    pre = [ln, ln, gemm, qk]
+    ffn = [ln, ln, gemm, gemm, gemm]
+    assert names == pre + pre + [att, gemm, gemm] + ffn + [gemm, gemm] + ffn + pre + [att, gemm, gemm] + ffn + [ln, ln]
+    att_calls = [[x for x in c[1:] if x not in ("p", None)] for c in calls if c[0] == "vap_attention_fwd"]
+    assert att_calls[0][:5] == [1, 4, 516, 516, 64] and att_calls[1][:5] == [1, 4, 258, 258, 64]  # J = 2 (226 + 32); plain block: 226 + 32
+    qk_calls = [[x for x in c[1:] if x not in ("p", None)] for c in calls if c[0] == "vap_qk_norm_rope"]
+    assert all(c[:4] == [258, 4, 64, 768] and c[5] == 226 for c in qk_calls)  # RoPE skips the 226 text rows (rope_row0)
