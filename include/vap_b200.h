@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define VAP_B200_VERSION 300 /* major*10000 + minor*100 + patch */
+#define VAP_B200_VERSION 301 /* major*10000 + minor*100 + patch */
 
 /* Library version (VAP_B200_VERSION of the build). */
 int vap_version(void);
@@ -128,6 +128,19 @@ int vap_attention_fwd_splitkv(const void* q, const void* k, const void* v, void*
                               int64_t v_sh, int64_t v_sl, float scale, void* stream);
 int vap_attention_combine(const void* o_part, const float* lse_part, int kv_splits, int B, int H, int Lq, int D, void* o, void* const* o_peers,
                           int npeers, int o_rows_per_peer, float* lse, int64_t o_sb, int64_t o_sh, int64_t o_sl, void* stream);
+
+/* (8) Classifier-free guidance + FlowMatchEuler scheduler update of the Wan denoise loop, one elementwise pass (HBM-bound):
+ *       n   = noise_uncond ? bf16(u + bf16(g * bf16(c - u))) : c     Ref: pipelines/wan/pipeline_wan_i2v_mot.py:874 (three bf16 tensor ops)
+ *       out = bf16(float(sample) + bf16(dt * n))                       Ref: schedulers/scheduling_flow_match_euler_discrete.py:433, 457, 462-467
+ *                                                                          (sample upcast to fp32; dt * model_output is a bf16 tensor op; cast back)
+ *     noise_cond / noise_uncond [batch, inner] bf16 contiguous (noise_uncond may be NULL: no guidance); sample [batch, inner] contiguous,
+ *     fp32 (sample_is_f32 = 1: the pipeline's initial latents) or bf16 (the later steps); out: batch rows of `inner` bf16 elements,
+ *     out_batch_stride apart — e.g. the latent channels of the NEXT step's transformer input [B, 16 + 20, F, h, w], which saves the
+ *     reference's torch.cat([latents, condition]) (:815).  dt = sigma_next - sigma as the caller's torch build would apply it
+ *     (CUDA: the fp32 value; a CPU run of the reference rounds the 0-dim dt to bf16 first).  inner and out_batch_stride must be
+ *     multiples of 8, all pointers 16-byte aligned. */
+int vap_cfg_flow_match_step(const void* noise_cond, const void* noise_uncond, const void* sample, int sample_is_f32, void* out, int64_t batch,
+                            int64_t inner, int64_t out_batch_stride, float guidance_scale, float dt, void* stream);
 
 /* (6) Bring-up probe for the tcgen05 descriptors: one CTA computes D[128,N] = A[128,K] * B, fp32 out.
  *     a_in_tmem: bit 0: 0 = A from shared memory (K-major, SWIZZLE_128B), 1 = A staged to TMEM as packed bf16;

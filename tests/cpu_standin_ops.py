@@ -130,8 +130,23 @@ def ulysses_unpack(src, out=None):
     return out
 
 
+def cfg_flow_match_step(noise_cond, noise_uncond, sample, *, guidance_scale, dt, out=None):
+    """vap_cfg_flow_match_step's contract (include/vap_b200.h (8)): every reference tensor op rounds once."""
+    n = noise_cond.float()
+    if noise_uncond is not None:
+        u = noise_uncond.float()
+        d = (n - u).to(BF16).float()
+        m = (torch.tensor(guidance_scale, dtype=torch.float32) * d).to(BF16).float()
+        n = (u + m).to(BF16).float()
+    y = (sample.float() + (torch.tensor(dt, dtype=torch.float32) * n).to(BF16).float()).to(BF16)
+    if out is None:
+        return y
+    out.copy_(y)
+    return out
+
+
 def install(vap) -> None:
     """Replace the kernel wrappers of `vap.ops` by the stand-ins (one test process only)."""
-    for name in ("adaln_layernorm", "qk_norm_rope_", "attention", "linear", "ulysses_pack", "ulysses_unpack"):
+    for name in ("adaln_layernorm", "qk_norm_rope_", "attention", "linear", "ulysses_pack", "ulysses_unpack", "cfg_flow_match_step"):
         setattr(vap.ops, name, globals()[name])
     vap.ops.sm_count = lambda: 148

@@ -270,3 +270,25 @@ def test_cog_mot_block_launch_sequence(tmp_path):
     assert att_calls[0][:5] == [1, 4, 516, 516, 64] and att_calls[1][:5] == [1, 4, 258, 258, 64]  # J = 2 (226 + 32); plain block: 226 + 32
     qk_calls = [[x for x in c[1:] if x not in ("p", None)] for c in calls if c[0] == "vap_qk_norm_rope"]
     assert all(c[:4] == [258, 4, 64, 768] and c[5] == 226 for c in qk_calls)  # RoPE skips the 226 text rows (rope_row0)
+
+
+def test_cfg_flow_match_step_contract_equals_the_reference_expression():
+    """The rounding points vap_cfg_flow_match_step implements (restated by the CPU stand-in) are those of the reference's tensor ops:
+    noise_uncond + g * (noise - noise_uncond) in bf16 (pipeline_wan_i2v_mot.py:874), then FlowMatchEulerDiscreteScheduler.step
+    (scheduling_flow_match_euler_discrete.py:433-467).  On the CPU torch rounds the 0-dim fp32 dt to bf16 before the multiply (a CUDA
+    run keeps it in fp32), so the comparison hands the stand-in the bf16-rounded dt."""
+    import cpu_standin_ops as so
+    g = torch.Generator().manual_seed(5)
+    c, u = torch.randn(2, 4096, generator=g).bfloat16(), torch.randn(2, 4096, generator=g).bfloat16()
+    sigma, sigma_next = torch.tensor(0.9375), torch.tensor(0.712345)
+    dt_b = float((sigma_next - sigma).bfloat16())
+    for sample in (torch.randn(2, 4096, generator=g), torch.randn(2, 4096, generator=g).bfloat16()):
+        noise = u + 5.0 * (c - u)
+        ref = (sample.to(torch.float32) + (sigma_next - sigma) * noise).to(noise.dtype)
+        assert torch.equal(so.cfg_flow_match_step(c, u, sample, guidance_scale=5.0, dt=dt_b), ref)
+        ref1 = (sample.to(torch.float32) + (sigma_next - sigma) * c).to(c.dtype)
+        assert torch.equal(so.cfg_flow_match_step(c, None, sample, guidance_scale=1.0, dt=dt_b), ref1)
+    with pytest.raises(vap.VapError):
+        vap.ops.cfg_flow_match_step(c, u, torch.zeros(2, 4096), guidance_scale=5.0, dt=-0.1)
+    lib = vap._lib.load()
+    assert lib.vap_cfg_flow_match_step(16, 0, 16, 1, 16, 1, 12, 16, 5.0, -0.1, 0) == -1 and b"multiple of 8" in lib.vap_last_error()

@@ -1,7 +1,9 @@
 """Run every GPU parity check of tests/gpu_checks.py in its own subprocess (a kernel fault or an mbarrier-watchdog trap
 kills only that check), with a timeout, and write gpurun_out/diag.json + one log per failing check.
 
-    python tools/gpu_diag.py [--only name1,name2] [--timeout 180]
+    python tools/gpu_diag.py [--only name1,name2] [--timeout 180] [--pending]
+
+--pending runs gpu_checks.CHECKS_PENDING instead (checks of code that has not been on a GPU yet; not part of `pytest -m gpu`).
 """
 import argparse
 import json
@@ -20,7 +22,7 @@ def run_one(name):
     import gpu_checks
     import torch
     t0 = time.time()
-    res = gpu_checks.CHECKS[name]()
+    res = {**gpu_checks.CHECKS, **gpu_checks.CHECKS_PENDING}[name]()
     torch.cuda.synchronize()
     print("RESULT " + json.dumps(dict(name=name, ok=True, seconds=round(time.time() - t0, 2), result=res)))
 
@@ -30,12 +32,13 @@ def main():
     ap.add_argument("--check")
     ap.add_argument("--only", default="")
     ap.add_argument("--timeout", type=int, default=180)
+    ap.add_argument("--pending", action="store_true")
     a = ap.parse_args()
     if a.check:
         return run_one(a.check)
     os.makedirs(OUT, exist_ok=True)
     import gpu_checks
-    names = [n for n in gpu_checks.CHECKS if not a.only or n in a.only.split(",")]
+    names = [n for n in (gpu_checks.CHECKS_PENDING if a.pending else gpu_checks.CHECKS) if not a.only or n in a.only.split(",")]
     summary = []
     for n in names:
         t0 = time.time()
@@ -54,7 +57,7 @@ def main():
             open(os.path.join(OUT, f"diag_{n}.log"), "w").write((e.stdout or b"").decode(errors="replace") + (e.stderr or b"").decode(errors="replace"))
         summary.append(rec)
         print(json.dumps(rec), flush=True)
-    json.dump(summary, open(os.path.join(OUT, "diag.json"), "w"), indent=1)
+    json.dump(summary, open(os.path.join(OUT, "diag_pending.json" if a.pending else "diag.json"), "w"), indent=1)
     bad = [r["name"] for r in summary if not r["ok"]]
     print(f"{len(summary) - len(bad)}/{len(summary)} checks passed; failing: {bad}")
     sys.exit(1 if bad else 0)

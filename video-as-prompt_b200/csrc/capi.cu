@@ -292,6 +292,18 @@ int vap_ulysses_unpack(const void* src, void* dst, int64_t L, int nsplit, int64_
     return launch_ulysses(src, dst, L, nsplit, chunk, dst_row_stride, src_row_stride, src_split_stride, 1, static_cast<cudaStream_t>(stream));
 }
 
+int vap_cfg_flow_match_step(const void* noise_cond, const void* noise_uncond, const void* sample, int sample_is_f32, void* out, int64_t batch,
+                            int64_t inner, int64_t out_batch_stride, float guidance_scale, float dt, void* stream) {
+    VAP_REQUIRE(noise_cond && sample && out, "vap_cfg_flow_match_step: null tensor");
+    StepParams p{};
+    p.cond = static_cast<const __nv_bfloat16*>(noise_cond), p.uncond = static_cast<const __nv_bfloat16*>(noise_uncond);
+    p.sample = sample, p.sample_is_f32 = sample_is_f32;
+    p.out = static_cast<__nv_bfloat16*>(out);
+    p.batch = batch, p.inner = inner, p.out_batch_stride = out_batch_stride;
+    p.guidance = guidance_scale, p.dt = dt;
+    return launch_cfg_flow_match_step(p, static_cast<cudaStream_t>(stream));
+}
+
 int vap_debug_set_attention_trace(void* device_buffer) {
     g_attn_trace = static_cast<long long*>(device_buffer);
     return 0;

@@ -373,4 +373,92 @@ int launch_qk_norm_rope(const QkParams& p, int cog_mode, cudaStream_t stream) {
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// Classifier-free guidance + FlowMatchEuler update of the Wan denoise loop in one pass.
+//   n   = u + g * (c - u)          three bf16 tensor ops in the reference (pipeline_wan_i2v_mot.py:874): one rounding each
+//   out = sample.float() + dt * n  dt * n is a bf16 tensor op (0-dim fp32 dt, bf16 n), the sum is fp32, the result is cast back
+//                                  to the model's dtype (scheduling_flow_match_euler_discrete.py:433, 457, 462-467)
+// HBM-bound: reads 2 + 2 (+2 / +4) bytes per element, writes 2; one thread per 8 elements, 16-byte accesses.  The output rows may
+// sit inside the next step's transformer input [B, C_latent + C_cond, F, h, w] (out_batch_stride), which removes that torch.cat.
+// __f*_rn intrinsics keep ptxas from contracting the separately rounded multiplies and adds into FMAs.
+// ------------------------------------------------------------------------------------------------------------------------
+template <bool kSampleF32>
+__global__ void __launch_bounds__(256) cfg_flow_match_kernel(const StepParams p) {
+    const int64_t vec_per_batch = p.inner / 8;
+    const int64_t total = p.batch * vec_per_batch;
+    for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t b = idx / vec_per_batch;
+        const int64_t e = (idx - b * vec_per_batch) * 8;  // element inside the batch
+        const int64_t in_off = b * p.inner + e;
+        float n[8], x[8];
+        {
+            const uint4 cu = ld_nc_v4(p.cond + in_off);
+            const uint32_t* cw = reinterpret_cast<const uint32_t*>(&cu);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = bf16x2_to_float2(cw[j]);
+                n[2 * j] = f.x, n[2 * j + 1] = f.y;
+            }
+        }
+        if (p.uncond) {
+            const uint4 uu = ld_nc_v4(p.uncond + in_off);
+            const uint32_t* uw = reinterpret_cast<const uint32_t*>(&uu);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = bf16x2_to_float2(uw[j]);
+                const float u2[2] = {f.x, f.y};
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const float d = bf16_round(__fsub_rn(n[2 * j + h], u2[h]));
+                    const float m = bf16_round(__fmul_rn(p.guidance, d));
+                    n[2 * j + h] = bf16_round(__fadd_rn(u2[h], m));
+                }
+            }
+        }
+        if (kSampleF32) {
+            const float4 a = *reinterpret_cast<const float4*>(static_cast<const float*>(p.sample) + in_off);
+            const float4 c = *reinterpret_cast<const float4*>(static_cast<const float*>(p.sample) + in_off + 4);
+            x[0] = a.x, x[1] = a.y, x[2] = a.z, x[3] = a.w, x[4] = c.x, x[5] = c.y, x[6] = c.z, x[7] = c.w;
+        } else {
+            const uint4 su = ld_nc_v4(static_cast<const __nv_bfloat16*>(p.sample) + in_off);
+            const uint32_t* sw = reinterpret_cast<const uint32_t*>(&su);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = bf16x2_to_float2(sw[j]);
+                x[2 * j] = f.x, x[2 * j + 1] = f.y;
+            }
+        }
+        float y[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = __fadd_rn(x[j], bf16_round(__fmul_rn(p.dt, n[j])));
+        uint4 o;
+        o.x = pack_bf16x2(y[0], y[1]);
+        o.y = pack_bf16x2(y[2], y[3]);
+        o.z = pack_bf16x2(y[4], y[5]);
+        o.w = pack_bf16x2(y[6], y[7]);
+        st_v4(p.out + b * p.out_batch_stride + e, o);
+    }
+}
+
+int launch_cfg_flow_match_step(const StepParams& p, cudaStream_t stream) {
+    VAP_REQUIRE(p.batch >= 0 && p.inner >= 0 && p.inner % 8 == 0, "cfg_flow_match_step: inner=%lld must be a non-negative multiple of 8",
+                static_cast<long long>(p.inner));
+    VAP_REQUIRE(p.out_batch_stride >= p.inner && p.out_batch_stride % 8 == 0, "cfg_flow_match_step: bad output batch stride");
+    VAP_REQUIRE((reinterpret_cast<uintptr_t>(p.cond) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.uncond) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(p.sample) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0,
+                "cfg_flow_match_step: tensors must be 16-byte aligned");
+    const int64_t total = p.batch * (p.inner / 8);
+    if (total == 0) return 0;
+    int64_t blocks = (total + 255) / 256;
+    const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
+    if (blocks > cap) blocks = cap;
+    if (p.sample_is_f32)
+        cfg_flow_match_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(p);
+    else
+        cfg_flow_match_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(p);
+    VAP_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+
 }  // namespace vap

@@ -95,6 +95,18 @@ struct GemmParams {
 };
 int launch_gemm_bf16(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, GemmParams p, cudaStream_t stream);
 
+// CFG + FlowMatchEuler update (one elementwise pass over the latents)
+struct StepParams {
+    const __nv_bfloat16* cond;    // [batch, inner] noise prediction of the conditional pass
+    const __nv_bfloat16* uncond;  // same shape, or null (no classifier-free guidance)
+    const void* sample;           // [batch, inner] fp32 or bf16 latents
+    int sample_is_f32;
+    __nv_bfloat16* out;           // batch rows of `inner` elements, out_batch_stride apart
+    int64_t batch, inner, out_batch_stride;
+    float guidance, dt;
+};
+int launch_cfg_flow_match_step(const StepParams& p, cudaStream_t stream);
+
 struct ProbeParams {
     const __nv_bfloat16* A;  // [128, K] row-major (used directly when a_in_tmem)
     float* Dout;             // [128, N]

@@ -3,7 +3,8 @@ transformer forward at B=1 + the scheduler update; with classifier-free guidance
 
 Mirrors the reference pipeline's loop body (diffusers/pipelines/wan/pipeline_wan_i2v_mot.py:801-877) and the default
 FlowMatchEulerDiscreteScheduler (diffusers/schedulers/scheduling_flow_match_euler_discrete.py:91-131, 249-349, 373-470);
-the scheduler update is O(latent) elementwise fp32 work and stays in torch.  The CogVideoX loop
+the scheduler update is O(latent) elementwise work: torch by default, or fused with the classifier-free-guidance combine into one
+kernel (`wan_denoise(fused_step=True)` -> vap_cfg_flow_match_step).  The CogVideoX loop
 (diffusers/pipelines/cogvideo/pipeline_cogvideox_image2video_mot.py:964-1057) runs one B=2 forward per step for classifier-free
 guidance and CogVideoXDPMScheduler (diffusers/schedulers/scheduling_dpm_cogvideox.py:181-232, 261-304, 306-440)."""
 from __future__ import annotations
@@ -32,10 +33,17 @@ def flow_match_step(model_output: torch.Tensor, sample: torch.Tensor, sigma: tor
 
 @torch.no_grad()
 def wan_denoise(model, latents: torch.Tensor, condition: torch.Tensor, latents_ref: torch.Tensor, condition_ref: torch.Tensor, cond_kwargs: dict,
-                uncond_kwargs: Optional[dict], num_steps: int, shift: float = 3.0, guidance_scale: float = 5.0, dtype=torch.bfloat16) -> torch.Tensor:
-    """Run `num_steps` denoise steps of the Wan VAP pipeline loop on `model` (ours or the reference's after install())."""
+                uncond_kwargs: Optional[dict], num_steps: int, shift: float = 3.0, guidance_scale: float = 5.0, dtype=torch.bfloat16,
+                fused_step: bool = False) -> torch.Tensor:
+    """Run `num_steps` denoise steps of the Wan VAP pipeline loop on `model` (ours or the reference's after install()).
+    fused_step: classifier-free guidance + scheduler update in ONE kernel (ops.cfg_flow_match_step) instead of seven torch
+    elementwise launches — same rounding points (opt-in until its GPU parity check has run, tests/gpu_checks.py)."""
     dev = latents.device
     timesteps, sigmas = flow_match_schedule(num_steps, shift, device=dev)
+    if fused_step:
+        from . import ops
+        sig_host = flow_match_schedule(num_steps, shift, device="cpu")[1]
+        dts = [float(sig_host[i + 1] - sig_host[i]) for i in range(num_steps)]  # fp32 differences, as the device computes them
     x_ref = torch.cat([latents_ref, condition_ref], dim=1).to(dtype)
     ts_ref = torch.ones((1, latents.shape[0]), dtype=torch.float32, device=dev)  # reference video is clean: timestep 1 (:812-813)
     for i in range(num_steps):
@@ -45,7 +53,13 @@ def wan_denoise(model, latents: torch.Tensor, condition: torch.Tensor, latents_r
         if uncond_kwargs is not None:
             noise_u = model(hidden_states=x_in, timestep=ts, hidden_states_mot_ref=x_ref, timestep_list_mot_ref=ts_ref, return_dict=False,
                             **uncond_kwargs)[0]
+            if fused_step:
+                latents = ops.cfg_flow_match_step(noise, noise_u, latents.contiguous(), guidance_scale=guidance_scale, dt=dts[i])
+                continue
             noise = noise_u + guidance_scale * (noise - noise_u)
+        if fused_step:
+            latents = ops.cfg_flow_match_step(noise, None, latents.contiguous(), guidance_scale=1.0, dt=dts[i])
+            continue
         latents = flow_match_step(noise, latents, sigmas[i], sigmas[i + 1])
     return latents
 

@@ -362,6 +362,43 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     return out
 
 
+def cfg_flow_match_step(noise_cond: torch.Tensor, noise_uncond: Optional[torch.Tensor], sample: torch.Tensor, *, guidance_scale: float, dt: float,
+                        out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Classifier-free guidance + FlowMatchEuler update in one pass (vap_cfg_flow_match_step):
+    ``(sample.float() + dt * (u + g * (c - u))).to(bf16)`` with the reference's bf16 rounding points.  noise_cond / noise_uncond
+    [B, ...] bf16 contiguous (noise_uncond None: no guidance), sample same shape, fp32 or bf16; `out` (optional) may be a channel
+    slice of the next step's transformer input ([B, C_all, ...][:, :C]): every batch element must be one contiguous block."""
+    _need_cuda_bf16(noise_cond, "noise_cond")
+    if not noise_cond.is_contiguous() or noise_cond.dim() < 1:
+        raise ValueError("noise_cond must be contiguous")
+    if noise_uncond is not None:
+        _need_cuda_bf16(noise_uncond, "noise_uncond")
+        if noise_uncond.shape != noise_cond.shape or not noise_uncond.is_contiguous():
+            raise ValueError("noise_uncond must be contiguous with the shape of noise_cond")
+    if not isinstance(sample, torch.Tensor) or not sample.is_cuda:
+        raise VapError("sample must be a CUDA tensor: the VAP kernels are CUDA-only (sm_100a); there is no CPU fallback")
+    if sample.dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError(f"sample must be float32 or bfloat16, got {sample.dtype}")
+    if sample.shape != noise_cond.shape or not sample.is_contiguous():
+        raise ValueError("sample must be contiguous with the shape of noise_cond")
+    B = noise_cond.shape[0]
+    inner = noise_cond.numel() // max(B, 1)
+    if inner % 8:
+        raise ValueError(f"elements per batch ({inner}) must be a multiple of 8")
+    if out is None:
+        out = torch.empty(noise_cond.shape, dtype=torch.bfloat16, device=noise_cond.device)
+    _need_cuda_bf16(out, "out")
+    if out.shape != noise_cond.shape or (B > 0 and not out[0].is_contiguous()):
+        raise ValueError("out must have the shape of noise_cond with every batch element contiguous")
+    obs = out.stride(0) if B > 1 else max(inner, 8)
+    if B * inner == 0:
+        return out
+    rc = _lib.load().vap_cfg_flow_match_step(noise_cond.data_ptr(), noise_uncond.data_ptr() if noise_uncond is not None else 0, sample.data_ptr(),
+                                             int(sample.dtype == torch.float32), out.data_ptr(), B, inner, obs, float(guidance_scale), float(dt), _stream())
+    _lib.check(rc, "vap_cfg_flow_match_step")
+    return out
+
+
 def ulysses_pack(src: torch.Tensor, nsplit: int, out: torch.Tensor) -> torch.Tensor:
     """out[s, l, :] = src[l, s*chunk:(s+1)*chunk].  src [L, nsplit*chunk] (row-strided view); out [nsplit, L, chunk] view whose
     rows / splits may be strided (e.g. the q, k or v slot of the all-to-all send buffer [P, L, 3, chunk])."""
