@@ -398,7 +398,7 @@ def check_wan_denoise():
     with torch.no_grad():
         lat = vap.denoise.wan_denoise(model, lat0.to(DEV), inp["hidden_states"][:, 16:].float().to(DEV), lat_ref.to(DEV),
                                       inp["hidden_states_mot_ref"][:, 16:].float().to(DEV), _to_dev(kw), _to_dev(kw_u), dn["steps"], dn["shift"],
-                                      dn["guidance"])
+                                      dn["guidance"], cache_context=False)  # the cached loop: CHECKS_PENDING["wan_denoise_cached"]
     cos, err = cosine(lat, dn["final_latents"]), rel_err(lat, dn["final_latents"])
     assert cos >= 0.999, f"wan 4-step denoise: cosine {cos} (rel err {err})"
     return dict(cosine=cos, err=err)
@@ -607,9 +607,35 @@ def check_wan_denoise_fused():
         for fused in (False, True):
             outs.append(vap.denoise.wan_denoise(model, lat0.to(DEV), inp["hidden_states"][:, 16:].float().to(DEV), lat_ref.to(DEV),
                                                 inp["hidden_states_mot_ref"][:, 16:].float().to(DEV), _to_dev(kw), _to_dev(kw_u), dn["steps"], dn["shift"],
-                                                dn["guidance"], fused_step=fused))
+                                                dn["guidance"], fused_step=fused, cache_context=False))
     cos = cosine(outs[1], dn["final_latents"])
     assert torch.equal(outs[0], outs[1]), f"fused step differs from the torch step: rel err {rel_err(outs[1], outs[0])}"
+    assert cos >= 0.999
+    return dict(cosine=cos, bit_exact=True)
+
+
+def check_wan_denoise_cached():
+    """wan_denoise with the context cache (embeddings + cross-attention K / V computed once per loop) == the uncached loop, bit for bit."""
+    g = _golden("wan_tiny.pt")
+    cfg, dn = g["cfg"], g["denoise"]
+    model = build_wan(cfg, g["weight_seed"])
+    f, h, w = g["latent"]
+    inp = synth.wan_inputs(cfg, f, h, w, seed=g["input_seed"])
+    neg = synth.wan_inputs(cfg, f, h, w, seed=dn["neg_seed"])
+    gen = torch.Generator().manual_seed(dn["seed"])
+    lat0 = torch.randn((1, 16, f, h, w), generator=gen)
+    lat_ref = torch.randn((1, 16, f, h, w), generator=gen)
+    kw = _to_dev({k: inp[k] for k in ("encoder_hidden_states", "encoder_hidden_states_image", "encoder_hidden_states_mot_ref",
+                                      "encoder_hidden_states_image_mot_ref", "num_mot_ref")})
+    kw_u = dict(kw, encoder_hidden_states=neg["encoder_hidden_states"].to(DEV), encoder_hidden_states_mot_ref=neg["encoder_hidden_states_mot_ref"].to(DEV))
+    outs = []
+    with torch.no_grad():
+        for cache in (False, True):
+            outs.append(vap.denoise.wan_denoise(model, lat0.to(DEV), inp["hidden_states"][:, 16:].float().to(DEV), lat_ref.to(DEV),
+                                                inp["hidden_states_mot_ref"][:, 16:].float().to(DEV), kw, kw_u, dn["steps"], dn["shift"], dn["guidance"],
+                                                cache_context=cache))
+    assert torch.equal(outs[0], outs[1]), f"cached loop differs: rel err {rel_err(outs[1], outs[0])}"
+    cos = cosine(outs[1], dn["final_latents"])
     assert cos >= 0.999
     return dict(cosine=cos, bit_exact=True)
 
@@ -673,4 +699,5 @@ CHECKS = {
 CHECKS_PENDING = {
     "cfg_flow_match_step": check_cfg_flow_match_step,
     "wan_denoise_fused": check_wan_denoise_fused,
+    "wan_denoise_cached": check_wan_denoise_cached,
 }

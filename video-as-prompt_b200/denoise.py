@@ -34,18 +34,33 @@ def flow_match_step(model_output: torch.Tensor, sample: torch.Tensor, sigma: tor
 @torch.no_grad()
 def wan_denoise(model, latents: torch.Tensor, condition: torch.Tensor, latents_ref: torch.Tensor, condition_ref: torch.Tensor, cond_kwargs: dict,
                 uncond_kwargs: Optional[dict], num_steps: int, shift: float = 3.0, guidance_scale: float = 5.0, dtype=torch.bfloat16,
-                fused_step: bool = False) -> torch.Tensor:
+                fused_step: bool = False, cache_context: bool = True) -> torch.Tensor:
     """Run `num_steps` denoise steps of the Wan VAP pipeline loop on `model` (ours or the reference's after install()).
+    cache_context: the text / CLIP context embeddings and every block's cross-attention K / V are the same at every step and in both
+    guidance passes; compute them once per loop (wan.context_cache; identical results — the cached tensors are what would be recomputed).
     fused_step: classifier-free guidance + scheduler update in ONE kernel (ops.cfg_flow_match_step) instead of seven torch
     elementwise launches — same rounding points (opt-in until its GPU parity check has run, tests/gpu_checks.py)."""
     dev = latents.device
     timesteps, sigmas = flow_match_schedule(num_steps, shift, device=dev)
     if fused_step:
-        from . import ops
         sig_host = flow_match_schedule(num_steps, shift, device="cpu")[1]
         dts = [float(sig_host[i + 1] - sig_host[i]) for i in range(num_steps)]  # fp32 differences, as the device computes them
+    from . import wan
     x_ref = torch.cat([latents_ref, condition_ref], dim=1).to(dtype)
     ts_ref = torch.ones((1, latents.shape[0]), dtype=torch.float32, device=dev)  # reference video is clean: timestep 1 (:812-813)
+    try:
+        with wan.context_cache(cache_context):
+            return _wan_denoise_loop(model, latents, condition, x_ref, ts_ref, cond_kwargs, uncond_kwargs, num_steps, timesteps, sigmas, guidance_scale, dtype,
+                                     dts if fused_step else None)
+    finally:
+        if cache_context and isinstance(model, torch.nn.Module):
+            wan.clear_context_cache(model)  # the entries keep the conditioning tensors alive: drop them with the loop
+
+
+def _wan_denoise_loop(model, latents, condition, x_ref, ts_ref, cond_kwargs, uncond_kwargs, num_steps, timesteps, sigmas, guidance_scale, dtype, dts):
+    fused_step = dts is not None
+    if fused_step:
+        from . import ops
     for i in range(num_steps):
         x_in = torch.cat([latents, condition], dim=1).to(dtype)
         ts = timesteps[i].expand(latents.shape[0])

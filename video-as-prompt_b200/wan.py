@@ -29,6 +29,57 @@ from .rope import Tables, as_tables, wan_rope_tables
 
 TEXT_CONTEXT_LEN = 512  # hardcoded by the reference (:126-127)
 
+# ----------------------------------------------------------------------------------------------
+# context cache: inside a denoise loop the text / CLIP context of a stream is the same tensor at every step and
+# in both classifier-free-guidance passes, so its embedding and every block's cross-attention K / V (projection + RMSNorm) can be
+# computed once.  Off by default (a benchmark step recomputes everything); `with context_cache():` around the loop turns it on.
+# Entries are keyed by the identity of the INPUT tensor (storage pointer, version counter, shape) and hold a reference to it, so a
+# recycled allocation can never alias; at most `_CTX_SLOTS` contexts (conditional + unconditional) are kept per module.
+# ----------------------------------------------------------------------------------------------
+_CTX_CACHE_ON = [False]
+_CTX_SLOTS = 2
+
+
+class context_cache:
+    """Context manager: cache context embeddings and cross-attention K / V across forwards (same results, less work)."""
+
+    def __init__(self, enabled: bool = True):
+        self.enabled = enabled
+
+    def __enter__(self):
+        self._prev = _CTX_CACHE_ON[0]
+        _CTX_CACHE_ON[0] = self.enabled
+        return self
+
+    def __exit__(self, *exc):
+        _CTX_CACHE_ON[0] = self._prev
+        return False
+
+
+def _tensor_key(*tensors):
+    return tuple(None if t is None else (t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride()), t.dtype, t.device) for t in tensors)
+
+
+def _cached(owner: nn.Module, slot: str, inputs, compute):
+    """compute() memoised on the identity of `inputs` while the context cache is on (LRU of _CTX_SLOTS entries per owner and slot)."""
+    if not _CTX_CACHE_ON[0]:
+        return compute()
+    entries = owner.__dict__.setdefault("_vap_ctx_cache", {}).setdefault(slot, [])
+    key = _tensor_key(*inputs)
+    for n, (k, _, val) in enumerate(entries):
+        if k == key:
+            entries.append(entries.pop(n))
+            return val
+    val = compute()
+    entries.append((key, tuple(inputs), val))  # the inputs are kept alive: their addresses cannot be reused while the entry exists
+    del entries[:-_CTX_SLOTS]
+    return val
+
+
+def clear_context_cache(model: nn.Module) -> None:
+    for m in model.modules():
+        m.__dict__.pop("_vap_ctx_cache", None)
+
 
 # ----------------------------------------------------------------------------------------------
 # cached, packed views of a module's parameters
@@ -126,18 +177,27 @@ def _cross_attn(attn: nn.Module, x: torch.Tensor, ctx: torch.Tensor, num_mot_ref
     q = _linear(attn.to_q, x)
     ops.qk_norm_rope_(q, None, heads=heads, head_dim=hd, wq=_f32(attn.norm_q, "w", attn.norm_q.weight), rows_per_batch=q.shape[1], eps=eps,
                       mode=ops.QK_WAN)
-    Wkv, bkv = _packed(attn, "kv", [attn.to_k, attn.to_v])
-    kv = ops.linear(ctx_txt, Wkv, bkv)
-    ops.qk_norm_rope_(kv[..., :inner], None, heads=heads, head_dim=hd, wq=_f32(attn.norm_k, "w", attn.norm_k.weight),
-                      rows_per_batch=kv.shape[1], eps=eps, mode=ops.QK_WAN)
-    qh = _heads_view(q, heads)
-    o = ops.attention(qh, _heads_view(kv[..., :inner], heads), _heads_view(kv[..., inner:], heads))
-    o = _token_major(o)
-    if img_len > 0 and getattr(attn, "add_k_proj", None) is not None:
+
+    def text_kv():
+        Wkv, bkv = _packed(attn, "kv", [attn.to_k, attn.to_v])
+        kv = ops.linear(ctx_txt, Wkv, bkv)
+        ops.qk_norm_rope_(kv[..., :inner], None, heads=heads, head_dim=hd, wq=_f32(attn.norm_k, "w", attn.norm_k.weight),
+                          rows_per_batch=kv.shape[1], eps=eps, mode=ops.QK_WAN)
+        return kv
+
+    def image_kv():
         Wi, bi = _packed(attn, "kv_img", [attn.add_k_proj, attn.add_v_proj])
         kvi = ops.linear(ctx_img, Wi, bi)
         ops.qk_norm_rope_(kvi[..., :inner], None, heads=heads, head_dim=hd, wq=_f32(attn.norm_added_k, "w", attn.norm_added_k.weight),
                           rows_per_batch=kvi.shape[1], eps=eps, mode=ops.QK_WAN)
+        return kvi
+
+    kv = _cached(attn, "kv", (ctx,), text_kv)  # keyed on the whole context tensor: ctx_txt / ctx_img are fresh views of it
+    qh = _heads_view(q, heads)
+    o = ops.attention(qh, _heads_view(kv[..., :inner], heads), _heads_view(kv[..., inner:], heads))
+    o = _token_major(o)
+    if img_len > 0 and getattr(attn, "add_k_proj", None) is not None:
+        kvi = _cached(attn, "kv_img", (ctx,), image_kv)
         o_img = _token_major(ops.attention(qh, _heads_view(kvi[..., :inner], heads), _heads_view(kvi[..., inner:], heads)))
         o = o + o_img  # two independent softmaxes summed in bf16 (:186)
     return o
@@ -374,17 +434,23 @@ class WanTimeTextImageEmbedding(nn.Module):
         emb = t[:, None].float() * torch.exp(exponent)[None, :]
         return torch.cat([torch.cos(emb), torch.sin(emb)], dim=-1)
 
+    def context(self, text: torch.Tensor, image: Optional[torch.Tensor]) -> torch.Tensor:
+        """The cross-attention context [B, (257 +) 512, d] = cat(image tokens, text tokens) (:979-982) — constant over a denoise loop,
+        memoised on the input tensors while `context_cache()` is on."""
+        def compute():
+            t = self.text_embedder(text)
+            return t if image is None else torch.cat([self.image_embedder(image), t], dim=1)
+        return _cached(self, "context", (text, image), compute)
+
     def forward(self, timesteps: List[torch.Tensor], text: torch.Tensor, image: Optional[torch.Tensor]):
+        """-> (temb [n, d], timestep_proj [n, 6 d], context)."""
         w_dtype = self.time_embedder.linear_1.weight.dtype
         tembs, projs = [], []
         for ts in timesteps:
             e = self.time_embedder(self._sinusoid(ts).to(w_dtype)).type_as(text)
             tembs.append(e)
             projs.append(self.time_proj(self.act_fn(e)))
-        text = self.text_embedder(text)
-        if image is not None:
-            image = self.image_embedder(image)
-        return torch.cat(tembs, 0), torch.cat(projs, 0), text, image
+        return torch.cat(tembs, 0), torch.cat(projs, 0), self.context(text, image)
 
 
 class WanTransformer3DMOTModel(nn.Module):
@@ -441,14 +507,11 @@ class WanTransformer3DMOTModel(nn.Module):
             x, xr = ulysses.shard_rows(x, sp).contiguous(), ulysses.shard_rows(xr, sp).contiguous()
             rope = tuple(ulysses.shard_rows(t, sp, 0) for t in rope)
             rope_r = tuple(ulysses.shard_rows(t, sp, 0) for t in rope_r)
-        temb, proj, ctx, ctx_img = self.condition_embedder([timestep], encoder_hidden_states, encoder_hidden_states_image)
+        temb, proj, ctx = self.condition_embedder([timestep], encoder_hidden_states, encoder_hidden_states_image)
         proj = proj.unflatten(1, (6, -1))
-        temb_r, proj_r, ctx_r, ctx_img_r = self.condition_embedder_mot_ref(list(timestep_list_mot_ref), encoder_hidden_states_mot_ref,
-                                                                          encoder_hidden_states_image_mot_ref)
+        temb_r, proj_r, ctx_r = self.condition_embedder_mot_ref(list(timestep_list_mot_ref), encoder_hidden_states_mot_ref,
+                                                                encoder_hidden_states_image_mot_ref)
         proj_r = proj_r.unflatten(1, (6, -1))
-        if ctx_img is not None:
-            ctx = torch.cat([ctx_img, ctx], dim=1)
-            ctx_r = torch.cat([ctx_img_r, ctx_r], dim=1)
 
         for block in self.blocks:
             x, xr = block(hidden_states=x, encoder_hidden_states=ctx, temb=proj, rotary_emb=rope, hidden_states_mot_ref=xr,
