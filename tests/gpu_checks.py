@@ -634,10 +634,16 @@ def check_wan_denoise_cached():
             outs.append(vap.denoise.wan_denoise(model, lat0.to(DEV), inp["hidden_states"][:, 16:].float().to(DEV), lat_ref.to(DEV),
                                                 inp["hidden_states_mot_ref"][:, 16:].float().to(DEV), kw, kw_u, dn["steps"], dn["shift"], dn["guidance"],
                                                 cache_context=cache))
+        lat_b2 = vap.denoise.wan_denoise(model, lat0.to(DEV), inp["hidden_states"][:, 16:].float().to(DEV), lat_ref.to(DEV),
+                                         inp["hidden_states_mot_ref"][:, 16:].float().to(DEV), kw, kw_u, dn["steps"], dn["shift"], dn["guidance"],
+                                         cache_context=True, batch_cfg=True)
     assert torch.equal(outs[0], outs[1]), f"cached loop differs: rel err {rel_err(outs[1], outs[0])}"
     cos = cosine(outs[1], dn["final_latents"])
     assert cos >= 0.999
-    return dict(cosine=cos, bit_exact=True)
+    # the B = 2 forward runs the same kernels per sample (per-batch launches or batch-strided launches): expected bit-exact as well
+    err_b2, cos_b2 = rel_err(lat_b2, outs[0]), cosine(lat_b2, dn["final_latents"])
+    assert cos_b2 >= 0.999 and err_b2 < 2e-2, f"batched-CFG loop: cosine {cos_b2}, rel err vs the sequential loop {err_b2}"
+    return dict(cosine=cos, bit_exact=True, batch_cfg_bit_exact=bool(torch.equal(lat_b2, outs[0])), batch_cfg_err=err_b2, batch_cfg_cosine=cos_b2)
 
 
 CHECKS = {

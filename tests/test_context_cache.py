@@ -47,6 +47,15 @@ def _worker(q):
         # context K/V projections: packed [2 * inner, inner] weights applied to 512 text rows / 257 image rows
         res["kv_launches_cache_%d" % cache] = sum(n for (N, K, M), n in counts.items() if M in (512, 257))
     res["bit_exact"] = bool(torch.equal(outs[0], outs[1]))
+    # classifier-free guidance as one B = 2 forward per step == two B = 1 forwards (same arithmetic per sample), with and without the cache
+    for cache in (False, True):
+        counts.clear()
+        lat = vap.denoise.wan_denoise(model, lat0.clone(), cond, lat_ref, cond_ref, kw, kw_u, 3, 3.0, 5.0, cache_context=cache, batch_cfg=True)
+        res["batch_cfg_exact_cache_%d" % cache] = bool(torch.equal(lat, outs[0]))
+        res["batch_cfg_launches_cache_%d" % cache] = sum(counts.values())
+    counts.clear()
+    vap.denoise.wan_denoise(model, lat0.clone(), cond, lat_ref, cond_ref, kw, kw_u, 3, 3.0, 5.0, cache_context=False)
+    res["sequential_launches"] = sum(counts.values())
     res["left_over_entries"] = sum(1 for m in model.modules() if "_vap_ctx_cache" in m.__dict__)
     # the cache keys on tensor identity AND version: an in-place edit of the conditioning must miss
     with vap.wan.context_cache():
@@ -73,3 +82,5 @@ def test_context_cache_is_bit_exact_and_skips_the_constant_projections():
     # the key is the concatenated [image | text] context, so 2 contexts x 2 projections x 5 modules = 20
     assert res["kv_launches_cache_0"] == 60 and res["kv_launches_cache_1"] == 20, res
     assert res["left_over_entries"] == 0 and res["version_miss"], res
+    assert res["batch_cfg_exact_cache_0"] and res["batch_cfg_exact_cache_1"], res
+    assert res["batch_cfg_launches_cache_0"] < res["sequential_launches"], res

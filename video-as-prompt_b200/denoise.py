@@ -34,10 +34,13 @@ def flow_match_step(model_output: torch.Tensor, sample: torch.Tensor, sigma: tor
 @torch.no_grad()
 def wan_denoise(model, latents: torch.Tensor, condition: torch.Tensor, latents_ref: torch.Tensor, condition_ref: torch.Tensor, cond_kwargs: dict,
                 uncond_kwargs: Optional[dict], num_steps: int, shift: float = 3.0, guidance_scale: float = 5.0, dtype=torch.bfloat16,
-                fused_step: bool = False, cache_context: bool = True) -> torch.Tensor:
+                fused_step: bool = False, cache_context: bool = True, batch_cfg: bool = False) -> torch.Tensor:
     """Run `num_steps` denoise steps of the Wan VAP pipeline loop on `model` (ours or the reference's after install()).
     cache_context: the text / CLIP context embeddings and every block's cross-attention K / V are the same at every step and in both
     guidance passes; compute them once per loop (wan.context_cache; identical results — the cached tensors are what would be recomputed).
+    batch_cfg: run the conditional and the unconditional pass of a step as ONE B = 2 forward (what the CogVideoX pipeline does,
+    pipeline_cogvideox_image2video_mot.py:972-1001) instead of the Wan pipeline's two sequential B = 1 forwards (:815-861): every weight
+    is read once per step and the per-stream GEMMs see twice the rows.  Same arithmetic per sample.
     fused_step: classifier-free guidance + scheduler update in ONE kernel (ops.cfg_flow_match_step) instead of seven torch
     elementwise launches — same rounding points (opt-in until its GPU parity check has run, tests/gpu_checks.py)."""
     dev = latents.device
@@ -48,26 +51,40 @@ def wan_denoise(model, latents: torch.Tensor, condition: torch.Tensor, latents_r
     from . import wan
     x_ref = torch.cat([latents_ref, condition_ref], dim=1).to(dtype)
     ts_ref = torch.ones((1, latents.shape[0]), dtype=torch.float32, device=dev)  # reference video is clean: timestep 1 (:812-813)
+    if batch_cfg and uncond_kwargs is not None:
+        # the B = 2 conditioning is concatenated ONCE, so the context cache sees the same tensors at every step
+        cond_kwargs = {k: (torch.cat([v, uncond_kwargs[k]], dim=0) if torch.is_tensor(v) else v) for k, v in cond_kwargs.items()}
+        x_ref, ts_ref = torch.cat([x_ref, x_ref], dim=0), torch.cat([ts_ref, ts_ref], dim=1)
+    else:
+        batch_cfg = False
     try:
         with wan.context_cache(cache_context):
             return _wan_denoise_loop(model, latents, condition, x_ref, ts_ref, cond_kwargs, uncond_kwargs, num_steps, timesteps, sigmas, guidance_scale, dtype,
-                                     dts if fused_step else None)
+                                     dts if fused_step else None, batch_cfg)
     finally:
         if cache_context and isinstance(model, torch.nn.Module):
             wan.clear_context_cache(model)  # the entries keep the conditioning tensors alive: drop them with the loop
 
 
-def _wan_denoise_loop(model, latents, condition, x_ref, ts_ref, cond_kwargs, uncond_kwargs, num_steps, timesteps, sigmas, guidance_scale, dtype, dts):
+def _wan_denoise_loop(model, latents, condition, x_ref, ts_ref, cond_kwargs, uncond_kwargs, num_steps, timesteps, sigmas, guidance_scale, dtype, dts,
+                      batch_cfg):
     fused_step = dts is not None
     if fused_step:
         from . import ops
+    nb = latents.shape[0]
     for i in range(num_steps):
         x_in = torch.cat([latents, condition], dim=1).to(dtype)
-        ts = timesteps[i].expand(latents.shape[0])
-        noise = model(hidden_states=x_in, timestep=ts, hidden_states_mot_ref=x_ref, timestep_list_mot_ref=ts_ref, return_dict=False, **cond_kwargs)[0]
+        ts = timesteps[i].expand(nb)
+        if batch_cfg:  # [conditional | unconditional] samples in one forward
+            both = model(hidden_states=torch.cat([x_in, x_in], dim=0), timestep=timesteps[i].expand(2 * nb), hidden_states_mot_ref=x_ref,
+                         timestep_list_mot_ref=ts_ref, return_dict=False, **cond_kwargs)[0]
+            noise, noise_u = both[:nb].contiguous(), both[nb:].contiguous()
+        else:
+            noise = model(hidden_states=x_in, timestep=ts, hidden_states_mot_ref=x_ref, timestep_list_mot_ref=ts_ref, return_dict=False, **cond_kwargs)[0]
         if uncond_kwargs is not None:
-            noise_u = model(hidden_states=x_in, timestep=ts, hidden_states_mot_ref=x_ref, timestep_list_mot_ref=ts_ref, return_dict=False,
-                            **uncond_kwargs)[0]
+            if not batch_cfg:
+                noise_u = model(hidden_states=x_in, timestep=ts, hidden_states_mot_ref=x_ref, timestep_list_mot_ref=ts_ref, return_dict=False,
+                                **uncond_kwargs)[0]
             if fused_step:
                 latents = ops.cfg_flow_match_step(noise, noise_u, latents.contiguous(), guidance_scale=guidance_scale, dt=dts[i])
                 continue
