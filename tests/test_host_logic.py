@@ -54,6 +54,14 @@ def test_ops_fail_loudly_on_cpu_tensors():
                           torch.zeros(1, 1, 8, 128, dtype=torch.bfloat16))
     with pytest.raises(TypeError):
         vap.ops._need_cuda_bf16("nope", "x")
+    # forward-only kernels: a tensor that wants gradients is refused instead of silently losing its graph (trainer drop-in is open)
+    w = torch.zeros(256, 256, dtype=torch.bfloat16, requires_grad=True)
+    with pytest.raises(vap.VapError, match="inference-only"):
+        vap.ops._need_cuda_bf16(w, "weight")
+    with pytest.raises(vap.VapError, match="inference-only"):
+        vap.ops.linear(w, w)
+    with torch.no_grad(), pytest.raises(vap.VapError, match="no CPU fallback"):
+        vap.ops.linear(w, w)
 
 
 def test_joint_sdpa_constraints():

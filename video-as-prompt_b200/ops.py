@@ -31,6 +31,10 @@ def _stream() -> int:
 def _need_cuda_bf16(t: torch.Tensor, name: str) -> None:
     if not isinstance(t, torch.Tensor):
         raise TypeError(f"{name} must be a torch.Tensor")
+    if t.requires_grad and torch.is_grad_enabled():
+        # the kernels are forward-only and their outputs carry no grad_fn: refusing is better than silently cutting the graph of a trainer
+        raise VapError(f"{name} requires grad inside a grad-enabled region: the VAP kernels are inference-only (no backward yet); "
+                       "call under torch.no_grad() / torch.inference_mode()")
     if not t.is_cuda:
         raise VapError(f"{name} is on {t.device}: the VAP kernels are CUDA-only (sm_100a); there is no CPU fallback")
     if t.dtype != torch.bfloat16:
