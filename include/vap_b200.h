@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define VAP_B200_VERSION 301 /* major*10000 + minor*100 + patch */
+#define VAP_B200_VERSION 302 /* major*10000 + minor*100 + patch */
 
 /* Library version (VAP_B200_VERSION of the build). */
 int vap_version(void);
@@ -128,6 +128,18 @@ int vap_attention_fwd_splitkv(const void* q, const void* k, const void* v, void*
                               int64_t v_sh, int64_t v_sl, float scale, void* stream);
 int vap_attention_combine(const void* o_part, const float* lse_part, int kv_splits, int B, int H, int Lq, int D, void* o, void* const* o_peers,
                           int npeers, int o_rows_per_peer, float* lse, int64_t o_sb, int64_t o_sh, int64_t o_sl, void* stream);
+
+/* (3c) Joint attention BACKWARD (written without GPU access at the end of round 1 — its parity check sits in
+ *      tests/gpu_checks.py:CHECKS_PENDING until it has run on a B200): dq, dk, dv from dout, the forward's output o and its
+ *      log-sum-exp lse [B,H,Lq] (the optional output of vap_attention_fwd).  Same layouts as (3): q / o / dout / dq [B,H,Lq,D],
+ *      k / v / dk / dv [B,H,Lkv,D] addressed by element strides, D in {64, 128} contiguous.  `strides` is a HOST array of 24 int64:
+ *      (batch, head, token) strides of q, k, v, o, dout, dq, dk, dv in that order.  delta_ws [B,H,Lq] fp32 is a caller-allocated
+ *      workspace (rowsum(dout * o)).  Three launches on `stream`: delta, dQ (per 128 query rows, streams K/V), dK+dV (per 128 KV
+ *      rows, streams Q/dO); deterministic, no atomics.
+ *      Ref: the autograd of F.scaled_dot_product_attention at transformer_wan_mot.py:637-644 / cogvideox_transformer_3d_mot.py:424-431
+ *      as the trainer runs it (finetrainers/trainer/sft_trainer/trainer.py:674-714, attention_dispatch.py:416-458). */
+int vap_attention_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse, void* dq, void* dk, void* dv,
+                      float* delta_ws, int B, int H, int Lq, int Lkv, int D, const int64_t* strides, float scale, void* stream);
 
 /* (8) Classifier-free guidance + FlowMatchEuler scheduler update of the Wan denoise loop, one elementwise pass (HBM-bound):
  *       n   = noise_uncond ? bf16(u + bf16(g * bf16(c - u))) : c     Ref: pipelines/wan/pipeline_wan_i2v_mot.py:874 (three bf16 tensor ops)

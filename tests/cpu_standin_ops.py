@@ -82,7 +82,10 @@ def qk_norm_rope_(q, k, *, heads, head_dim, wq, wk=None, bq=None, bk=None, cos=N
 
 def attention(q, k, v, *, scale=None, out=None, return_lse=False):
     B, H, Lq, D = q.shape
-    o = oc.sdpa_explicit_fp32(q, k, v).to(BF16)  # [B, H, Lq, D]
+    if scale is None or scale == D ** -0.5:
+        o = oc.sdpa_explicit_fp32(q, k, v).to(BF16)  # [B, H, Lq, D]
+    else:  # a caller-chosen softmax scale (the oracle helper fixes it at D^-1/2)
+        o = torch.matmul(torch.softmax(torch.matmul(q.float(), k.float().transpose(-1, -2)) * scale, dim=-1), v.float()).to(BF16)
     res = torch.empty((B, Lq, H, D), dtype=BF16).transpose(1, 2)  # token-major memory like the kernel's output
     res.copy_(o)
     if out is not None:
@@ -92,6 +95,25 @@ def attention(q, k, v, *, scale=None, out=None, return_lse=False):
         s = torch.matmul(q.float(), k.float().transpose(-1, -2)) * (scale or D ** -0.5)
         return res, torch.logsumexp(s, dim=-1)
     return res
+
+
+def attention_bwd(q, k, v, o, lse, dout, *, scale=None):
+    """vap_attention_bwd's arithmetic (attn_bwd_sm100.cu): P recomputed from the stored log-sum-exp, delta = rowsum(dO o O),
+    P and dS rounded to bf16 before the second round of products (they are tensor-core operands), fp32 accumulation."""
+    B, H, Lq, D = q.shape
+    sc = scale or D ** -0.5
+    qf, kf, vf, of, gf = (t.float() for t in (q, k, v, o, dout))
+    p = torch.exp(torch.matmul(qf, kf.transpose(-1, -2)) * sc - lse.unsqueeze(-1))
+    delta = (gf * of).sum(-1, keepdim=True)
+    ds = (p * (torch.matmul(gf, vf.transpose(-1, -2)) - delta) * sc).to(BF16).float()
+    pb = p.to(BF16).float()
+    outs = (torch.matmul(ds, kf), torch.matmul(ds.transpose(-1, -2), qf), torch.matmul(pb.transpose(-1, -2), gf))
+    res = []
+    for g in outs:
+        r = torch.empty((B, g.shape[2], H, D), dtype=BF16).transpose(1, 2)
+        r.copy_(g.to(BF16))
+        res.append(r)
+    return tuple(res)
 
 
 def linear(x, weight, bias=None, *, epilogue=0, residual=None, gate=None, rows_per_batch=None, out=None):
@@ -147,6 +169,6 @@ def cfg_flow_match_step(noise_cond, noise_uncond, sample, *, guidance_scale, dt,
 
 def install(vap) -> None:
     """Replace the kernel wrappers of `vap.ops` by the stand-ins (one test process only)."""
-    for name in ("adaln_layernorm", "qk_norm_rope_", "attention", "linear", "ulysses_pack", "ulysses_unpack", "cfg_flow_match_step"):
+    for name in ("adaln_layernorm", "qk_norm_rope_", "attention", "attention_bwd", "linear", "ulysses_pack", "ulysses_unpack", "cfg_flow_match_step"):
         setattr(vap.ops, name, globals()[name])
     vap.ops.sm_count = lambda: 148

@@ -558,6 +558,33 @@ def check_ulysses_p2p_emulated_splitkv():
         ops._SPLIT_CACHE.clear()
 
 
+def check_attention_bwd(B=1, H=2, Lq=300, Lkv=300, D=128, joint_layout=True, seed=80, tol=2e-2):
+    """vap_attention_bwd (dQ, dK, dV from dO + the forward's LSE) against torch autograd of the definition-level fp32 attention on the
+    GPU, called both directly and through the differentiable B2 seam (`joint_sdpa` under autograd).  Gate: max-abs <= 2e-2 relative
+    per gradient (P and dS are bf16 tensor-core operands, the outputs are bf16)."""
+    if joint_layout:
+        qkv = _randn((B, Lq, 3, H, D), seed).to(DEV)
+        q, k, v = (qkv[:, :, i].transpose(1, 2) for i in range(3))
+    else:
+        q = _randn((B, Lq, H, D), seed).to(DEV).transpose(1, 2)
+        k = _randn((B, Lkv, H, D), seed + 1).to(DEV).transpose(1, 2)
+        v = _randn((B, Lkv, H, D), seed + 2).to(DEV).transpose(1, 2)
+    go = _randn((B, Lq, H, D), seed + 3).to(DEV).transpose(1, 2)
+    ref_in = [t.detach().float().requires_grad_(True) for t in (q, k, v)]
+    s_ref = torch.matmul(ref_in[0], ref_in[1].transpose(-1, -2)) * D ** -0.5
+    o_ref = torch.matmul(torch.softmax(s_ref, dim=-1), ref_in[2])
+    ref = torch.autograd.grad(o_ref, ref_in, go.float())
+    o, lse = ops.attention(q, k, v, return_lse=True)
+    got = ops.attention_bwd(q, k, v, o, lse, go)
+    errs = [rel_err(a, b) for a, b in zip(got, ref)]
+    # through autograd (what a trainer does): leaves that require grad, joint_sdpa, backward
+    leaves = [t.detach().clone().requires_grad_(True) for t in (q, k, v)]
+    vap.joint_sdpa(*leaves).backward(go)
+    errs_seam = [rel_err(t.grad, b) for t, b in zip(leaves, ref)]
+    assert max(errs) <= tol and max(errs_seam) <= tol, f"attention bwd B={B} H={H} Lq={Lq} Lkv={Lkv} D={D}: dq/dk/dv rel err {errs}, via autograd {errs_seam}"
+    return dict(dq=errs[0], dk=errs[1], dv=errs[2], seam=max(errs_seam))
+
+
 def check_cfg_flow_match_step(B=2, inner=16 * 3 * 16 * 16):
     """vap_cfg_flow_match_step against the reference's own tensor expression evaluated by torch ON THE GPU (integer-exact comparison
     of the bf16 results): pipeline_wan_i2v_mot.py:874 + scheduling_flow_match_euler_discrete.py:433-467.  torch's CUDA kernel keeps
@@ -703,6 +730,11 @@ CHECKS = {
 # Checks of code written without GPU access (the round's GPU budget was spent): run by `tools/gpu_diag.py --pending`, promoted into
 # CHECKS (and so into `pytest -m gpu`) once they have passed on a B200.
 CHECKS_PENDING = {
+    "attn_bwd_d128": lambda: check_attention_bwd(1, 2, 300, 300, 128),
+    "attn_bwd_one_tile": lambda: check_attention_bwd(1, 1, 100, 100, 128, joint_layout=False),
+    "attn_bwd_d64": lambda: check_attention_bwd(2, 3, 452, 260, 64, joint_layout=False),
+    "attn_bwd_tails": lambda: check_attention_bwd(1, 1, 130, 128 * 5 + 7, 128, joint_layout=False),
+    "attn_bwd_multi_tile": lambda: check_attention_bwd(1, 2, 1000, 1000, 128),
     "cfg_flow_match_step": check_cfg_flow_match_step,
     "wan_denoise_fused": check_wan_denoise_fused,
     "wan_denoise_cached": check_wan_denoise_cached,

@@ -20,7 +20,7 @@ PKG = CSRC.parent
 ROOT = PKG.parent
 LIB = PKG / "libvap_b200.so"
 BUILD = CSRC / "build"
-SOURCES = ["capi.cu", "norm_kernels.cu", "gemm_sm100.cu", "attn_sm100.cu", "probe_sm100.cu"]
+SOURCES = ["capi.cu", "norm_kernels.cu", "gemm_sm100.cu", "attn_sm100.cu", "attn_bwd_sm100.cu", "probe_sm100.cu"]
 HEADERS = ["vap_common.cuh", "vap_kernels.cuh", str(ROOT / "include" / "vap_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [

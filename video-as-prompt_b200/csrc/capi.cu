@@ -292,6 +292,25 @@ int vap_ulysses_unpack(const void* src, void* dst, int64_t L, int nsplit, int64_
     return launch_ulysses(src, dst, L, nsplit, chunk, dst_row_stride, src_row_stride, src_split_stride, 1, static_cast<cudaStream_t>(stream));
 }
 
+int vap_attention_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse, void* dq, void* dk, void* dv,
+                      float* delta_ws, int B, int H, int Lq, int Lkv, int D, const int64_t* strides, float scale, void* stream) {
+    VAP_REQUIRE(q && k && v && o && dout && lse && dq && dk && dv && delta_ws && strides, "vap_attention_bwd: null argument");
+    AttnBwdArgs a{};
+    a.B = B, a.H = H, a.Lq = Lq, a.Lkv = Lkv;
+    const int64_t* s = strides;  // (batch, head, token) element strides of q, k, v, o, dout, dq, dk, dv in that order
+    a.q = AttnTensor{static_cast<const __nv_bfloat16*>(q), s[0], s[1], s[2]};
+    a.k = AttnTensor{static_cast<const __nv_bfloat16*>(k), s[3], s[4], s[5]};
+    a.v = AttnTensor{static_cast<const __nv_bfloat16*>(v), s[6], s[7], s[8]};
+    a.o = AttnTensor{static_cast<const __nv_bfloat16*>(o), s[9], s[10], s[11]};
+    a.dout = AttnTensor{static_cast<const __nv_bfloat16*>(dout), s[12], s[13], s[14]};
+    a.dq = AttnGrad{static_cast<__nv_bfloat16*>(dq), s[15], s[16], s[17]};
+    a.dk = AttnGrad{static_cast<__nv_bfloat16*>(dk), s[18], s[19], s[20]};
+    a.dv = AttnGrad{static_cast<__nv_bfloat16*>(dv), s[21], s[22], s[23]};
+    a.lse = lse, a.delta = delta_ws;
+    a.scale = scale;
+    return launch_attention_bwd(a, D, static_cast<cudaStream_t>(stream));
+}
+
 int vap_cfg_flow_match_step(const void* noise_cond, const void* noise_uncond, const void* sample, int sample_is_f32, void* out, int64_t batch,
                             int64_t inner, int64_t out_batch_stride, float guidance_scale, float dt, void* stream) {
     VAP_REQUIRE(noise_cond && sample && out, "vap_cfg_flow_match_step: null tensor");

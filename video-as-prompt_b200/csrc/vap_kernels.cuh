@@ -70,6 +70,21 @@ struct AttnTensor {
 };
 int launch_attention_fwd(const AttnTensor& q, const AttnTensor& k, const AttnTensor& v, AttnParams p, int D, cudaStream_t stream);
 
+// Attention backward (attn_bwd_sm100.cu): dQ, dK, dV from dO, O and the forward's log-sum-exp.
+struct AttnGrad {
+    __nv_bfloat16* ptr;
+    int64_t sb, sh, sl;
+};
+struct AttnBwdArgs {
+    int B, H, Lq, Lkv;
+    AttnTensor q, k, v, o, dout;  // q / o / dout [B,H,Lq,D], k / v [B,H,Lkv,D] by element strides
+    const float* lse;             // [B, H, Lq] natural-log LSE of the scaled scores (vap_attention_fwd's optional output)
+    float* delta;                 // [B, H, Lq] workspace: rowsum(dO o O)
+    AttnGrad dq, dk, dv;
+    float scale;
+};
+int launch_attention_bwd(const AttnBwdArgs& a, int D, cudaStream_t stream);
+
 // Merge of split-KV partials: O = sum_s w_s O_s, w_s = exp(lse_s - lse) ; the result goes to `dst` exactly as the attention
 // epilogue would have written it (plain strided tensor or rows scattered to their owning peers; dst.lse optional).
 struct AttnCombineParams {

@@ -170,6 +170,38 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: Optio
     return (out, lse) if return_lse else out
 
 
+def attention_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, o: torch.Tensor, lse: torch.Tensor, dout: torch.Tensor, *,
+                  scale: Optional[float] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Gradients of `attention` (vap_attention_bwd): q / o / dout [B,H,Lq,D], k / v [B,H,Lkv,D] (any batch/head/token strides, D
+    contiguous), lse [B,H,Lq] fp32 from ``attention(..., return_lse=True)``.  Returns dq, dk, dv with the logical shapes of q, k, v,
+    laid out token-major like the forward's output.  Pending its first GPU run (tests/gpu_checks.py:CHECKS_PENDING)."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v"), (o, "o"), (dout, "dout")):
+        _need_cuda_bf16(t, n)
+        if t.dim() != 4 or t.stride(-1) != 1:
+            raise ValueError(f"{n} must be [B,H,L,D] with contiguous D, got shape {tuple(t.shape)} strides {t.stride()}")
+    B, H, Lq, D = q.shape
+    Lkv = k.shape[2]
+    if k.shape != (B, H, Lkv, D) or v.shape != (B, H, Lkv, D) or o.shape != q.shape or dout.shape != q.shape:
+        raise ValueError(f"q {tuple(q.shape)}, k {tuple(k.shape)}, v {tuple(v.shape)}, o {tuple(o.shape)}, dout {tuple(dout.shape)} are inconsistent")
+    if lse.shape != (B, H, Lq) or not lse.is_contiguous():
+        raise ValueError(f"lse must be a contiguous [B,H,Lq] tensor, got {tuple(lse.shape)}")
+    lse_ptr = _need_cuda_f32(lse, "lse")
+    if scale is None:
+        scale = D ** -0.5
+    dq = torch.empty((B, Lq, H, D), dtype=torch.bfloat16, device=q.device).transpose(1, 2)
+    dk = torch.empty((B, Lkv, H, D), dtype=torch.bfloat16, device=q.device).transpose(1, 2)
+    dv = torch.empty((B, Lkv, H, D), dtype=torch.bfloat16, device=q.device).transpose(1, 2)
+    if B * H * Lq * Lkv == 0:
+        return dq.zero_(), dk.zero_(), dv.zero_()
+    delta = torch.empty((B, H, Lq), dtype=torch.float32, device=q.device)
+    import ctypes
+    strides = (ctypes.c_int64 * 24)(*[st for t in (q, k, v, o, dout, dq, dk, dv) for st in t.stride()[:3]])
+    rc = _lib.load().vap_attention_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), dout.data_ptr(), lse_ptr, dq.data_ptr(), dk.data_ptr(),
+                                       dv.data_ptr(), delta.data_ptr(), B, H, Lq, Lkv, D, strides, float(scale), _stream())
+    _lib.check(rc, "vap_attention_bwd")
+    return dq, dk, dv
+
+
 _SPLIT_CACHE = {}
 
 

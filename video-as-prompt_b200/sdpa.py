@@ -14,6 +14,26 @@ from . import ops
 _ORIGINAL_SDPA = None
 
 
+class _JointAttention(torch.autograd.Function):
+    """Differentiable joint attention for the trainer's B2 seam: forward = vap_attention_fwd (keeps O and the log-sum-exp),
+    backward = vap_attention_bwd.  (The backward kernel is pending its first GPU run)"""
+
+    @staticmethod
+    def forward(ctx, q, k, v, scale):
+        o, lse = ops.attention(q, k, v, scale=scale, return_lse=True)
+        ctx.save_for_backward(q, k, v, o, lse)
+        ctx.scale = scale
+        return o
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, k, v, o, lse = ctx.saved_tensors
+        if dout.stride(-1) != 1:
+            dout = dout.contiguous()
+        dq, dk, dv = ops.attention_bwd(q, k, v, o, lse, dout, scale=ctx.scale)
+        return dq, dk, dv, None
+
+
 def joint_sdpa(query: torch.Tensor, key: torch.Tensor, value: torch.Tensor, attn_mask: Optional[torch.Tensor] = None,
                dropout_p: float = 0.0, is_causal: bool = False, scale: Optional[float] = None, enable_gqa: bool = False,
                attention_kwargs: Optional[Dict[str, Any]] = None) -> torch.Tensor:
@@ -32,6 +52,8 @@ def joint_sdpa(query: torch.Tensor, key: torch.Tensor, value: torch.Tensor, attn
     if query.shape[-1] not in (64, 128):
         raise ValueError(f"joint_sdpa: head_dim {query.shape[-1]} not in (64, 128)")
     q, k, v = (t if t.stride(-1) == 1 else t.contiguous() for t in (query, key, value))
+    if torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad):
+        return _JointAttention.apply(q, k, v, scale)  # trainer path: O keeps a grad_fn
     return ops.attention(q, k, v, scale=scale)
 
 
