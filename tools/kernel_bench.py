@@ -2,7 +2,7 @@
 (BASELINE.json configs[4]: joint-attention sweep 8k-128k, head_dim 128; plus the real joint lengths and the GEMM shapes
 of the Wan-14B / CogVideoX-5B blocks).  CUDA-event timing, 3 warm-ups, L2 flushed between iterations.
 
-    python tools/kernel_bench.py [--attn] [--gemm] [--quick] > gpurun_out/kernel_bench.json
+    python tools/kernel_bench.py [--attn] [--gemm] [--mem] [--bwd] [--quick] > gpurun_out/kernel_bench.json
 """
 import argparse
 import importlib
@@ -65,6 +65,32 @@ def attn_case(H, J, D, results):
     print(json.dumps(rec), flush=True)
 
 
+def attn_bwd_case(H, J, D, results):
+    """Backward of the joint attention: vap_attention_bwd (delta + dQ + dK/dV kernels) against torch autograd through SDPA (cuDNN / flash).
+    FLOP convention: 2.5 x the forward's 4 H J^2 D (five J x J x D products); the kernels execute seven (S and dP are recomputed)."""
+    g = torch.Generator(device=DEV).manual_seed(0)
+    qkv = torch.randn((1, J, 3 * H * D), generator=g, device=DEV, dtype=torch.float32).to(torch.bfloat16)
+    q, k, v = (qkv[..., i * H * D:(i + 1) * H * D].unflatten(2, (H, D)).transpose(1, 2) for i in range(3))
+    go = torch.randn((1, J, H, D), generator=g, device=DEV, dtype=torch.float32).to(torch.bfloat16).transpose(1, 2)
+    flops = 10.0 * H * J * J * D
+    rec = dict(kind="attention_bwd", H=H, J=J, D=D, flop=flops)
+    o, lse = ops.attention(q, k, v, return_lse=True)
+    best, _ = timeit(lambda: ops.attention_bwd(q, k, v, o, lse, go))
+    rec["vap_ms"], rec["vap_tflops"] = best, flops / best / 1e9
+    from torch.nn.attention import SDPBackend, sdpa_kernel
+    for name, be in (("cudnn", SDPBackend.CUDNN_ATTENTION), ("flash", SDPBackend.FLASH_ATTENTION)):
+        try:
+            leaves = [t.contiguous().requires_grad_(True) for t in (q, k, v)]
+            with sdpa_kernel(be):
+                out = F.scaled_dot_product_attention(*leaves)
+                best, _ = timeit(lambda: torch.autograd.grad(out, leaves, go, retain_graph=True))
+            rec[f"torch_{name}_bwd_ms"], rec[f"torch_{name}_bwd_tflops"] = best, flops / best / 1e9
+        except Exception as e:  # noqa: BLE001
+            rec[f"torch_{name}_bwd_err"] = str(e)[:120]
+    results.append(rec)
+    print(json.dumps(rec), flush=True)
+
+
 def gemm_case(M, N, K, results, epilogue=0):
     g = torch.Generator(device=DEV).manual_seed(0)
     x = torch.randn((M, K), generator=g, device=DEV, dtype=torch.float32).to(torch.bfloat16)
@@ -107,9 +133,10 @@ def main():
     ap.add_argument("--attn", action="store_true")
     ap.add_argument("--gemm", action="store_true")
     ap.add_argument("--mem", action="store_true")
+    ap.add_argument("--bwd", action="store_true", help="attention backward (not part of the default set)")
     ap.add_argument("--quick", action="store_true")
     a = ap.parse_args()
-    if not (a.attn or a.gemm or a.mem):
+    if not (a.attn or a.gemm or a.mem or a.bwd):
         a.attn = a.gemm = a.mem = True
     results = []
     if a.attn:
@@ -117,6 +144,9 @@ def main():
                                                                        (40, 65536, 128), (5, 151200, 128), (48, 35552, 64)]
         for H, J, D in cases:
             attn_case(H, J, D, results)
+    if a.bwd:
+        for H, J, D in ([(40, 16384, 128)] if a.quick else [(40, 16384, 128), (40, 40560, 128), (48, 35552, 64)]):
+            attn_bwd_case(H, J, D, results)
     if a.gemm:
         cases = [(20280, 15360, 5120), (20280, 5120, 5120)] if a.quick else [(20280, 15360, 5120), (20280, 5120, 5120), (20280, 13824, 5120),
                                                                               (20280, 5120, 13824), (17776, 9216, 3072), (17776, 12288, 3072), (769, 10240, 5120)]
