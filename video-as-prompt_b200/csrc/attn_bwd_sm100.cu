@@ -223,25 +223,27 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmOwnA, const __grid_constan
                 tmem_ld_wait();
                 uint32_t pk_p[16], pk_ds[16];
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    float pv[2], dsv[2];
+                for (int e4 = 0; e4 < 8; ++e4) {  // four columns per step
+                    float lse2[4] = {row_lse2, row_lse2, row_lse2, row_lse2}, delta[4] = {row_delta, row_delta, row_delta, row_delta};
+                    if (kDKV) {  // per-column statistics of the streamed q rows: every lane reads the same 16 bytes (broadcast)
+                        const float4 l4 = ld_shared_v4_f32(stat + 4u * (32 * ch + 4 * e4));
+                        const float4 d4 = ld_shared_v4_f32(stat + 512u + 4u * (32 * ch + 4 * e4));
+                        lse2[0] = l4.x, lse2[1] = l4.y, lse2[2] = l4.z, lse2[3] = l4.w;
+                        delta[0] = d4.x, delta[1] = d4.y, delta[2] = d4.z, delta[3] = d4.w;
+                    }
+                    float pv[4], dsv[4];
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int col = 32 * ch + 2 * e + h;
-                        float lse2 = row_lse2, delta = row_delta;
-                        if (kDKV) {
-                            lse2 = ld_shared_f32(stat + 4u * col);
-                            delta = ld_shared_f32(stat + 512u + 4u * col);
-                        }
-                        float pe = ex2_approx(fmaf(__uint_as_float(sr[2 * e + h]), c, -lse2));
+                    for (int h = 0; h < 4; ++h) {
+                        const int col = 32 * ch + 4 * e4 + h;
+                        float pe = ex2_approx(fmaf(__uint_as_float(sr[4 * e4 + h]), c, -lse2[h]));
                         // outside the sequences: streamed rows past the end (zero-filled by TMA: S = 0 would give p = exp(-lse)) and rows
                         // of the resident tile past its end contribute nothing
                         if (col >= valid || !own_ok) pe = 0.f;
                         pv[h] = pe;
-                        dsv[h] = pe * (__uint_as_float(dr[2 * e + h]) - delta) * p.scale;
+                        dsv[h] = pe * (__uint_as_float(dr[4 * e4 + h]) - delta[h]) * p.scale;
                     }
-                    pk_p[e] = pack_bf16x2(pv[0], pv[1]);
-                    pk_ds[e] = pack_bf16x2(dsv[0], dsv[1]);
+                    pk_p[2 * e4] = pack_bf16x2(pv[0], pv[1]), pk_p[2 * e4 + 1] = pack_bf16x2(pv[2], pv[3]);
+                    pk_ds[2 * e4] = pack_bf16x2(dsv[0], dsv[1]), pk_ds[2 * e4 + 1] = pack_bf16x2(dsv[2], dsv[3]);
                 }
                 // packed bf16 over the fp32 columns this thread has already consumed: chunk ch read columns [32 ch, 32 ch + 32) and
                 // writes [16 ch, 16 ch + 16)

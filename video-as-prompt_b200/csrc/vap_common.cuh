@@ -481,6 +481,12 @@ __device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
     return v;
 }
 
+__device__ __forceinline__ float4 ld_shared_v4_f32(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
 // named barrier over a subset of warps
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
