@@ -1,6 +1,6 @@
 """bench.py — DiT denoise steps/s of the Wan2.1-14B VAP MoT transformer (49 frames, 480x832) on N B200s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config wan14b|wan14b_720p|cog5b|wan_tiny]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config wan14b|wan14b_d20|wan14b_d10|wan14b_720p|cog5b|wan_tiny]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 One "step" = one transformer forward at B=1 (what both reference pipelines repeat; Wan's CFG doubles it) + the scheduler
@@ -45,6 +45,12 @@ def workloads(synth):
         "wan14b": dict(family="wan", cfg=synth.WAN_14B, latent=(13, 60, 104), name="Wan2.1-I2V-14B VAP (40/40 MoT blocks), 49f 480x832"),
         "wan14b_720p": dict(family="wan", cfg=synth.WAN_14B, latent=(21, 90, 160), name="Wan2.1-I2V-14B VAP (40/40 MoT blocks), 81f 720x1280"),
         "cog5b": dict(family="cog", cfg=synth.COG_5B, latent=(13, 60, 90), name="CogVideoX-5B-I2V VAP (41/42 MoT blocks), 49f 480x720"),
+        # the reference's other two expert placements (examples/training/sft/wan/vap_mot/config_ori_d_20.json — the shipped training default — and
+        # config_ori_d_10.json; SURVEY §8 note 5): every 2nd / 4th block carries the MoT branch, the others run the target stream only
+        "wan14b_d20": dict(family="wan", cfg=dict(synth.WAN_14B, block_idx_with_mot_ref=list(range(0, 40, 2))), latent=(13, 60, 104),
+                           name="Wan2.1-I2V-14B VAP (20/40 MoT blocks, config_ori_d_20), 49f 480x832"),
+        "wan14b_d10": dict(family="wan", cfg=dict(synth.WAN_14B, block_idx_with_mot_ref=list(range(0, 40, 4))), latent=(13, 60, 104),
+                           name="Wan2.1-I2V-14B VAP (10/40 MoT blocks, config_ori_d_10), 49f 480x832"),
         # same widths as wan14b with 2 of the 40 blocks: fast to initialise, used for the ncu launch list (per-block kernel shares are identical)
         "wan14b_2l": dict(family="wan", cfg=dict(synth.WAN_14B, num_layers=2, block_idx_with_mot_ref=[0, 1]), latent=(13, 60, 104),
                           name="Wan2.1-I2V-14B VAP widths, 2 MoT blocks, 49f 480x832 (profiling only)"),
@@ -362,8 +368,10 @@ def main():
         roof = None
         if attn_events:
             times = [e0.elapsed_time(e1) for e0, e1, _ in attn_events]
-            B_, H_, J_, D_ = attn_events[0][2]
-            fl = 4.0 * B_ * H_ * J_ * J_ * D_
+            # per-launch algorithmic FLOPs from each launch's own shape (configs with plain blocks mix J = S + Sr and J = S launches)
+            fls = [4.0 * sh[0] * sh[1] * sh[2] * sh[2] * sh[3] for _, _, sh in attn_events]
+            B_, H_, J_, D_ = max((tuple(sh) for _, _, sh in attn_events), key=lambda sh: sh[2])
+            fl = sum(fls) / len(fls)
             avg = sum(times) / len(times)
             traffic, traffic_src = None, None
             try:  # DRAM bytes of this launch from the committed ncu --set full capture of the same shape (profiles/)
