@@ -673,6 +673,24 @@ def check_wan_denoise_cached():
     return dict(cosine=cos, bit_exact=True, batch_cfg_bit_exact=bool(torch.equal(lat_b2, outs[0])), batch_cfg_err=err_b2, batch_cfg_cosine=cos_b2)
 
 
+def check_wan_dead_ref_skip(tol=5e-3):
+    """WanTransformer3DMOTModel.skip_dead_reference_work: the last MoT block drops the expert stream's query rows, O-projection,
+    cross-attention and FFN.  Same model output up to the attention kernel's warp-level rescale vote in the one 256-row block that used to
+    hold both target and reference rows (the target rows' arithmetic is otherwise identical), and still within the gate of the reference."""
+    g = _golden("wan_tiny.pt")
+    cfg = g["cfg"]
+    model = build_wan(cfg, g["weight_seed"])
+    inp = _to_dev(synth.wan_inputs(cfg, *g["latent"], seed=g["input_seed"]))
+    with torch.no_grad():
+        full = model(**inp, return_dict=False)[0]
+        model.skip_dead_reference_work = True
+        lean = model(**inp, return_dict=False)[0]
+        model.skip_dead_reference_work = False
+    err, err_ref = rel_err(lean, full), rel_err(lean, g["final"])
+    assert err <= tol and err_ref <= 2e-2, f"dead-work skip: rel err vs the full path {err}, vs the reference {err_ref}"
+    return dict(err=err, err_ref=err_ref, bit_exact=bool(torch.equal(lean, full)))
+
+
 CHECKS = {
     "probe_ss": lambda: check_probe(False, False, 128, 128),
     "probe_ss_n256": lambda: check_probe(False, False, 256, 64),
@@ -738,4 +756,5 @@ CHECKS_PENDING = {
     "cfg_flow_match_step": check_cfg_flow_match_step,
     "wan_denoise_fused": check_wan_denoise_fused,
     "wan_denoise_cached": check_wan_denoise_cached,
+    "wan_dead_ref_skip": check_wan_dead_ref_skip,
 }

@@ -56,6 +56,19 @@ def _worker(q):
     counts.clear()
     vap.denoise.wan_denoise(model, lat0.clone(), cond, lat_ref, cond_ref, kw, kw_u, 3, 3.0, 5.0, cache_context=False)
     res["sequential_launches"] = sum(counts.values())
+    # dead reference-stream work in the last MoT block: skipping it must not change the model output
+    with torch.no_grad():
+        full = model(**inp, return_dict=False)[0]
+        counts.clear()
+        model(**inp, return_dict=False)
+        n_full = sum(counts.values())
+        model.skip_dead_reference_work = True
+        counts.clear()
+        lean = model(**inp, return_dict=False)[0]
+        n_lean = sum(counts.values())
+        model.skip_dead_reference_work = False
+    res["dead_skip_exact"] = bool(torch.equal(full, lean))
+    res["dead_skip_linears"] = (n_full, n_lean)
     res["left_over_entries"] = sum(1 for m in model.modules() if "_vap_ctx_cache" in m.__dict__)
     # the cache keys on tensor identity AND version: an in-place edit of the conditioning must miss
     with vap.wan.context_cache():
@@ -84,3 +97,5 @@ def test_context_cache_is_bit_exact_and_skips_the_constant_projections():
     assert res["left_over_entries"] == 0 and res["version_miss"], res
     assert res["batch_cfg_exact_cache_0"] and res["batch_cfg_exact_cache_1"], res
     assert res["batch_cfg_launches_cache_0"] < res["sequential_launches"], res
+    # the expert stream of the last MoT block loses its O-projection, 4 cross-attention projections and 2 FFN GEMMs
+    assert res["dead_skip_exact"] and res["dead_skip_linears"][0] - res["dead_skip_linears"][1] == 7, res

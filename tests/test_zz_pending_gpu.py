@@ -18,7 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(400)]
 
 
-HOST_LOGIC_ONLY = ["wan_denoise_cached"]
+HOST_LOGIC_ONLY = ["wan_denoise_cached", "wan_dead_ref_skip"]
 assert set(HOST_LOGIC_ONLY) <= set(gpu_checks.CHECKS_PENDING)
 
 

@@ -3,7 +3,7 @@
 # failure so that a faulting kernel is launched once, not five times.  `nvidia-smi` Xid lines are printed after each stage.
 set -x
 xid() { dmesg 2>/dev/null | grep -i xid | tail -3; nvidia-smi --query-gpu=name,clocks.sm --format=csv,noheader; }
-python tools/gpu_diag.py --pending --only wan_denoise_cached,cfg_flow_match_step,wan_denoise_fused; xid
+python tools/gpu_diag.py --pending --only wan_denoise_cached,wan_dead_ref_skip,cfg_flow_match_step,wan_denoise_fused; xid
 for c in attn_bwd_one_tile attn_bwd_d128 attn_bwd_d64 attn_bwd_tails attn_bwd_multi_tile; do
   python tools/gpu_diag.py --pending --only $c || { echo "STOP at $c"; cat gpurun_out/diag_$c.log | tail -20; xid; exit 1; }
   xid

@@ -310,6 +310,15 @@ def wan_block_forward(self: nn.Module, hidden_states: torch.Tensor, encoder_hidd
     else:
         _self_attn_qkv(attn1, xn, tables, out=qkv[:, :S])
         _self_attn_qkv(attn1_r, xn_r, tables_r, out=qkv[:, S:])
+        if self.__dict__.get("_vap_ref_output_unused", False) and ulysses.current() is None:
+            # Last MoT block of a shell whose output head reads the target stream only (:951-987): the expert stream's output is dead,
+            # so its query rows, O-projection, cross-attention and FFN are skipped; its K / V still feed the target's attention.
+            # Opt-in (WanTransformer3DMOTModel.skip_dead_reference_work): the returned reference stream is then the block's INPUT.
+            q, k, v = _split_qkv(qkv, heads)
+            o = _token_major(ops.attention(q[:, :, :S], k, v))
+            x = _linear(attn1.to_out[0], o, epilogue=ops.EPI_GATE_RES_F32, residual=x, gate=gate)
+            x = _stream_tail(self, "", x, encoder_hidden_states, c_shift, c_scale1p, c_gate, eps, 1)
+            return x, hidden_states_mot_ref
         o = _joint_attention(qkv, heads)  # [B, J, inner], rows [target | ref]
     x = _linear(attn1.to_out[0], o[:, :S], epilogue=ops.EPI_GATE_RES_F32, residual=x, gate=gate)
     xr = _linear(attn1_r.to_out[0], o[:, S:], epilogue=ops.EPI_GATE_RES_F32, residual=xr, gate=gate_r)
@@ -483,6 +492,10 @@ class WanTransformer3DMOTModel(nn.Module):
                                 with_mot_ref=i in block_idx_with_mot_ref, _block_idx=i) for i in range(num_layers)])
         self.norm_out = FP32LayerNorm(inner, eps, elementwise_affine=False)
         self.proj_out = nn.Linear(inner, out_channels * math.prod(patch_size))
+        # SURVEY §7 "dead work in the reference": after the last MoT block nothing reads the expert stream.  True skips that block's
+        # expert-side query rows / O-projection / cross-attention / FFN (same model output, ~1 % less work at 40/40 MoT blocks).
+        # Off by default: the benchmark step and the per-block parity checks run the reference's full arithmetic.
+        self.skip_dead_reference_work = False
         self.scale_shift_table = nn.Parameter(torch.randn(1, 2, inner) / inner ** 0.5)
 
     def forward(self, hidden_states: torch.Tensor, timestep: torch.Tensor, encoder_hidden_states: torch.Tensor,
@@ -513,7 +526,9 @@ class WanTransformer3DMOTModel(nn.Module):
                                                                 encoder_hidden_states_image_mot_ref)
         proj_r = proj_r.unflatten(1, (6, -1))
 
-        for block in self.blocks:
+        last_mot = max((i for i, b in enumerate(self.blocks) if b.with_mot_ref), default=-1)
+        for i, block in enumerate(self.blocks):
+            block.__dict__["_vap_ref_output_unused"] = bool(self.skip_dead_reference_work) and i == last_mot
             x, xr = block(hidden_states=x, encoder_hidden_states=ctx, temb=proj, rotary_emb=rope, hidden_states_mot_ref=xr,
                           encoder_hidden_states_mot_ref=ctx_r, temb_mot_ref=proj_r, rotary_emb_mot_ref=rope_r, num_mot_ref=num_mot_ref)
 
