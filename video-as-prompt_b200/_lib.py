@@ -6,11 +6,11 @@ fallback: if the shared library is missing or a call fails, a ``VapError`` is ra
 from __future__ import annotations
 
 import ctypes
+import os as _os
 from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
-import os as _os
 # VAP_B200_LIB: developer override used by tools/attn_variants.sh to A/B kernel builds; the product path is the in-tree library
 LIB_PATH = Path(_os.environ["VAP_B200_LIB"]) if _os.environ.get("VAP_B200_LIB") else _PKG / "libvap_b200.so"
 

@@ -5,6 +5,8 @@ on ``torch.cuda.current_stream()``.  Nothing here computes on the CPU; a CPU ten
 """
 from __future__ import annotations
 
+import ctypes
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -194,7 +196,6 @@ def attention_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, o: torch.Te
     if B * H * Lq * Lkv == 0:
         return dq.zero_(), dk.zero_(), dv.zero_()
     delta = torch.empty((B, H, Lq), dtype=torch.float32, device=q.device)
-    import ctypes
     strides = (ctypes.c_int64 * 24)(*[st for t in (q, k, v, o, dout, dq, dk, dv) for st in t.stride()[:3]])
     rc = _lib.load().vap_attention_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), dout.data_ptr(), lse_ptr, dq.data_ptr(), dk.data_ptr(),
                                        dv.data_ptr(), delta.data_ptr(), B, H, Lq, Lkv, D, strides, float(scale), _stream())
@@ -208,7 +209,6 @@ _SPLIT_CACHE = {}
 def _auto_kv_splits(B: int, H: int, Lq: int, Lkv: int) -> int:
     """Split count `attention` / `attention_scatter` use by themselves: VAP_ATTN_SPLITKV = "auto" (default: the wave model of
     attention_kv_splits), "0" / "1" (never split) or a number in [2, 8] (always split, for testing)."""
-    import os
     key = (B, H, Lq, Lkv)
     s = _SPLIT_CACHE.get(key)
     if s is None:
@@ -284,7 +284,6 @@ def attention_splitkv(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, kv_spli
 
 def _ptr_table(ptrs):
     """Host array of device pointers (void* const*) for the peer-table entry points."""
-    import ctypes
     arr = (ctypes.c_void_p * len(ptrs))(*[int(p) for p in ptrs])
     return arr
 
