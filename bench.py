@@ -405,6 +405,13 @@ def main():
         torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+        if use_graph:
+            # NCCL work captured into a CUDA graph kept the ranks from exiting cleanly on 2 GPUs (graphs.py, status note): the line is
+            # printed and every rank has passed the barrier, so leave without the communicator teardown instead of hanging torchrun
+            torch.cuda.synchronize()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
         dist.destroy_process_group()
 
 
