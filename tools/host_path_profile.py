@@ -1,6 +1,6 @@
 """Host-side launch-path profiler (runs WITHOUT a GPU): how long does Python take to issue one forward's launches?
 
-At 8 GPUs the 480p step is bound by the Python / ctypes launch path.  This tool swaps libvap_b200.so for a stub whose
+At 8 GPUs the 480p step did not get faster with faster kernels: how much of it is the Python / ctypes launch path?  This tool swaps libvap_b200.so for a stub whose
 entry points have the same names and return 0 at once (built here with gcc from the SIGNATURES table), lets CPU bf16 tensors through
 the ops' device checks, and runs the stand-alone Wan / CogVideoX shell at small shapes — so that what remains is exactly the host
 work per launch: argument validation, torch.empty, view arithmetic, ctypes marshalling, and the torch glue ops.
@@ -22,7 +22,6 @@ import os
 import pstats
 import subprocess
 import sys
-import tempfile
 import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -37,11 +36,13 @@ def build_stub(sigs) -> ctypes.CDLL:
     src = "\n".join(f"int {name}() {{ return {300 if name == 'vap_version' else (148 if name == 'vap_sm_count' else 0)}; }}"
                     for name in sigs if name != "vap_last_error")
     src += '\nconst char* vap_last_error() { return "stub"; }\n'
-    d = tempfile.mkdtemp(prefix="vap_stub_")
-    c, so = os.path.join(d, "stub.c"), os.path.join(d, "libvap_stub.so")
+    d = os.path.join(ROOT, "video-as-prompt_b200", "csrc", "build", "stub")  # git-ignored build directory
+    os.makedirs(d, exist_ok=True)
+    c, so = os.path.join(d, "stub.c"), os.path.join(d, f"libvap_stub_{os.getpid()}.so")
     open(c, "w").write(src)
     subprocess.run(["gcc", "-shared", "-fPIC", "-O1", "-w", "-o", so, c], check=True)
     lib = ctypes.CDLL(so)
+    os.unlink(so)  # the mapping stays valid; nothing is left behind
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args
