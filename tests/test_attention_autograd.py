@@ -34,6 +34,19 @@ def _worker(q_out):
         ref_grads = torch.autograd.grad(ref_o, ref_in, go.float())
         res[name] = [((a.float() - b).abs().max() / b.abs().max()).item() for a, b in zip(grads, ref_grads)]
         res[name + "_fwd"] = ((o.float() - ref_o).abs().max() / ref_o.abs().max()).item()
+    # an expanded gradient (o.sum().backward()) must be materialised before it reaches the kernel wrapper
+    leaves = [t.detach().clone().requires_grad_(True) for t in qkv]
+    seen = {}
+    real_bwd = vap.ops.attention_bwd
+
+    def spy(q, k, v, o, lse, dout, **kw):
+        seen["strides"] = dout.stride()
+        return real_bwd(q, k, v, o, lse, dout, **kw)
+
+    vap.ops.attention_bwd = spy
+    vap.joint_sdpa(*leaves, scale=0.2).sum().backward()
+    vap.ops.attention_bwd = real_bwd
+    res["expanded_grad_strides"] = list(seen["strides"])
     # no grad needed -> plain forward, no graph
     with torch.no_grad():
         res["nograd_has_fn"] = vap.joint_sdpa(*[t.detach() for t in qkv]).grad_fn is not None
@@ -51,6 +64,7 @@ def test_joint_sdpa_is_differentiable_and_matches_torch_autograd():
         assert res[name + "_fwd"] < 1e-2, res
         assert all(e < 2e-2 for e in res[name]), res  # bf16 operands (P, dS) and bf16 outputs against fp32 autograd
     assert res["nograd_has_fn"] is False
+    assert res["expanded_grad_strides"][-1] == 1 and all(st > 0 for st in res["expanded_grad_strides"]), res
 
 
 def test_c_abi_rejects_bad_backward_arguments_without_a_gpu():

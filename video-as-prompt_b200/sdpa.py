@@ -28,7 +28,9 @@ class _JointAttention(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         q, k, v, o, lse = ctx.saved_tensors
-        if dout.stride(-1) != 1:
+        # autograd may hand over an expanded (stride 0) or oddly strided gradient, e.g. after o.sum(): the kernel wants D contiguous and
+        # (batch, head, token) strides that are positive multiples of 8 elements
+        if dout.stride(-1) != 1 or any(n > 1 and (st <= 0 or st % 8) for n, st in zip(dout.shape[:3], dout.stride()[:3])) or dout.data_ptr() % 16:
             dout = dout.contiguous()
         dq, dk, dv = ops.attention_bwd(q, k, v, o, lse, dout, scale=ctx.scale)
         return dq, dk, dv, None
