@@ -72,3 +72,62 @@ def test_install_on_the_reference_model_matches_the_reference(family):
     assert "error" not in res, res.get("error")
     assert res["block"] < 2e-2 and res["processor"] < 2e-2, res
     assert res["block_restored"] and res["processor_restored"] and res["keys_unchanged"], res
+
+
+def _train_worker(q):
+    """The trainer's contract at the SDPA seam (finetrainers/trainer/sft_trainer/trainer.py:154-164, 674-714): only parameters with
+    "_mot_ref" in their name train; the loss back-propagates through the reference's own block code and OUR attention."""
+    try:
+        sys.path.insert(0, ROOT)
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        sys.path.insert(0, os.path.join(REF, "diffusers", "src"))
+        sys.dont_write_bytecode = True
+        torch.set_num_threads(4)
+        vap = importlib.import_module("video-as-prompt_b200")
+        import cpu_standin_ops
+        cpu_standin_ops.install(vap)
+        from diffusers import WanTransformer3DMOTModel as RefModel
+        cfg = dict(vap.synth.WAN_TINY, num_layers=2, block_idx_with_mot_ref=[0, 1])
+        inp = vap.synth.wan_inputs(cfg, 2, 8, 8, seed=0)
+        model = RefModel(**cfg).to(torch.bfloat16).train()
+        vap.synth.fill_module_(model, seed=7, num_layers=cfg["num_layers"])
+        for name, prm in model.named_parameters():
+            prm.requires_grad_("_mot_ref" in name)
+        target = torch.randn(model(**inp, return_dict=False)[0].shape, generator=torch.Generator().manual_seed(1))
+
+        def grads():
+            model.zero_grad(set_to_none=True)
+            out = model(**inp, return_dict=False)[0].float()
+            torch.nn.functional.mse_loss(out, target).backward()
+            return {n: p.grad.float().clone() for n, p in model.named_parameters() if p.grad is not None}
+
+        ref = grads()
+        vap.install(model, level="sdpa")
+        got = grads()
+        vap.uninstall(model)
+        res = {"n_ref": len(ref), "n_got": len(got), "same_names": sorted(ref) == sorted(got)}
+        # cosine per parameter (bf16 training noise makes max-abs a poor gate for gradients), worst case over all trainable tensors
+        cos = {}
+        for n in ref:
+            a, b = ref[n].double().flatten(), got[n].double().flatten()
+            if a.norm() > 0:
+                cos[n] = (torch.dot(a, b) / (a.norm() * b.norm())).item()
+        res["worst_cosine"] = min(cos.values())
+        res["worst_name"] = min(cos, key=cos.get)
+        res["attn_grads_present"] = any("attn1_mot_ref.to_q" in n for n in got)
+        q.put(res)
+    except Exception:  # noqa: BLE001
+        import traceback
+        q.put({"error": traceback.format_exc()[-3000:]})
+
+
+def test_sdpa_seam_trains_the_reference_model():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    p = ctx.Process(target=_train_worker, args=(q,))
+    p.start()
+    res = q.get(timeout=600)
+    p.join(60)
+    assert "error" not in res, res.get("error")
+    assert res["same_names"] and res["n_got"] > 0 and res["attn_grads_present"], res
+    assert res["worst_cosine"] > 0.99, res
