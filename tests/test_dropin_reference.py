@@ -74,7 +74,7 @@ def test_install_on_the_reference_model_matches_the_reference(family):
     assert res["block_restored"] and res["processor_restored"] and res["keys_unchanged"], res
 
 
-def _train_worker(q):
+def _train_worker(family, q):
     """The trainer's contract at the SDPA seam (finetrainers/trainer/sft_trainer/trainer.py:154-164, 674-714): only parameters with
     "_mot_ref" in their name train; the loss back-propagates through the reference's own block code and OUR attention."""
     try:
@@ -86,9 +86,14 @@ def _train_worker(q):
         vap = importlib.import_module("video-as-prompt_b200")
         import cpu_standin_ops
         cpu_standin_ops.install(vap)
-        from diffusers import WanTransformer3DMOTModel as RefModel
-        cfg = dict(vap.synth.WAN_TINY, num_layers=2, block_idx_with_mot_ref=[0, 1])
-        inp = vap.synth.wan_inputs(cfg, 2, 8, 8, seed=0)
+        if family == "wan":
+            from diffusers import WanTransformer3DMOTModel as RefModel
+            cfg = dict(vap.synth.WAN_TINY, num_layers=2, block_idx_with_mot_ref=[0, 1])
+            inp = vap.synth.wan_inputs(cfg, 2, 8, 8, seed=0)
+        else:
+            from diffusers import CogVideoXTransformer3DMOTModel as RefModel
+            cfg = dict(vap.synth.COG_TINY, num_layers=2, block_idx_with_mot_ref=[0, 1])
+            inp = vap.synth.cog_inputs(cfg, 2, 8, 12, seed=0)
         model = RefModel(**cfg).to(torch.bfloat16).train()
         vap.synth.fill_module_(model, seed=7, num_layers=cfg["num_layers"])
         for name, prm in model.named_parameters():
@@ -121,10 +126,11 @@ def _train_worker(q):
         q.put({"error": traceback.format_exc()[-3000:]})
 
 
-def test_sdpa_seam_trains_the_reference_model():
+@pytest.mark.parametrize("family", ["wan", "cog"])
+def test_sdpa_seam_trains_the_reference_model(family):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    p = ctx.Process(target=_train_worker, args=(q,))
+    p = ctx.Process(target=_train_worker, args=(family, q))
     p.start()
     res = q.get(timeout=600)
     p.join(60)
