@@ -300,3 +300,18 @@ def test_cfg_flow_match_step_contract_equals_the_reference_expression():
         vap.ops.cfg_flow_match_step(c, u, torch.zeros(2, 4096), guidance_scale=5.0, dt=-0.1)
     lib = vap._lib.load()
     assert lib.vap_cfg_flow_match_step(16, 0, 16, 1, 16, 1, 12, 16, 5.0, -0.1, 0) == -1 and b"multiple of 8" in lib.vap_last_error()
+
+
+def test_bench_flop_accounting_matches_the_survey():
+    """bench.py's algorithmic-FLOP model (roofline numerators, model_tflops) reproduces SURVEY.md §8's figures for the three expert placements
+    of Wan2.1-14B at 49f 480x832 (2.349e15 / 1.594e15 / 1.216e15 per forward, 3.369e13 per joint attention) and for 81f 720p (2.244e16, 4.682e14)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    w = bench.workloads(vap.synth)
+    want = {"wan14b": (2.349e15, 3.369e13), "wan14b_d20": (1.594e15, 3.369e13), "wan14b_d10": (1.216e15, 3.369e13), "wan14b_720p": (2.244e16, 4.682e14)}
+    for name, (total, attn) in want.items():
+        f, h, wd = w[name]["latent"]
+        S = f * (h // 2) * (wd // 2)
+        got_total, got_attn = bench.wan_flops(w[name]["cfg"], S, S)
+        assert abs(got_total / total - 1) < 1e-3 and abs(got_attn / attn - 1) < 1e-3, (name, got_total, got_attn)
+    assert [i for i in w["wan14b_d20"]["cfg"]["block_idx_with_mot_ref"]] == list(range(0, 40, 2))
