@@ -19,14 +19,18 @@
 // elementwise pass are serialised (one tile pair in flight); overlap (ping-pong as in the forward) is the next step.
 //
 // Warps: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4-7 elementwise + epilogue (thread t <-> TMEM lane t <-> tile row t).
+// kSplit = 2 (VAP_ATTN_BWD_SPLIT=2, experimental): a second set of four elementwise warps (8-11) takes the upper 64 streamed columns;
+// each set packs its bf16 results over ITS OWN already-consumed fp32 columns (set s: columns [64 s, 64 s + 32)), so the sets never touch
+// each other's data and the TMEM-operand address of K-step k becomes 64 (k / 4) + 8 (k % 4) instead of 8 k.
 // TMEM: [0,128) S / S^T (P^T written over it as packed bf16), [128,256) dP / dP^T (dS / dS^T over it), [256, 256+D) first
 // accumulator (dQ or dV), [256+D, 256+2D) second accumulator (dK).
+#include <cstdlib>
 #include "vap_kernels.cuh"
 
 namespace vap {
 
-constexpr int kBwdThreads = 256;
 constexpr int kBwdTile = 128;
+constexpr int bwd_threads(int split) { return 128 + 128 * split; }
 constexpr float kLog2e = 1.4426950408889634f;
 
 template <int D>
@@ -53,8 +57,8 @@ struct BwdParams {
 };
 
 // tmOwnA / tmOwnB: the CTA's resident tiles (Q_i, dO_i) or (K_j, V_j); tmStrA / tmStrB: the streamed tiles (K_j, V_j) or (Q_i, dO_i).
-template <int D, bool kDKV>
-__global__ void __launch_bounds__(kBwdThreads, 1)
+template <int D, bool kDKV, int kSplit>
+__global__ void __launch_bounds__(bwd_threads(kSplit), 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmOwnA, const __grid_constant__ CUtensorMap tmOwnB,
                 const __grid_constant__ CUtensorMap tmStrA, const __grid_constant__ CUtensorMap tmStrB, const BwdParams p) {
     using Cfg = BwdCfg<D>;
@@ -94,7 +98,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmOwnA, const __grid_constan
         }
         mbar_init(own_full, 1);
         mbar_init(sdp_full, 1);
-        mbar_init(ds_full, 128);  // one arrive per elementwise thread
+        mbar_init(ds_full, 128 * kSplit);  // one arrive per elementwise thread
         mbar_init(acc_done, 1);
         fence_mbar_init();
     }
@@ -152,8 +156,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmOwnA, const __grid_constan
         };
         auto issue_ts = [&](uint32_t col_acc, uint32_t col_a, uint32_t b_addr, uint32_t accumulate) {
 #pragma unroll
-            for (int k = 0; k < kBwdTile / 16; ++k)  // A: packed bf16 pairs, 8 TMEM columns per 16 streamed rows; B rows [16k, 16k+16) are 2048 B apart
-                umma_ts(col_acc, col_a + 8 * k, make_smem_desc(b_addr + k * 2048, Cfg::kHalfBytes, 1024, kLayoutSw128), idesc_ts, k != 0 ? 1u : accumulate);
+            for (int k = 0; k < kBwdTile / 16; ++k) {  // A: packed bf16 pairs, 8 TMEM columns per 16 streamed rows; B rows [16k, 16k+16) are 2048 B apart
+                constexpr int kStepsPerSet = (kBwdTile / 16) / kSplit;  // elementwise set s packed its columns at [128 / kSplit * s, ...)
+                const uint32_t a_col = col_a + (kBwdTile / kSplit) * (k / kStepsPerSet) + 8 * (k % kStepsPerSet);
+                umma_ts(col_acc, a_col, make_smem_desc(b_addr + k * 2048, Cfg::kHalfBytes, 1024, kLayoutSw128), idesc_ts, k != 0 ? 1u : accumulate);
+            }
         };
         int stage = 0;
         uint32_t phase = 0;
@@ -190,6 +197,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmOwnA, const __grid_constan
     } else if (warp >= 4) {
         // ===== elementwise + epilogue: thread t <-> TMEM lane t <-> row own0 + t of the resident tile =====
         const int q4 = warp & 3;
+        const int set = (warp - 4) >> 2;                  // which quarter / half of the streamed columns this warp handles
+        constexpr int kColsPerSet = kBwdTile / kSplit;
+        const int col_base = set * kColsPerSet;
         const int t = q4 * 32 + lane;
         const uint32_t lane_addr = static_cast<uint32_t>(q4 * 32) << 16;
         const uint32_t s_col = tmem_base + lane_addr + Cfg::kColS;
@@ -206,35 +216,38 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmOwnA, const __grid_constan
         for (int it = 0; it < n_it; ++it) {
             const uint32_t stat = stat_smem + (it & 1) * (2 * 128 * 4);
             if (kDKV) {  // statistics of the streamed q rows: thread t fetches row t's, everybody reads all 128 (rows past Lq: 0, 0)
-                const int qrow = it * kBwdTile + t;
-                const bool ok = qrow < p.Lq;
-                st_shared_f32(stat + 4u * t, ok ? p.lse[stat_base + qrow] * kLog2e : 0.f);
-                st_shared_f32(stat + 512u + 4u * t, ok ? p.delta[stat_base + qrow] : 0.f);
-                named_bar_sync(1, 128);
+                if (set == 0) {
+                    const int qrow = it * kBwdTile + t;
+                    const bool ok = qrow < p.Lq;
+                    st_shared_f32(stat + 4u * t, ok ? p.lse[stat_base + qrow] * kLog2e : 0.f);
+                    st_shared_f32(stat + 512u + 4u * t, ok ? p.delta[stat_base + qrow] : 0.f);
+                }
+                named_bar_sync(1, 128 * kSplit);
             }
             mbar_wait(sdp_full, it & 1);
             tc_fence_after();
             const int valid = str_len - it * kBwdTile;  // streamed rows (TMEM columns) inside the sequence
 #pragma unroll 1
-            for (int ch = 0; ch < 4; ++ch) {
+            for (int ch = 0; ch < 4 / kSplit; ++ch) {
+                const int c0 = col_base + 32 * ch;  // first of this chunk's 32 fp32 columns
                 uint32_t sr[32], dr[32];
-                tmem_ld_x32(s_col + 32 * ch, sr);
-                tmem_ld_x32(dp_col + 32 * ch, dr);
+                tmem_ld_x32(s_col + c0, sr);
+                tmem_ld_x32(dp_col + c0, dr);
                 tmem_ld_wait();
                 uint32_t pk_p[16], pk_ds[16];
 #pragma unroll
                 for (int e4 = 0; e4 < 8; ++e4) {  // four columns per step
                     float lse2[4] = {row_lse2, row_lse2, row_lse2, row_lse2}, delta[4] = {row_delta, row_delta, row_delta, row_delta};
                     if (kDKV) {  // per-column statistics of the streamed q rows: every lane reads the same 16 bytes (broadcast)
-                        const float4 l4 = ld_shared_v4_f32(stat + 4u * (32 * ch + 4 * e4));
-                        const float4 d4 = ld_shared_v4_f32(stat + 512u + 4u * (32 * ch + 4 * e4));
+                        const float4 l4 = ld_shared_v4_f32(stat + 4u * (c0 + 4 * e4));
+                        const float4 d4 = ld_shared_v4_f32(stat + 512u + 4u * (c0 + 4 * e4));
                         lse2[0] = l4.x, lse2[1] = l4.y, lse2[2] = l4.z, lse2[3] = l4.w;
                         delta[0] = d4.x, delta[1] = d4.y, delta[2] = d4.z, delta[3] = d4.w;
                     }
                     float pv[4], dsv[4];
 #pragma unroll
                     for (int h = 0; h < 4; ++h) {
-                        const int col = 32 * ch + 4 * e4 + h;
+                        const int col = c0 + 4 * e4 + h;
                         float pe = ex2_approx(fmaf(__uint_as_float(sr[4 * e4 + h]), c, -lse2[h]));
                         // outside the sequences: streamed rows past the end (zero-filled by TMA: S = 0 would give p = exp(-lse)) and rows
                         // of the resident tile past its end contribute nothing
@@ -245,10 +258,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmOwnA, const __grid_constan
                     pk_p[2 * e4] = pack_bf16x2(pv[0], pv[1]), pk_p[2 * e4 + 1] = pack_bf16x2(pv[2], pv[3]);
                     pk_ds[2 * e4] = pack_bf16x2(dsv[0], dsv[1]), pk_ds[2 * e4 + 1] = pack_bf16x2(dsv[2], dsv[3]);
                 }
-                // packed bf16 over the fp32 columns this thread has already consumed: chunk ch read columns [32 ch, 32 ch + 32) and
-                // writes [16 ch, 16 ch + 16)
-                if (kDKV) tmem_st_x16(s_col + 16 * ch, pk_p);
-                tmem_st_x16(dp_col + 16 * ch, pk_ds);
+                // packed bf16 over the fp32 columns this thread has already consumed: chunk ch read columns [base + 32 ch, base + 32 ch + 32)
+                // and writes [base + 16 ch, base + 16 ch + 16)
+                if (kDKV) tmem_st_x16(s_col + col_base + 16 * ch, pk_p);
+                tmem_st_x16(dp_col + col_base + 16 * ch, pk_ds);
             }
             tmem_st_wait();
             tc_fence_before();
@@ -265,6 +278,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmOwnA, const __grid_constan
             const uint32_t acc_col = tmem_base + lane_addr + (a == 0 ? Cfg::kColAcc0 : Cfg::kColAcc1);
 #pragma unroll 1
             for (int c0 = 0; c0 < D; c0 += 32) {
+                if (((a * (D / 32) + c0 / 32) % kSplit) != set) continue;  // the sets share the epilogue's 32-column chunks
                 uint32_t ov[32];
                 tmem_ld_x32(acc_col + c0, ov);
                 tmem_ld_wait();
@@ -332,15 +346,24 @@ static int make_bwd_tmap(CUtensorMap* tm, const AttnTensor& t, int B, int H, int
     return make_tmap_bf16(tm, t.ptr, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-template <int D>
+static int bwd_split_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("VAP_ATTN_BWD_SPLIT");
+        mode = (e && atoi(e) == 2) ? 2 : 1;
+    }
+    return mode;
+}
+
+template <int D, int kSplit>
 static int launch_bwd_d(const AttnBwdArgs& a, cudaStream_t stream) {
     using Cfg = BwdCfg<D>;
     static_assert(Cfg::kSmemBytes <= 232448, "shared memory budget");
     static_assert(8 * (2 * Cfg::kStages + 5) <= Cfg::kBarBytes, "barrier area");
     static bool attr_set = false;
     if (!attr_set) {
-        VAP_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-        VAP_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        VAP_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<D, false, kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        VAP_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<D, true, kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         attr_set = true;
     }
     // 1. delta = rowsum(dO o O)
@@ -364,7 +387,7 @@ static int launch_bwd_d(const AttnBwdArgs& a, cudaStream_t stream) {
     p.out0 = a.dq.ptr, p.out0_sb = a.dq.sb, p.out0_sh = a.dq.sh, p.out0_sl = a.dq.sl;
     {
         const dim3 grid((a.Lq + kBwdTile - 1) / kBwdTile, a.H, a.B);
-        attn_bwd_kernel<D, false><<<grid, kBwdThreads, Cfg::kSmemBytes, stream>>>(tmQ, tmDO, tmK, tmV, p);
+        attn_bwd_kernel<D, false, kSplit><<<grid, bwd_threads(kSplit), Cfg::kSmemBytes, stream>>>(tmQ, tmDO, tmK, tmV, p);
         VAP_CHECK_CUDA(cudaGetLastError());
     }
     // 3. dV, dK: one CTA per 128 kv rows, streams Q / dO
@@ -372,7 +395,7 @@ static int launch_bwd_d(const AttnBwdArgs& a, cudaStream_t stream) {
     p.out1 = a.dk.ptr, p.out1_sb = a.dk.sb, p.out1_sh = a.dk.sh, p.out1_sl = a.dk.sl;
     {
         const dim3 grid((a.Lkv + kBwdTile - 1) / kBwdTile, a.H, a.B);
-        attn_bwd_kernel<D, true><<<grid, kBwdThreads, Cfg::kSmemBytes, stream>>>(tmK, tmV, tmQ, tmDO, p);
+        attn_bwd_kernel<D, true, kSplit><<<grid, bwd_threads(kSplit), Cfg::kSmemBytes, stream>>>(tmK, tmV, tmQ, tmDO, p);
         VAP_CHECK_CUDA(cudaGetLastError());
     }
     return 0;
@@ -389,7 +412,8 @@ int launch_attention_bwd(const AttnBwdArgs& a, int D, cudaStream_t stream) {
     for (const AttnGrad* g : outs)
         VAP_REQUIRE(g->ptr && (reinterpret_cast<uintptr_t>(g->ptr) & 15) == 0 && g->sl % 8 == 0 && g->sh % 8 == 0 && g->sb % 8 == 0,
                     "attention bwd: gradients must be 16-byte aligned with strides that are multiples of 8 elements");
-    return D == 128 ? launch_bwd_d<128>(a, stream) : launch_bwd_d<64>(a, stream);
+    if (bwd_split_mode() == 2) return D == 128 ? launch_bwd_d<128, 2>(a, stream) : launch_bwd_d<64, 2>(a, stream);
+    return D == 128 ? launch_bwd_d<128, 1>(a, stream) : launch_bwd_d<64, 1>(a, stream);
 }
 
 }  // namespace vap
