@@ -592,6 +592,13 @@ def check_attention_bwd_split2(**kw):
     return check_attention_bwd(**kw)
 
 
+def check_attention_bwd_prefetch(**kw):
+    """dQ kernel with S double-buffered (VAP_ATTN_BWD_PREFETCH=1) and both elementwise sets — own process, like the split-2 check."""
+    os.environ["VAP_ATTN_BWD_PREFETCH"] = "1"
+    os.environ["VAP_ATTN_BWD_SPLIT"] = "2"
+    return check_attention_bwd(**kw)
+
+
 def check_cfg_flow_match_step(B=2, inner=16 * 3 * 16 * 16):
     """vap_cfg_flow_match_step against the reference's own tensor expression evaluated by torch ON THE GPU (integer-exact comparison
     of the bf16 results): pipeline_wan_i2v_mot.py:874 + scheduling_flow_match_euler_discrete.py:433-467.  torch's CUDA kernel keeps
@@ -761,6 +768,8 @@ CHECKS_PENDING = {
     "attn_bwd_tails": lambda: check_attention_bwd(1, 1, 130, 128 * 5 + 7, 128, joint_layout=False),
     "attn_bwd_multi_tile": lambda: check_attention_bwd(1, 2, 1000, 1000, 128),
     "attn_bwd_split2_d128": lambda: check_attention_bwd_split2(B=1, H=2, Lq=300, Lkv=647, D=128, joint_layout=False),
+    "attn_bwd_prefetch_d128": lambda: check_attention_bwd_prefetch(B=1, H=2, Lq=300, Lkv=647, D=128, joint_layout=False),
+    "attn_bwd_prefetch_d64": lambda: check_attention_bwd_prefetch(B=1, H=2, Lq=452, Lkv=260, D=64, joint_layout=False),
     "attn_bwd_split2_d64": lambda: check_attention_bwd_split2(B=2, H=3, Lq=452, Lkv=260, D=64, joint_layout=False),
     "cfg_flow_match_step": check_cfg_flow_match_step,
     "wan_denoise_fused": check_wan_denoise_fused,

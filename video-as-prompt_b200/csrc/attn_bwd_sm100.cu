@@ -54,6 +54,7 @@ struct BwdParams {
     __nv_bfloat16* out1;  // dK (dKV kernel)
     int64_t out1_sb, out1_sh, out1_sl;
     float scale, scale_log2;
+    int prefetch_s;  // dQ kernel only (VAP_ATTN_BWD_PREFETCH=1, experimental): S double-buffered in the TMEM columns the dK accumulator would use
 };
 
 // tmOwnA / tmOwnB: the CTA's resident tiles (Q_i, dO_i) or (K_j, V_j); tmStrA / tmStrB: the streamed tiles (K_j, V_j) or (Q_i, dO_i).
@@ -164,17 +165,29 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmOwnA, const __grid_constan
         };
         int stage = 0;
         uint32_t phase = 0;
+        // dQ kernel with prefetch: S(it + 1) = Q K_{it+1}^T is issued right after dP(it), into the other S buffer, so that it runs on the
+        // tensor pipe while the threads work on step it (dP cannot follow: its columns hold dS(it) until dQ += dS K has read them)
+        const bool pre = !kDKV && p.prefetch_s != 0;
+        auto s_buf = [&](int i) { return col_s + ((pre && (i & 1)) ? 384u : 0u); };
         mbar_wait(own_full, 0);
         for (int it = 0; it < n_it; ++it) {
             mbar_wait(st_full(stage), phase);
             tc_fence_after();
             const uint32_t str_a = str_smem + stage * 2 * Cfg::kTileBytes, str_b = str_a + Cfg::kTileBytes;
             if (elect_one()) {
-                issue_ss(col_s, own_smem, str_a);                       // S = Q K^T      | S^T  = K Q^T
-                issue_ss(col_dp, own_smem + Cfg::kTileBytes, str_b);    // dP = dO V^T    | dP^T = V dO^T
+                if (!pre || it == 0) issue_ss(s_buf(it), own_smem, str_a);  // S = Q K^T      | S^T  = K Q^T
+                issue_ss(col_dp, own_smem + Cfg::kTileBytes, str_b);        // dP = dO V^T    | dP^T = V dO^T
                 umma_commit(sdp_full);
             }
             __syncwarp();
+            if (pre && it + 1 < n_it) {
+                const int nstage = (stage + 1 == Cfg::kStages) ? 0 : stage + 1;
+                const uint32_t nphase = (stage + 1 == Cfg::kStages) ? (phase ^ 1) : phase;
+                mbar_wait(st_full(nstage), nphase);  // K_{it+1} has landed (the loop waits on it again next iteration: already complete)
+                tc_fence_after();
+                if (elect_one()) issue_ss(s_buf(it + 1), own_smem, str_smem + nstage * 2 * Cfg::kTileBytes);
+                __syncwarp();
+            }
             mbar_wait(ds_full, it & 1);
             tc_fence_after();
             if (elect_one()) {
@@ -231,7 +244,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmOwnA, const __grid_constan
             for (int ch = 0; ch < 4 / kSplit; ++ch) {
                 const int c0 = col_base + 32 * ch;  // first of this chunk's 32 fp32 columns
                 uint32_t sr[32], dr[32];
-                tmem_ld_x32(s_col + c0, sr);
+                tmem_ld_x32(s_col + ((!kDKV && p.prefetch_s != 0 && (it & 1)) ? 384u : 0u) + c0, sr);
                 tmem_ld_x32(dp_col + c0, dr);
                 tmem_ld_wait();
                 uint32_t pk_p[16], pk_ds[16];
@@ -346,6 +359,15 @@ static int make_bwd_tmap(CUtensorMap* tm, const AttnTensor& t, int B, int H, int
     return make_tmap_bf16(tm, t.ptr, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
+static int bwd_prefetch_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("VAP_ATTN_BWD_PREFETCH");
+        mode = (e && atoi(e) == 1) ? 1 : 0;
+    }
+    return mode;
+}
+
 static int bwd_split_mode() {
     static int mode = -1;
     if (mode < 0) {
@@ -383,6 +405,7 @@ static int launch_bwd_d(const AttnBwdArgs& a, cudaStream_t stream) {
     p.B = a.B, p.H = a.H, p.Lq = a.Lq, p.Lkv = a.Lkv;
     p.lse = a.lse, p.delta = a.delta;
     p.scale = a.scale, p.scale_log2 = a.scale * kLog2e;
+    p.prefetch_s = bwd_prefetch_mode();
     // 2. dQ: one CTA per 128 q rows, streams K / V
     p.out0 = a.dq.ptr, p.out0_sb = a.dq.sb, p.out0_sh = a.dq.sh, p.out0_sl = a.dq.sl;
     {
