@@ -73,6 +73,18 @@ def test_joint_sdpa_constraints():
         vap.joint_sdpa(q.float(), q.float(), q.float())
     with pytest.raises(ValueError, match="head_dim"):
         vap.joint_sdpa(q[..., :96], q[..., :96], q[..., :96])
+    # non-strict global patch (trainer use): calls outside the envelope reach the ORIGINAL torch SDPA, calls inside never do
+    import torch.nn.functional as F
+    orig = F.scaled_dot_product_attention
+    vap.sdpa.patch_scaled_dot_product_attention(strict=False)
+    try:
+        x = torch.randn(1, 2, 8, 96)
+        assert torch.allclose(F.scaled_dot_product_attention(x, x, x, is_causal=True), orig(x, x, x, is_causal=True))
+        with pytest.raises(vap.VapError, match="no CPU fallback"):
+            F.scaled_dot_product_attention(q, q, q)  # inside the envelope: the kernel or nothing
+    finally:
+        vap.sdpa.unpatch_scaled_dot_product_attention()
+    assert F.scaled_dot_product_attention is orig
 
 
 @pytest.mark.parametrize("family", ["wan", "cog"])

@@ -31,7 +31,9 @@ def _blocks(model: nn.Module):
     raise TypeError(f"{type(model).__name__} has neither `.blocks` (Wan) nor `.transformer_blocks` (CogVideoX)")
 
 
-def install(model: nn.Module, level: str = "block") -> nn.Module:
+def install(model: nn.Module, level: str = "block", strict: bool = True) -> nn.Module:
+    """strict=False (levels "processor" / "sdpa"): SDPA calls outside the kernel's envelope — a VAE's or text encoder's attention under the
+    global patch — fall through to the original torch function instead of raising (sdpa.patch_scaled_dot_product_attention)."""
     family, blocks = _blocks(model)
     if level == "block":
         fwd = wan.wan_block_forward if family == "wan" else cogvideox.cog_block_forward
@@ -48,9 +50,9 @@ def install(model: nn.Module, level: str = "block") -> nn.Module:
                 if proc is not None and type(proc).__name__ in table and hasattr(m, "set_processor"):
                     m.__dict__.setdefault("_vap_original_processor", proc)
                     m.set_processor(table[type(proc).__name__]())
-        sdpa.patch_scaled_dot_product_attention()
+        sdpa.patch_scaled_dot_product_attention(strict)
     elif level == "sdpa":
-        sdpa.patch_scaled_dot_product_attention()
+        sdpa.patch_scaled_dot_product_attention(strict)
     else:
         raise ValueError(f"unknown level {level!r}; expected 'block', 'processor' or 'sdpa'")
     return model
