@@ -148,8 +148,9 @@ int vap_attention_bwd(const void* q, const void* k, const void* v, const void* o
  *     noise_cond / noise_uncond [batch, inner] bf16 contiguous (noise_uncond may be NULL: no guidance); sample [batch, inner] contiguous,
  *     fp32 (sample_is_f32 = 1: the pipeline's initial latents) or bf16 (the later steps); out: batch rows of `inner` bf16 elements,
  *     out_batch_stride apart — e.g. the latent channels of the NEXT step's transformer input [B, 16 + 20, F, h, w], which saves the
- *     reference's torch.cat([latents, condition]) (:815).  dt = sigma_next - sigma as the caller's torch build would apply it
- *     (CUDA: the fp32 value; a CPU run of the reference rounds the 0-dim dt to bf16 first).  inner and out_batch_stride must be
+ *     reference's torch.cat([latents, condition]) (:815).  dt: the value torch multiplies by — the scheduler's dt is a 0-dim fp32 TENSOR,
+ *     which torch casts to the other operand's dtype (bf16) before the multiply, so the caller passes float(bf16(sigma_next - sigma));
+ *     the kernel itself multiplies by whatever fp32 value it is given.  inner and out_batch_stride must be
  *     multiples of 8, all pointers 16-byte aligned. */
 int vap_cfg_flow_match_step(const void* noise_cond, const void* noise_uncond, const void* sample, int sample_is_f32, void* out, int64_t batch,
                             int64_t inner, int64_t out_batch_stride, float guidance_scale, float dt, void* stream);

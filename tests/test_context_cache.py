@@ -56,6 +56,12 @@ def _worker(q):
     counts.clear()
     vap.denoise.wan_denoise(model, lat0.clone(), cond, lat_ref, cond_ref, kw, kw_u, 3, 3.0, 5.0, cache_context=False)
     res["sequential_launches"] = sum(counts.values())
+    # the fused CFG + scheduler step (stand-in of vap_cfg_flow_match_step's contract) reproduces the torch expression loop bit for bit
+    fused = vap.denoise.wan_denoise(model, lat0.clone(), cond, lat_ref, cond_ref, kw, kw_u, 3, 3.0, 5.0, fused_step=True)
+    res["fused_step_exact"] = bool(torch.equal(fused, outs[0]))
+    fused1 = vap.denoise.wan_denoise(model, lat0.clone(), cond, lat_ref, cond_ref, kw, None, 2, 3.0, 5.0, fused_step=True)
+    plain1 = vap.denoise.wan_denoise(model, lat0.clone(), cond, lat_ref, cond_ref, kw, None, 2, 3.0, 5.0)
+    res["fused_step_no_cfg_exact"] = bool(torch.equal(fused1, plain1))
     # dead reference-stream work in the last MoT block: skipping it must not change the model output
     with torch.no_grad():
         full = model(**inp, return_dict=False)[0]
@@ -96,6 +102,7 @@ def test_context_cache_is_bit_exact_and_skips_the_constant_projections():
     assert res["kv_launches_cache_0"] == 60 and res["kv_launches_cache_1"] == 20, res
     assert res["left_over_entries"] == 0 and res["version_miss"], res
     assert res["batch_cfg_exact_cache_0"] and res["batch_cfg_exact_cache_1"], res
+    assert res["fused_step_exact"] and res["fused_step_no_cfg_exact"], res
     assert res["batch_cfg_launches_cache_0"] < res["sequential_launches"], res
     # the expert stream of the last MoT block loses its O-projection, 4 cross-attention projections and 2 FFN GEMMs
     assert res["dead_skip_exact"] and res["dead_skip_linears"][0] - res["dead_skip_linears"][1] == 7, res

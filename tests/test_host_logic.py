@@ -295,8 +295,8 @@ def test_cog_mot_block_launch_sequence(tmp_path):
 def test_cfg_flow_match_step_contract_equals_the_reference_expression():
     """The rounding points vap_cfg_flow_match_step implements (restated by the CPU stand-in) are those of the reference's tensor ops:
     noise_uncond + g * (noise - noise_uncond) in bf16 (pipeline_wan_i2v_mot.py:874), then FlowMatchEulerDiscreteScheduler.step
-    (scheduling_flow_match_euler_discrete.py:433-467).  On the CPU torch rounds the 0-dim fp32 dt to bf16 before the multiply (a CUDA
-    run keeps it in fp32), so the comparison hands the stand-in the bf16-rounded dt."""
+    (scheduling_flow_match_euler_discrete.py:433-467).  torch casts the scheduler's 0-dim fp32 dt to the tensor operand's dtype (bf16)
+    before the multiply, so the kernel's caller hands over the bf16-rounded dt — as this comparison does."""
     import cpu_standin_ops as so
     g = torch.Generator().manual_seed(5)
     c, u = torch.randn(2, 4096, generator=g).bfloat16(), torch.randn(2, 4096, generator=g).bfloat16()

@@ -47,7 +47,9 @@ def wan_denoise(model, latents: torch.Tensor, condition: torch.Tensor, latents_r
     timesteps, sigmas = flow_match_schedule(num_steps, shift, device=dev)
     if fused_step:
         sig_host = flow_match_schedule(num_steps, shift, device="cpu")[1]
-        dts = [float(sig_host[i + 1] - sig_host[i]) for i in range(num_steps)]  # fp32 differences, as the device computes them
+        # dt = sigma_next - sigma is a 0-dim fp32 TENSOR in the scheduler, and torch casts a 0-dim tensor operand to the other operand's
+        # dtype (bf16) before the multiply (TensorIterator's common dtype; only Python / CPU-scalar operands keep fp32): hand the kernel that value
+        dts = [float((sig_host[i + 1] - sig_host[i]).to(torch.bfloat16)) for i in range(num_steps)]
     from . import wan
     x_ref = torch.cat([latents_ref, condition_ref], dim=1).to(dtype)
     ts_ref = torch.ones((1, latents.shape[0]), dtype=torch.float32, device=dev)  # reference video is clean: timestep 1 (:812-813)
