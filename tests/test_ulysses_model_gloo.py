@@ -55,6 +55,12 @@ def _worker(rank, world, port, family, ret):
             sp = vap.ulysses.enable(mode="nccl")  # the collective transport (gloo here); "p2p" needs NVLink peer memory
             assert vap.ulysses.current() is sp
             out = model(**inp, return_dict=False)[0].float()
+            if family == "wan":  # the context cache is rank-local host logic: same sharded forward, bit for bit, hit or miss
+                with vap.wan.context_cache():
+                    c1 = model(**inp, return_dict=False)[0].float()
+                    c2 = model(**inp, return_dict=False)[0].float()
+                vap.wan.clear_context_cache(model)
+                assert torch.equal(c1, out) and torch.equal(c2, out)
             vap.ulysses.disable()
         ret[rank] = ((out - ref).abs().max() / ref.abs().max()).item()
     finally:
