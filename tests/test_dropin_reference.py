@@ -50,6 +50,8 @@ def _worker(family, q):
         res = {}
         for level in ("block", "processor"):
             vap.install(model, level=level)
+            if family == "wan":  # the shell's per-forward CPU RoPE build + H2D copy is replaced by the cached device tables
+                res[level + "_rope_swapped"] = isinstance(model.rope(inp["hidden_states"]), tuple) and isinstance(model.rope_mot_ref(inp["hidden_states_mot_ref"]), tuple)
             out = run()
             vap.uninstall(model)
             res[level] = ((out - ref).abs().max() / ref.abs().max()).item()
@@ -72,6 +74,8 @@ def test_install_on_the_reference_model_matches_the_reference(family):
     assert "error" not in res, res.get("error")
     assert res["block"] < 2e-2 and res["processor"] < 2e-2, res
     assert res["block_restored"] and res["processor_restored"] and res["keys_unchanged"], res
+    if family == "wan":
+        assert res["block_rope_swapped"] and res["processor_rope_swapped"], res
 
 
 def _train_worker(family, q):

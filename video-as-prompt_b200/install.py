@@ -16,7 +16,7 @@ import types
 
 import torch.nn as nn
 
-from . import cogvideox, sdpa, wan
+from . import cogvideox, rope, sdpa, wan
 
 _WAN_PROC = {"WanAttnMOTProcessor2_0": wan.WanAttnMOTProcessor2_0, "WanAttnCrossMOTProcessor2_0": wan.WanAttnCrossMOTProcessor2_0,
              "WanAttnProcessor2_0": wan.WanAttnProcessor2_0}
@@ -31,6 +31,30 @@ def _blocks(model: nn.Module):
     raise TypeError(f"{type(model).__name__} has neither `.blocks` (Wan) nor `.transformer_blocks` (CogVideoX)")
 
 
+def _swap_wan_rope(model: nn.Module) -> None:
+    """The reference's Wan shell rebuilds the RoPE tables on the CPU in float64 and copies them to the device at EVERY forward
+    (WanRotaryPosEmbed.forward / WanRotaryPosEmbedRef.forward, transformer_wan_mot.py:390-409, 429-464: 2 x S x 64 complex128 = 41.6 MB
+    of H2D traffic per forward at 480p).  Our blocks / processors also take compact device tables, so the two rope modules' forwards are
+    rebound to the cached device builder (rope.wan_rope_tables: same positions — target t = 0..F-1, reference t = -F..-1 —, float64 angles)."""
+    for name, is_ref in (("rope", False), ("rope_mot_ref", True)):
+        mod = getattr(model, name, None)
+        if mod is None or not all(hasattr(mod, a) for a in ("attention_head_dim", "patch_size", "max_seq_len")):
+            continue
+        mod.__dict__["_vap_original_forward"] = mod.forward
+
+        def tables(hidden_states, _m=mod, _ref=is_ref):
+            return rope.wan_rope_tables(_m.attention_head_dim, tuple(_m.patch_size), tuple(hidden_states.shape[2:]), ref=_ref,
+                                        device=hidden_states.device, max_seq_len=_m.max_seq_len)
+        mod.forward = tables
+
+
+def _restore_wan_rope(model: nn.Module) -> None:
+    for name in ("rope", "rope_mot_ref"):
+        mod = getattr(model, name, None)
+        if mod is not None and mod.__dict__.pop("_vap_original_forward", None) is not None:
+            del mod.forward
+
+
 def install(model: nn.Module, level: str = "block", strict: bool = True) -> nn.Module:
     """strict=False (levels "processor" / "sdpa"): SDPA calls outside the kernel's envelope — a VAE's or text encoder's attention under the
     global patch — fall through to the original torch function instead of raising (sdpa.patch_scaled_dot_product_attention)."""
@@ -42,6 +66,8 @@ def install(model: nn.Module, level: str = "block", strict: bool = True) -> nn.M
                 raise TypeError(f"{type(blk).__name__} is not a MoT block (no `with_mot_ref`)")
             blk.__dict__["_vap_original_forward"] = blk.forward
             blk.forward = types.MethodType(fwd, blk)
+        if family == "wan":
+            _swap_wan_rope(model)
     elif level == "processor":
         table = _WAN_PROC if family == "wan" else _COG_PROC
         for blk in blocks:
@@ -50,6 +76,8 @@ def install(model: nn.Module, level: str = "block", strict: bool = True) -> nn.M
                 if proc is not None and type(proc).__name__ in table and hasattr(m, "set_processor"):
                     m.__dict__.setdefault("_vap_original_processor", proc)
                     m.set_processor(table[type(proc).__name__]())
+        if family == "wan":
+            _swap_wan_rope(model)
         sdpa.patch_scaled_dot_product_attention(strict)
     elif level == "sdpa":
         sdpa.patch_scaled_dot_product_attention(strict)
@@ -68,5 +96,6 @@ def uninstall(model: nn.Module) -> nn.Module:
             proc = m.__dict__.pop("_vap_original_processor", None)
             if proc is not None:
                 m.set_processor(proc)
+    _restore_wan_rope(model)
     sdpa.unpatch_scaled_dot_product_attention()
     return model
