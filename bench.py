@@ -392,6 +392,10 @@ def main():
                 "clocks": clocks, "gpu_launches": n_launch,
                 "e2e": {"value": a.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "roofline": roof, "model_tflops": (total_flops / (ms_dev / a.steps * 1e-3) / 1e12) if total_flops else None}
+        if w["family"] == "wan":
+            # the Wan pipeline runs TWO B = 1 forwards per denoise step under classifier-free guidance (pipeline_wan_i2v_mot.py:815-861);
+            # `value` counts one forward + scheduler update as a step, this is the same measurement expressed per guided step (derived, not re-timed)
+            line["cfg_inclusive"] = {"value": line["value"] / 2.0, "unit": "guided steps/s", "derived": "value / 2 (two forwards per guided step)"}
         if world == 1 and not a.no_cpu_baseline and w["family"] == "wan":
             line["cpu_baseline"] = cpu_baseline_entry(vap, w, S, S)
         print(json.dumps(line), flush=True)
