@@ -20,9 +20,10 @@ OUT = os.path.join(ROOT, "gpurun_out")
 
 def run_one(name):
     import gpu_checks
+    import ref_gpu_checks
     import torch
     t0 = time.time()
-    res = {**gpu_checks.CHECKS, **gpu_checks.CHECKS_PENDING}[name]()
+    res = {**gpu_checks.CHECKS, **gpu_checks.CHECKS_PENDING, **ref_gpu_checks.CHECKS}[name]()
     torch.cuda.synchronize()
     print("RESULT " + json.dumps(dict(name=name, ok=True, seconds=round(time.time() - t0, 2), result=res)))
 
@@ -33,12 +34,15 @@ def main():
     ap.add_argument("--only", default="")
     ap.add_argument("--timeout", type=int, default=180)
     ap.add_argument("--pending", action="store_true")
+    ap.add_argument("--reference", action="store_true", help="run tests/ref_gpu_checks.CHECKS (parity against the staged reference on the GPU)")
     a = ap.parse_args()
     if a.check:
         return run_one(a.check)
     os.makedirs(OUT, exist_ok=True)
     import gpu_checks
-    names = [n for n in (gpu_checks.CHECKS_PENDING if a.pending else gpu_checks.CHECKS) if not a.only or n in a.only.split(",")]
+    import ref_gpu_checks
+    table = ref_gpu_checks.CHECKS if a.reference else gpu_checks.CHECKS_PENDING if a.pending else gpu_checks.CHECKS
+    names = [n for n in table if not a.only or n in a.only.split(",")]
     summary = []
     for n in names:
         t0 = time.time()
@@ -57,7 +61,7 @@ def main():
             open(os.path.join(OUT, f"diag_{n}.log"), "w").write((e.stdout or b"").decode(errors="replace") + (e.stderr or b"").decode(errors="replace"))
         summary.append(rec)
         print(json.dumps(rec), flush=True)
-    json.dump(summary, open(os.path.join(OUT, "diag_pending.json" if a.pending else "diag.json"), "w"), indent=1)
+    json.dump(summary, open(os.path.join(OUT, "diag_reference.json" if a.reference else "diag_pending.json" if a.pending else "diag.json"), "w"), indent=1)
     bad = [r["name"] for r in summary if not r["ok"]]
     print(f"{len(summary) - len(bad)}/{len(summary)} checks passed; failing: {bad}")
     sys.exit(1 if bad else 0)

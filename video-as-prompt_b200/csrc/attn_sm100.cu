@@ -67,9 +67,201 @@ struct AttnCfg {
     static constexpr int kColS0 = 0, kColS1 = 128, kColO0 = 256, kColO1 = 256 + D;
 };
 
+// Shared-memory map of one CTA: Q tiles | K/V ring | mbarriers.
+template <int D>
+struct AttnSmem {
+    using Cfg = AttnCfg<D>;
+    uint32_t q_smem, kv_smem, bar_base;
+    __device__ __forceinline__ explicit AttnSmem(uint32_t smem_base)
+        : q_smem(smem_base), kv_smem(smem_base + 2 * Cfg::kTileBytes), bar_base(smem_base + 2 * Cfg::kTileBytes + Cfg::kKvStages * Cfg::kTileBytes) {}
+    __device__ __forceinline__ uint32_t kv_full(int s) const { return bar_base + 8u * s; }
+    __device__ __forceinline__ uint32_t kv_empty(int s) const { return bar_base + 8u * (Cfg::kKvStages + s); }
+    __device__ __forceinline__ uint32_t q_full() const { return bar_base + 8u * (2 * Cfg::kKvStages); }
+    __device__ __forceinline__ uint32_t s_full(int i) const { return bar_base + 8u * (2 * Cfg::kKvStages + 1 + i); }            // S_i(j) in TMEM (and PV_i(j-1) done)
+    __device__ __forceinline__ uint32_t p_full(int i, int c) const { return bar_base + 8u * (2 * Cfg::kKvStages + 3 + 2 * i + c); }  // half c of P_i(j) in TMEM
+    __device__ __forceinline__ uint32_t pv_half(int i) const { return bar_base + 8u * (2 * Cfg::kKvStages + 7 + i); }           // the PV MMAs of half 0 have completed
+    __device__ __forceinline__ uint32_t o_done(int i) const { return bar_base + 8u * (2 * Cfg::kKvStages + 9 + i); }
+    __device__ __forceinline__ uint32_t tmem_ptr_addr() const { return bar_base + 8u * (2 * Cfg::kKvStages + 11); }
+    // one thread: p_arrivals = softmax warps per Q tile (each arrives once per published half)
+    __device__ __forceinline__ void init_barriers(int cluster_size, int p_arrivals) const {
+        for (int s = 0; s < Cfg::kKvStages; ++s) {
+            mbar_init(kv_full(s), 1);
+            mbar_init(kv_empty(s), cluster_size);  // one tcgen05.commit per CTA of the cluster
+        }
+        mbar_init(q_full(), 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(s_full(i), 1);
+            mbar_init(p_full(i, 0), p_arrivals);
+            mbar_init(p_full(i, 1), p_arrivals);
+            mbar_init(pv_half(i), 1);
+            mbar_init(o_done(i), 1);
+        }
+        fence_mbar_init();
+    }
+};
+
+// The producer and MMA warps run their loops warp-wide (all lanes wait on the mbarriers, one elected lane issues): control flow and
+// descriptors stay warp-uniform, so ptxas keeps them in uniform registers instead of wrapping every UTCHMMA / UTMALDG in an R2UR
+// waterfall loop.
 // CL = 2: clusters of two CTAs (adjacent 256-row query blocks of the same head) share every K / V tile: each CTA fetches half of
 // the tile's rows and TMA multicasts them into both CTAs' shared memory, so K / V cross the L2 -> SM fabric once per 512 query
 // rows; a ring slot is reusable when BOTH CTAs' MMAs have read it (multicast tcgen05.commit on the empty barriers).
+template <int D, int CL>
+__device__ __forceinline__ void attn_producer_warp(const AttnSmem<D>& sm, const CUtensorMap* tmQ, const CUtensorMap* tmK, const CUtensorMap* tmV, int q0, int head,
+                                                   int batch, int j0, int n_kv, int cta_rank) {
+    using Cfg = AttnCfg<D>;
+    if (elect_one()) {
+        mbar_arrive_expect_tx(sm.q_full(), 2 * Cfg::kTileBytes);
+        for (int t = 0; t < 2; ++t)
+            for (int h = 0; h < Cfg::kHalves; ++h)
+                tma_load_4d(sm.q_smem + t * Cfg::kTileBytes + h * Cfg::kHalfBytes, tmQ, sm.q_full(), h * 64, q0 + t * kBlockM, head, batch);
+    }
+    __syncwarp();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int j = 0; j < n_kv; ++j) {
+        for (int kv = 0; kv < 2; ++kv) {  // K_j then V_j
+            mbar_wait(sm.kv_empty(stage), phase ^ 1);
+            if (elect_one()) {
+                mbar_arrive_expect_tx(sm.kv_full(stage), Cfg::kTileBytes);
+                const uint32_t dst = sm.kv_smem + stage * Cfg::kTileBytes;
+                for (int h = 0; h < Cfg::kHalves; ++h) {
+                    if (CL == 2)  // my 64 rows of the tile, into both CTAs
+                        tma_load_4d_multicast(dst + h * Cfg::kHalfBytes + cta_rank * (kBlockN / 2) * 128, kv == 0 ? tmK : tmV, sm.kv_full(stage), h * 64,
+                                              (j0 + j) * kBlockN + cta_rank * (kBlockN / 2), head, batch, 3);
+                    else
+                        tma_load_4d(dst + h * Cfg::kHalfBytes, kv == 0 ? tmK : tmV, sm.kv_full(stage), h * 64, (j0 + j) * kBlockN, head, batch);
+                }
+            }
+            __syncwarp();
+            if (++stage == Cfg::kKvStages) {
+                stage = 0;
+                phase ^= 1;
+            }
+        }
+    }
+}
+
+#if VAP_ATTN_TRACE
+#define TRM(k) do { if (trm && j < 64) trm[j * 8 + (k)] = clock64(); } while (0)
+#else
+#define TRM(k) do { } while (0)
+#endif
+
+template <int D, int CL>
+__device__ __forceinline__ void attn_mma_warp(const AttnSmem<D>& sm, uint32_t tmem_base, int n_kv, long long* trm) {
+    using Cfg = AttnCfg<D>;
+    constexpr uint32_t idesc_qk = make_idesc_bf16(kBlockM, kBlockN, 0, 0);  // S = Q K^T : A, B K-major
+    constexpr uint32_t idesc_pv = make_idesc_bf16(kBlockM, D, 0, 1);        // O = P V   : A (TMEM) K-major, B MN-major
+    const uint32_t col_s[2] = {tmem_base + Cfg::kColS0, tmem_base + Cfg::kColS1};
+    const uint32_t col_o[2] = {tmem_base + Cfg::kColO0, tmem_base + Cfg::kColO1};
+    const uint32_t q_smem = sm.q_smem, kv_smem = sm.kv_smem;
+
+    auto issue_qk = [&](int i, uint32_t k_addr) {
+        const uint32_t q_addr = q_smem + i * Cfg::kTileBytes;
+        if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < D / 16; ++k) {
+                const uint32_t off = (k >> 2) * Cfg::kHalfBytes + (k & 3) * 32;
+                umma_ss(col_s[i], make_smem_desc(q_addr + off, 0, 1024, kLayoutSw128),
+                        make_smem_desc(k_addr + off, 0, 1024, kLayoutSw128), idesc_qk, k != 0 ? 1u : 0u);
+            }
+        }
+        __syncwarp();
+    };
+    auto issue_pv_half = [&](int i, int c, uint32_t v_addr, uint32_t accumulate) {
+        if (elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < kBlockN / 32; ++kk) {
+                const int k = 4 * c + kk;
+                // A: P_i, packed bf16 pairs, 8 TMEM columns per 16 kv;  B: V rows [16k, 16k+16) (2048 B apart),
+                // MN-major: 64-column slabs kHalfBytes apart (LBO), 8-row groups 1024 B apart (SBO)
+                umma_ts(col_o[i], col_s[i] + 8 * k, make_smem_desc(v_addr + k * 2048, Cfg::kHalfBytes, 1024, kLayoutSw128), idesc_pv,
+                        k != 0 ? 1u : accumulate);
+            }
+        }
+        __syncwarp();
+    };
+    auto commit = [&](uint32_t bar) {
+        if (elect_one()) umma_commit(bar);
+        __syncwarp();
+    };
+    auto release = [&](uint32_t bar) {  // a K / V ring slot: in a cluster the arrive goes to both CTAs' empty barriers
+        if (elect_one()) {
+            if (CL == 2) umma_commit_multicast(bar, 3);
+            else umma_commit(bar);
+        }
+        __syncwarp();
+    };
+
+    int stage = 0;
+    uint32_t phase = 0;
+    auto advance = [&]() {
+        if (++stage == Cfg::kKvStages) {
+            stage = 0;
+            phase ^= 1;
+        }
+    };
+    mbar_wait(sm.q_full(), 0);
+    mbar_wait(sm.kv_full(stage), phase);  // K_0
+    tc_fence_after();
+    issue_qk(0, kv_smem + stage * Cfg::kTileBytes);
+    commit(sm.s_full(0));
+    issue_qk(1, kv_smem + stage * Cfg::kTileBytes);
+    commit(sm.s_full(1));
+    release(sm.kv_empty(stage));
+    advance();
+    for (int j = 0; j < n_kv; ++j) {
+        const uint32_t par = j & 1;
+        const int v_stage = stage;
+        TRM(0);
+        mbar_wait(sm.kv_full(stage), phase);  // V_j
+        advance();
+        const int k_stage = stage;
+        const bool has_next = (j + 1 < n_kv);
+        if (has_next) {
+            mbar_wait(sm.kv_full(stage), phase);  // K_{j+1}
+            advance();
+        }
+        TRM(1);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            mbar_wait(sm.p_full(i, 0), par);
+            tc_fence_after();
+            TRM(2 + 2 * i);
+            issue_pv_half(i, 0, kv_smem + v_stage * Cfg::kTileBytes, j > 0 ? 1u : 0u);
+            commit(sm.pv_half(i));
+            mbar_wait(sm.p_full(i, 1), par);
+            tc_fence_after();
+            issue_pv_half(i, 1, kv_smem + v_stage * Cfg::kTileBytes, 1u);
+            if (has_next) {
+                issue_qk(i, kv_smem + k_stage * Cfg::kTileBytes);
+                commit(sm.s_full(i));  // also covers PV_i(j): O_i is quiescent when the softmax sees S_i(j+1)
+            } else {
+                commit(sm.o_done(i));
+            }
+            TRM(3 + 2 * i);
+        }
+        release(sm.kv_empty(v_stage));
+        if (has_next) release(sm.kv_empty(k_stage));
+    }
+}
+
+// Work-item coordinates of a CTA: (batch, head, 256 query rows) and — split-KV: grid z = batch * kv_splits + split — its KV tile range.
+struct AttnWork {
+    int q0, head, batch, j0, n_kv;
+    unsigned split;
+    __device__ __forceinline__ explicit AttnWork(const AttnParams& p) {
+        q0 = blockIdx.x * (2 * kBlockM);
+        head = blockIdx.y;
+        batch = static_cast<int>(blockIdx.z) / p.kv_splits;
+        split = blockIdx.z - static_cast<unsigned>(batch * p.kv_splits);
+        const int n_kv_all = (p.Lkv + kBlockN - 1) / kBlockN;
+        j0 = static_cast<int>(split * static_cast<unsigned>(n_kv_all) / static_cast<unsigned>(p.kv_splits));
+        n_kv = static_cast<int>((split + 1u) * static_cast<unsigned>(n_kv_all) / static_cast<unsigned>(p.kv_splits)) - j0;
+    }
+};
+
 template <int D, int CL>
 __global__ void __launch_bounds__(kAttnThreads, 1)  // registers are granted per 4 warps: 18 warps cost 20 -> 96 per thread
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -77,52 +269,26 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     using Cfg = AttnCfg<D>;
     constexpr int kPolyPairs = (D == 128) ? VAP_ATTN_POLY_PAIRS_D128 : VAP_ATTN_POLY_PAIRS_D64;
     extern __shared__ uint8_t smem_raw[];
-    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t q_smem = smem_base;
-    const uint32_t kv_smem = smem_base + 2 * Cfg::kTileBytes;
-    const uint32_t bar_base = kv_smem + Cfg::kKvStages * Cfg::kTileBytes;
-    auto kv_full = [&](int s) { return bar_base + 8u * s; };
-    auto kv_empty = [&](int s) { return bar_base + 8u * (Cfg::kKvStages + s); };
-    const uint32_t q_full = bar_base + 8u * (2 * Cfg::kKvStages);
-    auto s_full = [&](int i) { return bar_base + 8u * (2 * Cfg::kKvStages + 1 + i); };            // S_i(j) in TMEM (and PV_i(j-1) done)
-    auto p_full = [&](int i, int c) { return bar_base + 8u * (2 * Cfg::kKvStages + 3 + 2 * i + c); };  // half c of P_i(j) in TMEM
-    auto pv_half = [&](int i) { return bar_base + 8u * (2 * Cfg::kKvStages + 7 + i); };           // the PV MMAs of half 0 have completed
-    auto o_done = [&](int i) { return bar_base + 8u * (2 * Cfg::kKvStages + 9 + i); };
-    const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * Cfg::kKvStages + 11);
+    const AttnSmem<D> sm((smem_u32(smem_raw) + 1023u) & ~1023u);
+    auto s_full = [&](int i) { return sm.s_full(i); };
+    auto p_full = [&](int i, int c) { return sm.p_full(i, c); };
+    auto pv_half = [&](int i) { return sm.pv_half(i); };
+    auto o_done = [&](int i) { return sm.o_done(i); };
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int q0 = blockIdx.x * (2 * kBlockM);
-    const int head = blockIdx.y;
-    // split-KV: grid z = batch * kv_splits + split; this CTA attends to KV tiles [j0, j0 + n_kv) (all of them when kv_splits == 1)
-    const int batch = static_cast<int>(blockIdx.z) / p.kv_splits;
-    const unsigned split = blockIdx.z - static_cast<unsigned>(batch * p.kv_splits);
-    const int n_kv_all = (p.Lkv + kBlockN - 1) / kBlockN;
-    const int j0 = static_cast<int>(split * static_cast<unsigned>(n_kv_all) / static_cast<unsigned>(p.kv_splits));
-    const int n_kv = static_cast<int>((split + 1u) * static_cast<unsigned>(n_kv_all) / static_cast<unsigned>(p.kv_splits)) - j0;
+    const AttnWork wk(p);
+    const int q0 = wk.q0, head = wk.head, batch = wk.batch, j0 = wk.j0, n_kv = wk.n_kv;
+    const unsigned split = wk.split;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQ);
         tma_prefetch_desc(&tmK);
         tma_prefetch_desc(&tmV);
     }
-    if (warp == 1 && lane == 0) {
-        for (int s = 0; s < Cfg::kKvStages; ++s) {
-            mbar_init(kv_full(s), 1);
-            mbar_init(kv_empty(s), CL);  // one tcgen05.commit per CTA of the cluster
-        }
-        mbar_init(q_full, 1);
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(s_full(i), 1);
-            mbar_init(p_full(i, 0), kSoftmaxWarps / 2);  // one arrive per softmax warp of the tile
-            mbar_init(p_full(i, 1), kSoftmaxWarps / 2);
-            mbar_init(pv_half(i), 1);
-            mbar_init(o_done(i), 1);
-        }
-        fence_mbar_init();
-    }
+    if (warp == 1 && lane == 0) sm.init_barriers(CL, kSoftmaxWarps / 2);
     if (warp == 0) {
-        tmem_alloc(tmem_ptr_addr, Cfg::kTmemCols);
+        tmem_alloc(sm.tmem_ptr_addr(), Cfg::kTmemCols);
         tmem_relinquish();
     }
     tc_fence_before();
@@ -130,146 +296,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     if (CL == 2) cluster_sync_all();  // the peer's barriers are initialised before anything of ours can reach them
     tc_fence_after();
     uint32_t tmem_base;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(sm.tmem_ptr_addr()));
     const int cta_rank = (CL == 2) ? static_cast<int>(cluster_ctarank()) : 0;
 
-    // The producer and MMA warps run their loops warp-wide (all lanes wait on the mbarriers, one elected lane issues):
-    // control flow and descriptors stay warp-uniform, so ptxas keeps them in uniform registers instead of wrapping
-    // every UTCHMMA / UTMALDG in an R2UR waterfall loop.
     if (warp < kFirstSoftmaxWarp) {
         if (warp == 0) {
-            // ===== TMA producer =====
-            if (elect_one()) {
-                mbar_arrive_expect_tx(q_full, 2 * Cfg::kTileBytes);
-                for (int t = 0; t < 2; ++t)
-                    for (int h = 0; h < Cfg::kHalves; ++h)
-                        tma_load_4d(q_smem + t * Cfg::kTileBytes + h * Cfg::kHalfBytes, &tmQ, q_full, h * 64, q0 + t * kBlockM, head, batch);
-            }
-            __syncwarp();
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int j = 0; j < n_kv; ++j) {
-                for (int kv = 0; kv < 2; ++kv) {  // K_j then V_j
-                    mbar_wait(kv_empty(stage), phase ^ 1);
-                    if (elect_one()) {
-                        mbar_arrive_expect_tx(kv_full(stage), Cfg::kTileBytes);
-                        const uint32_t dst = kv_smem + stage * Cfg::kTileBytes;
-                        for (int h = 0; h < Cfg::kHalves; ++h) {
-                            if (CL == 2)  // my 64 rows of the tile, into both CTAs
-                                tma_load_4d_multicast(dst + h * Cfg::kHalfBytes + cta_rank * (kBlockN / 2) * 128, kv == 0 ? &tmK : &tmV, kv_full(stage), h * 64,
-                                                      (j0 + j) * kBlockN + cta_rank * (kBlockN / 2), head, batch, 3);
-                            else
-                                tma_load_4d(dst + h * Cfg::kHalfBytes, kv == 0 ? &tmK : &tmV, kv_full(stage), h * 64, (j0 + j) * kBlockN, head, batch);
-                        }
-                    }
-                    __syncwarp();
-                    if (++stage == Cfg::kKvStages) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
-                }
-            }
+            attn_producer_warp<D, CL>(sm, &tmQ, &tmK, &tmV, q0, head, batch, j0, n_kv, cta_rank);
         } else if (warp == 1) {
-            // ===== MMA issuer =====
-            constexpr uint32_t idesc_qk = make_idesc_bf16(kBlockM, kBlockN, 0, 0);  // S = Q K^T : A, B K-major
-            constexpr uint32_t idesc_pv = make_idesc_bf16(kBlockM, D, 0, 1);        // O = P V   : A (TMEM) K-major, B MN-major
-            const uint32_t col_s[2] = {tmem_base + Cfg::kColS0, tmem_base + Cfg::kColS1};
-            const uint32_t col_o[2] = {tmem_base + Cfg::kColO0, tmem_base + Cfg::kColO1};
-
-            auto issue_qk = [&](int i, uint32_t k_addr) {
-                const uint32_t q_addr = q_smem + i * Cfg::kTileBytes;
-                if (elect_one()) {
-#pragma unroll
-                    for (int k = 0; k < D / 16; ++k) {
-                        const uint32_t off = (k >> 2) * Cfg::kHalfBytes + (k & 3) * 32;
-                        umma_ss(col_s[i], make_smem_desc(q_addr + off, 0, 1024, kLayoutSw128),
-                                make_smem_desc(k_addr + off, 0, 1024, kLayoutSw128), idesc_qk, k != 0 ? 1u : 0u);
-                    }
-                }
-                __syncwarp();
-            };
-            auto issue_pv_half = [&](int i, int c, uint32_t v_addr, uint32_t accumulate) {
-                if (elect_one()) {
-#pragma unroll
-                    for (int kk = 0; kk < kBlockN / 32; ++kk) {
-                        const int k = 4 * c + kk;
-                        // A: P_i, packed bf16 pairs, 8 TMEM columns per 16 kv;  B: V rows [16k, 16k+16) (2048 B apart),
-                        // MN-major: 64-column slabs kHalfBytes apart (LBO), 8-row groups 1024 B apart (SBO)
-                        umma_ts(col_o[i], col_s[i] + 8 * k, make_smem_desc(v_addr + k * 2048, Cfg::kHalfBytes, 1024, kLayoutSw128), idesc_pv,
-                                k != 0 ? 1u : accumulate);
-                    }
-                }
-                __syncwarp();
-            };
-            auto commit = [&](uint32_t bar) {
-                if (elect_one()) umma_commit(bar);
-                __syncwarp();
-            };
-            auto release = [&](uint32_t bar) {  // a K / V ring slot: in a cluster the arrive goes to both CTAs' empty barriers
-                if (elect_one()) {
-                    if (CL == 2) umma_commit_multicast(bar, 3);
-                    else umma_commit(bar);
-                }
-                __syncwarp();
-            };
-
-            int stage = 0;
-            uint32_t phase = 0;
-            auto advance = [&]() {
-                if (++stage == Cfg::kKvStages) {
-                    stage = 0;
-                    phase ^= 1;
-                }
-            };
-            mbar_wait(q_full, 0);
-            mbar_wait(kv_full(stage), phase);  // K_0
-            tc_fence_after();
-            issue_qk(0, kv_smem + stage * Cfg::kTileBytes);
-            commit(s_full(0));
-            issue_qk(1, kv_smem + stage * Cfg::kTileBytes);
-            commit(s_full(1));
-            release(kv_empty(stage));
-            advance();
-            long long* trm = (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) ? p.trace + 1024 : nullptr;
-#if VAP_ATTN_TRACE
-#define TRM(k) do { if (trm && j < 64) trm[j * 8 + (k)] = clock64(); } while (0)
-#else
-#define TRM(k) do { } while (0)
-#endif
-            for (int j = 0; j < n_kv; ++j) {
-                const uint32_t par = j & 1;
-                const int v_stage = stage;
-                TRM(0);
-                mbar_wait(kv_full(stage), phase);  // V_j
-                advance();
-                const int k_stage = stage;
-                const bool has_next = (j + 1 < n_kv);
-                if (has_next) {
-                    mbar_wait(kv_full(stage), phase);  // K_{j+1}
-                    advance();
-                }
-                TRM(1);
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    mbar_wait(p_full(i, 0), par);
-                    tc_fence_after();
-                    TRM(2 + 2 * i);
-                    issue_pv_half(i, 0, kv_smem + v_stage * Cfg::kTileBytes, j > 0 ? 1u : 0u);
-                    commit(pv_half(i));
-                    mbar_wait(p_full(i, 1), par);
-                    tc_fence_after();
-                    issue_pv_half(i, 1, kv_smem + v_stage * Cfg::kTileBytes, 1u);
-                    if (has_next) {
-                        issue_qk(i, kv_smem + k_stage * Cfg::kTileBytes);
-                        commit(s_full(i));  // also covers PV_i(j): O_i is quiescent when the softmax sees S_i(j+1)
-                    } else {
-                        commit(o_done(i));
-                    }
-                    TRM(3 + 2 * i);
-                }
-                release(kv_empty(v_stage));
-                if (has_next) release(kv_empty(k_stage));
-            }
+            attn_mma_warp<D, CL>(sm, tmem_base, n_kv, (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) ? p.trace + 1024 : nullptr);
         }
     } else {
         // ===== softmax + epilogue warps =====
@@ -483,6 +517,231 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 }
 
 
+// ------------------------------------------------------------------------------------------------------------------------
+// "row" organisation of the softmax: ONE THREAD PER QUERY ROW, four warps per Q tile, 12 warps per CTA.
+//   warp 0: TMEM allocator + TMA producer, warp 1: MMA issuer (both shared with the kernel above), warps 2-3: idle (they only give their
+//   registers away), warps 4-7: softmax of Q tile 0, warps 8-11: softmax of Q tile 1.
+// Thread t of warp (4 + 4 i + q) owns TMEM lane 32 q + t = query row 128 i + 32 q + t: tcgen05.ld.32x32b hands it whole 32-column
+// chunks of its score row, so there is no shuffle, no quad, no vote except the (rare) reference update; its packed-bf16 P row goes back
+// with tcgen05.st.32x32b in the layout the TS MMA reads.  Same arithmetic as above: speculative p = 2^(s c - m_used c), partial-sum
+// trigger at 2^8, lazy O rescale, P published in two 64-column halves.  Fewer warps (8 instead of 16 softmax warps share the four
+// schedulers with nothing but each other) leave issue slots for the FMA-pipe exp2 polynomial (kPoly of every 8 pairs), which is what
+// takes load off the MUFU — at D = 128 the MUFU needs 2048 clk per pair of tile steps against 2048 clk of MMAs.
+// Register budget: setmaxnreg moves registers from warps 0-3 (96) to the softmax warps (208): 128 x 96 + 256 x 208 = 65536.
+// ------------------------------------------------------------------------------------------------------------------------
+constexpr int kRowThreads = 384;
+constexpr int kRowFirstSoftmaxWarp = 4;
+#ifndef VAP_ATTN_ROW_POLY_D128
+#define VAP_ATTN_ROW_POLY_D128 1
+#endif
+#ifndef VAP_ATTN_ROW_POLY_D64
+#define VAP_ATTN_ROW_POLY_D64 2
+#endif
+#ifndef VAP_ATTN_ROW_PREFETCH
+#define VAP_ATTN_ROW_PREFETCH 1  // 1: the whole 128-column score row is loaded at the top of a step (128 registers), 0: 64 columns per half
+#endif
+
+template <int D, int CL>
+__global__ void __launch_bounds__(kRowThreads, 1)
+attn_fwd_row_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+    using Cfg = AttnCfg<D>;
+    constexpr int kPoly = (D == 128) ? VAP_ATTN_ROW_POLY_D128 : VAP_ATTN_ROW_POLY_D64;
+    extern __shared__ uint8_t smem_raw[];
+    const AttnSmem<D> sm((smem_u32(smem_raw) + 1023u) & ~1023u);
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmK);
+        tma_prefetch_desc(&tmV);
+    }
+    if (warp == 1 && lane == 0) sm.init_barriers(CL, 4);
+    if (warp == 0) {
+        tmem_alloc(sm.tmem_ptr_addr(), Cfg::kTmemCols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (CL == 2) cluster_sync_all();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(sm.tmem_ptr_addr()));
+    const int cta_rank = (CL == 2) ? static_cast<int>(cluster_ctarank()) : 0;
+
+    if (warp < kRowFirstSoftmaxWarp) {
+        setmaxnreg_dec<96>();
+        const AttnWork wk(p);  // recomputed per role: values carried across the setmaxnreg split get spilled
+        if (warp == 0) {
+            attn_producer_warp<D, CL>(sm, &tmQ, &tmK, &tmV, wk.q0, wk.head, wk.batch, wk.j0, wk.n_kv, cta_rank);
+        } else if (warp == 1) {
+            attn_mma_warp<D, CL>(sm, tmem_base, wk.n_kv, nullptr);
+        }
+    } else {
+        setmaxnreg_inc<208>();
+        const AttnWork wk(p);
+        const int i = (warp - kRowFirstSoftmaxWarp) >> 2;  // Q tile
+        const int q = warp & 3;                            // TMEM lane quarter this warp may touch
+        const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+        const uint32_t s_col = tmem_base + lane_addr + (i == 0 ? Cfg::kColS0 : Cfg::kColS1);
+        const uint32_t o_col = tmem_base + lane_addr + (i == 0 ? Cfg::kColO0 : Cfg::kColO1);
+        const int row = wk.q0 + i * kBlockM + q * 32 + lane;
+        const float c = p.scale_log2;
+        const uint64_t c2 = pack_f32x2(c, c);
+        const float thr_off = kRescaleThreshold / c;
+        float m_used = -INFINITY;  // the reference this row's accumulators are scaled by (lazily updated)
+        float thr = -INFINITY;     // m_used + 8 / c (only the polynomial pairs are judged by their scores)
+        uint64_t nmc2 = 0ull;      // packed (-m_used c, -m_used c)
+        uint64_t l2 = 0ull;        // packed partial sums of this row
+
+        for (int j = 0; j < wk.n_kv; ++j) {
+            mbar_wait(sm.s_full(i), j & 1);  // QK_i(j) complete, and with it PV_i(j-1): O_i is quiescent until our first p_full arrive
+            tc_fence_after();
+            uint32_t sc[VAP_ATTN_ROW_PREFETCH ? 4 : 2][32];
+            if (VAP_ATTN_ROW_PREFETCH) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) tmem_ld_x32(s_col + 32 * t, sc[t]);
+                tmem_ld_wait();
+            }
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                uint32_t(&sa)[32] = sc[VAP_ATTN_ROW_PREFETCH ? 2 * ch : 0];
+                uint32_t(&sb)[32] = sc[VAP_ATTN_ROW_PREFETCH ? 2 * ch + 1 : 1];
+                if (!VAP_ATTN_ROW_PREFETCH) {
+                    tmem_ld_x32(s_col + 64 * ch, sa);
+                    tmem_ld_x32(s_col + 64 * ch + 32, sb);
+                    tmem_ld_wait();
+                }
+                const int valid = p.Lkv - (wk.j0 + j) * kBlockN - 64 * ch;  // column e of this half is inside the sequence iff e < valid
+                if (valid < 64) {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        if (e >= valid) sa[e] = __float_as_uint(-INFINITY);
+                        if (32 + e >= valid) sb[e] = __float_as_uint(-INFINITY);
+                    }
+                }
+#define SF(x) __uint_as_float((x) < 32 ? sa[(x) & 31] : sb[(x) & 31])
+                uint32_t pk[32];  // packed P columns 32 ch + e  (kv 64 ch + 2 e, 2 e + 1)
+                uint64_t ls[4];
+#pragma unroll 1
+                for (int pass = 0;; ++pass) {  // at most two passes: the second one runs against the refreshed reference
+                    ls[0] = 0ull, ls[1] = 0ull, ls[2] = 0ull, ls[3] = 0ull;
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        const uint64_t x2 = fma_f32x2(pack_f32x2(SF(2 * e), SF(2 * e + 1)), c2, nmc2);
+                        float x0, x1, p0, p1;
+                        unpack_f32x2(x2, x0, x1);
+                        if ((e & 7) < kPoly) {
+                            ex2_poly_x2(x0, x1, p0, p1);
+                        } else {
+                            p0 = ex2_approx(x0);
+                            p1 = ex2_approx(x1);
+                        }
+                        ls[e & 3] = add_f32x2(ls[e & 3], pack_f32x2(p0, p1));
+                        pk[e] = pack_bf16x2(p0, p1);
+                    }
+                    ls[0] = add_f32x2(add_f32x2(ls[0], ls[1]), add_f32x2(ls[2], ls[3]));
+                    float lo, hi;
+                    unpack_f32x2(ls[0], lo, hi);
+                    // a MUFU result above 2^8 (ex2.approx overflows cleanly to +inf) shows in the partial sum; the polynomial's exponent
+                    // arithmetic is only valid for x < 128, so its pairs are judged by their scores; the first half-tile has no reference yet
+                    bool need = (lo + hi > kSumTrigger) || (m_used == -INFINITY);
+                    if constexpr (kPoly > 0) {
+                        float pm = -INFINITY;
+#pragma unroll
+                        for (int e = 0; e < 32; ++e)
+                            if ((e & 7) < kPoly) pm = fmax3(pm, SF(2 * e), SF(2 * e + 1));
+                        need = need || (pm > thr);
+                    }
+                    if (pass == 1 || !__any_sync(0xffffffffu, need)) break;
+                    // ---- reference update: this row's maximum, rescale the warp's 32 rows of O (factor 1 where nothing changed), repeat ----
+                    float mx = fmax3(SF(0), SF(1), SF(2));
+#pragma unroll
+                    for (int e = 3; e < 63; e += 2) mx = fmax3(mx, SF(e), SF(e + 1));
+                    mx = fmaxf(mx, SF(63));
+                    const float mn = fmaxf(m_used, mx);
+                    if (j > 0 || ch > 0) {
+                        if (ch > 0) {  // the PV MMAs of this step's first half must have left O_i
+                            mbar_wait(sm.pv_half(i), j & 1);
+                            tc_fence_after();
+                        }
+                        const float f = ex2_approx((m_used - mn) * c);
+                        l2 = mul_f32x2(l2, pack_f32x2(f, f));
+#pragma unroll 1
+                        for (int g = 0; g < D / 32; ++g) {
+                            uint32_t ov[32];
+                            tmem_ld_x32(o_col + 32 * g, ov);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * f);
+                            tmem_st_x32(o_col + 32 * g, ov);
+                        }
+                    }
+                    m_used = mn;
+                    thr = mn + thr_off;
+                    nmc2 = pack_f32x2(-mn * c, -mn * c);
+                }
+#undef SF
+                l2 = add_f32x2(l2, ls[0]);
+                tmem_st_x32(s_col + 32 * ch, pk);
+                tmem_st_wait();  // covers the rescaled O columns too
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(sm.p_full(i, ch));
+            }
+        }
+        // ===== epilogue: O / l -> bf16 -> global, 16-byte stores (a thread writes its row's 32-column chunk = 64 contiguous bytes) =====
+        {
+            float lo, hi;
+            unpack_f32x2(l2, lo, hi);
+            const float l = lo + hi;
+            mbar_wait(sm.o_done(i), 0);
+            tc_fence_after();
+            const float inv_l = 1.f / l;
+            const bool row_ok = row < p.Lq;
+            // plain mode: one output tensor; peer mode (Ulysses exchange #2 fused into the epilogue): the query rows of rank r are
+            // stored straight into rank r's output buffer over NVLink; split-KV: partial O of this KV range
+            __nv_bfloat16* orow;
+            if (p.o_rows_per_peer > 0) {
+                const int peer = row / p.o_rows_per_peer;
+                orow = (peer < 8 ? p.o_peer[peer] : p.o_peer[0]) + wk.batch * p.o_sb + wk.head * p.o_sh + static_cast<int64_t>(row - peer * p.o_rows_per_peer) * p.o_sl;
+            } else {
+                orow = p.o + static_cast<uint64_t>(wk.split) * static_cast<uint64_t>(p.o_split_stride) + wk.batch * p.o_sb + wk.head * p.o_sh + static_cast<int64_t>(row) * p.o_sl;
+            }
+#pragma unroll 1
+            for (int g = 0; g < D / 32; ++g) {
+                uint32_t ov[32];
+                tmem_ld_x32(o_col + 32 * g, ov);
+                tmem_ld_wait();
+                if (row_ok) {
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        uint4 o;
+                        o.x = pack_bf16x2(__uint_as_float(ov[8 * v + 0]) * inv_l, __uint_as_float(ov[8 * v + 1]) * inv_l);
+                        o.y = pack_bf16x2(__uint_as_float(ov[8 * v + 2]) * inv_l, __uint_as_float(ov[8 * v + 3]) * inv_l);
+                        o.z = pack_bf16x2(__uint_as_float(ov[8 * v + 4]) * inv_l, __uint_as_float(ov[8 * v + 5]) * inv_l);
+                        o.w = pack_bf16x2(__uint_as_float(ov[8 * v + 6]) * inv_l, __uint_as_float(ov[8 * v + 7]) * inv_l);
+                        st_v4(orow + 32 * g + 8 * v, o);
+                    }
+                }
+            }
+            if (p.lse && row_ok)
+                p.lse[static_cast<uint64_t>(wk.split) * static_cast<uint64_t>(p.lse_split_stride) + (static_cast<int64_t>(wk.batch) * p.H + wk.head) * p.Lq + row] =
+                    m_used * p.scale + logf(l);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (CL == 2) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it or signal its barriers
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    }
+}
+
+
 static int make_attn_tmap(CUtensorMap* tm, const AttnTensor& t, int B, int H, int L, int D, int box_rows, const char* name) {
     VAP_REQUIRE((reinterpret_cast<uintptr_t>(t.ptr) & 15) == 0, "attention: %s must be 16-byte aligned", name);
     VAP_REQUIRE(t.sl % 8 == 0 && t.sh % 8 == 0 && t.sb % 8 == 0, "attention: %s strides must be multiples of 8 elements", name);
@@ -494,43 +753,68 @@ static int make_attn_tmap(CUtensorMap* tm, const AttnTensor& t, int B, int H, in
     return make_tmap_bf16(tm, t.ptr, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
+// Developer switches, read per call (cheap: two getenv), so tools can A/B variants inside one process:
+//   VAP_ATTN_CLUSTER=2   two-CTA clusters sharing the K / V tiles by TMA multicast
+//   VAP_ATTN_SOFTMAX     "row" (one thread per query row, 12 warps) or "lane16" (16-lane TMEM shapes, 18 warps)
 static int attn_cluster_mode() {
-    static int mode = -1;
-    if (mode < 0) {
-        const char* e = getenv("VAP_ATTN_CLUSTER");
-        mode = e ? atoi(e) : 0;
-    }
-    return mode;
+    const char* e = getenv("VAP_ATTN_CLUSTER");
+    return e ? atoi(e) : 0;
+}
+#ifndef VAP_ATTN_DEFAULT_ROW
+#define VAP_ATTN_DEFAULT_ROW 0
+#endif
+static bool attn_row_mode() {
+    const char* e = getenv("VAP_ATTN_SOFTMAX");
+    if (!e || !*e) return VAP_ATTN_DEFAULT_ROW != 0;
+    return e[0] == 'r';
 }
 
-template <int D, int CL>
+// cudaFuncSetAttribute is per device: remember which devices have been opted in to the large dynamic shared memory (one flag per kernel
+// instantiation and device; a benign race — two threads may both set it)
+template <typename Kernel>
+static int attn_opt_in_smem(Kernel kernel, int bytes, bool (&done)[64]) {
+    int dev = 0;
+    VAP_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !done[dev]) {
+        VAP_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        if (dev >= 0 && dev < 64) done[dev] = true;
+    }
+    return 0;
+}
+
+template <int D, int CL, bool ROW>
 static int launch_attn_d(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const AttnParams& p, cudaStream_t stream) {
     using Cfg = AttnCfg<D>;
     static_assert(Cfg::kSmemBytes <= 232448, "shared memory budget");
     static_assert(2 * Cfg::kKvStages + 12 <= Cfg::kBarBytes / 8, "barrier area");
-    static bool attr_set = false;
-    if (!attr_set) {
-        VAP_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<D, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-        attr_set = true;
-    }
+    auto kernel = ROW ? attn_fwd_row_kernel<D, CL> : attn_fwd_kernel<D, CL>;
+    constexpr int threads = ROW ? kRowThreads : kAttnThreads;
+    static bool opted_in[64] = {};
+    if (int rc = attn_opt_in_smem(kernel, Cfg::kSmemBytes, opted_in)) return rc;
     const unsigned q_blocks = static_cast<unsigned>((p.Lq + 2 * kBlockM - 1) / (2 * kBlockM));
     if (CL == 1) {
         const dim3 grid(q_blocks, p.H, p.B * p.kv_splits);
-        attn_fwd_kernel<D, CL><<<grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(tmQ, tmK, tmV, p);
+        kernel<<<grid, threads, Cfg::kSmemBytes, stream>>>(tmQ, tmK, tmV, p);
         VAP_CHECK_CUDA(cudaGetLastError());
         return 0;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((q_blocks + 1) / 2 * 2, p.H, p.B * p.kv_splits);  // a trailing CTA without query rows still loads and consumes its share of K / V
-    cfg.blockDim = dim3(kAttnThreads);
+    cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     cfg.stream = stream;
     cudaLaunchAttribute attr{};
     attr.id = cudaLaunchAttributeClusterDimension;
     attr.val.clusterDim.x = 2, attr.val.clusterDim.y = 1, attr.val.clusterDim.z = 1;
     cfg.attrs = &attr, cfg.numAttrs = 1;
-    VAP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, attn_fwd_kernel<D, CL>, tmQ, tmK, tmV, p));
+    VAP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmQ, tmK, tmV, p));
     return 0;
+}
+
+template <int D>
+static int launch_attn_variant(bool cluster, bool row, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const AttnParams& p, cudaStream_t stream) {
+    if (row) return cluster ? launch_attn_d<D, 2, true>(tmQ, tmK, tmV, p, stream) : launch_attn_d<D, 1, true>(tmQ, tmK, tmV, p, stream);
+    return cluster ? launch_attn_d<D, 2, false>(tmQ, tmK, tmV, p, stream) : launch_attn_d<D, 1, false>(tmQ, tmK, tmV, p, stream);
 }
 
 int launch_attention_fwd(const AttnTensor& q, const AttnTensor& k, const AttnTensor& v, AttnParams p, int D, cudaStream_t stream) {
@@ -558,8 +842,8 @@ int launch_attention_fwd(const AttnTensor& q, const AttnTensor& k, const AttnTen
     if (make_attn_tmap(&tmQ, q, p.B, p.H, p.Lq, D, kBlockM, "q")) return -3;
     if (make_attn_tmap(&tmK, k, p.B, p.H, p.Lkv, D, cluster ? kBlockN / 2 : kBlockN, "k")) return -3;
     if (make_attn_tmap(&tmV, v, p.B, p.H, p.Lkv, D, cluster ? kBlockN / 2 : kBlockN, "v")) return -3;
-    if (cluster) return D == 128 ? launch_attn_d<128, 2>(tmQ, tmK, tmV, p, stream) : launch_attn_d<64, 2>(tmQ, tmK, tmV, p, stream);
-    return D == 128 ? launch_attn_d<128, 1>(tmQ, tmK, tmV, p, stream) : launch_attn_d<64, 1>(tmQ, tmK, tmV, p, stream);
+    const bool row = attn_row_mode();
+    return D == 128 ? launch_attn_variant<128>(cluster, row, tmQ, tmK, tmV, p, stream) : launch_attn_variant<64>(cluster, row, tmQ, tmK, tmV, p, stream);
 }
 
 // ------------------------------------------------------------------------------------------------------------------------

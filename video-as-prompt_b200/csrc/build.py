@@ -41,11 +41,17 @@ def _digest() -> str:
     return h.hexdigest()
 
 
+LAST_BUILD = "not run"  # "compiled" or "reused (source hash match)": what the last build() call did
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
+    global LAST_BUILD
     stamp = PKG / ".libvap_b200.hash"
     digest = _digest()
     if not force and LIB.exists() and stamp.exists() and stamp.read_text().strip() == digest:
+        LAST_BUILD = "reused (source hash match)"
         return LIB
+    LAST_BUILD = "compiled"
     BUILD.mkdir(exist_ok=True)
 
     def compile_one(src: str):
@@ -77,4 +83,4 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
 if __name__ == "__main__":
     lib = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
-    print(lib)
+    print(f"{LAST_BUILD}: {lib}")

@@ -92,4 +92,3 @@ def unpatch_scaled_dot_product_attention() -> None:
         F.scaled_dot_product_attention = _ORIGINAL_SDPA
         _ORIGINAL_SDPA = None
     _STRICT = True
-_STRICT = True  # False: calls outside the kernel's envelope go to the ORIGINAL torch SDPA (see patch_scaled_dot_product_attention)

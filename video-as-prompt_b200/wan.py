@@ -56,8 +56,14 @@ class context_cache:
         return False
 
 
+def _ver(t: torch.Tensor) -> int:
+    """Version counter of `t`; inference tensors (created under torch.inference_mode()) do not track one and cannot be written in place
+    outside inference mode, so a constant is as good (the cache entries hold a reference to the tensor: no aliasing by reallocation)."""
+    return 0 if t.is_inference() else t._version
+
+
 def _tensor_key(*tensors):
-    return tuple(None if t is None else (t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride()), t.dtype, t.device) for t in tensors)
+    return tuple(None if t is None else (t.data_ptr(), _ver(t), tuple(t.shape), tuple(t.stride()), t.dtype, t.device) for t in tensors)
 
 
 def _cached(owner: nn.Module, slot: str, inputs, compute):
@@ -87,12 +93,38 @@ def clear_context_cache(model: nn.Module) -> None:
 def _f32(owner: nn.Module, name: str, t: torch.Tensor) -> torch.Tensor:
     """fp32 copy of a small per-channel parameter, refreshed when the parameter storage or version changes."""
     cache = owner.__dict__.setdefault("_vap_f32", {})
-    key = (t.data_ptr(), t._version, t.device)
+    key = (t.data_ptr(), _ver(t), t.device)
     ent = cache.get(name)
     if ent is None or ent[0] != key:
         ent = (key, t.detach().to(torch.float32).contiguous())
         cache[name] = ent
     return ent[1]
+
+
+def _plain_linear(lin: nn.Module) -> nn.Module:
+    """The fused path reads `weight` / `bias` directly, so a layer must BE its weight: a PEFT / LoRA wrapper (whose `.weight` is the base
+    layer's — the unmerged adapter and `attention_kwargs["scale"]` would silently be dropped) or an FSDP2 / tensor-parallel DTensor
+    parameter (a shard, not the matrix) is refused with the way out."""
+    if hasattr(lin, "base_layer") or hasattr(lin, "lora_A"):
+        raise ops.VapError(f"{type(lin).__name__} is a PEFT / LoRA-wrapped layer: the fused VAP path computes with `.weight` only and would drop the "
+                           "adapter — call merge_and_unload() (or fuse_lora()) first, or use install(level='sdpa')")
+    w = lin.weight
+    if type(w).__name__ == "DTensor" or type(getattr(w, "data", w)).__name__ == "DTensor" or hasattr(w, "_local_tensor"):
+        raise ops.VapError("the layer's weight is a DTensor (FSDP2 / tensor parallel shard): the fused VAP path needs whole matrices — "
+                           "use install(level='sdpa') under FSDP, or install() before sharding for inference")
+    return lin
+
+
+def _adjacent(tensors: List[torch.Tensor]) -> Optional[torch.Tensor]:
+    """If `tensors` already sit back to back in one storage (a packed buffer made earlier — possibly by another module object sharing the
+    same parameters, e.g. the reference's model given our shell's tensors), the [sum N, ...] view over them; else None."""
+    t0 = tensors[0]
+    base, off = t0.untyped_storage().data_ptr(), t0.storage_offset()
+    for t in tensors:
+        if not t.is_contiguous() or t.untyped_storage().data_ptr() != base or t.storage_offset() != off or t.shape[1:] != t0.shape[1:]:
+            return None
+        off += t.numel()
+    return t0.as_strided((sum(t.shape[0] for t in tensors),) + tuple(t0.shape[1:]), t0.stride(), t0.storage_offset())
 
 
 def _packed(owner: nn.Module, name: str, linears: List[nn.Linear]) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
@@ -104,9 +136,16 @@ def _packed(owner: nn.Module, name: str, linears: List[nn.Linear]) -> Tuple[torc
     w0 = linears[0].weight
     if ent is not None and ent[0].device == w0.device and w0.data_ptr() == ent[0].data_ptr():
         return ent
+    for l in linears:
+        _plain_linear(l)
     with torch.no_grad():
-        W = torch.cat([l.weight.detach() for l in linears], dim=0).contiguous()
         has_bias = linears[0].bias is not None
+        W = _adjacent([l.weight.detach() for l in linears])
+        bvec = _adjacent([l.bias.detach() for l in linears]) if has_bias else None
+        if W is not None and (bvec is not None or not has_bias):
+            cache[name] = (W, bvec)
+            return cache[name]
+        W = torch.cat([l.weight.detach() for l in linears], dim=0).contiguous()
         bvec = torch.cat([l.bias.detach() for l in linears], dim=0).contiguous() if has_bias else None
         r = 0
         for l in linears:
@@ -120,6 +159,7 @@ def _packed(owner: nn.Module, name: str, linears: List[nn.Linear]) -> Tuple[torc
 
 
 def _linear(lin: nn.Linear, x: torch.Tensor, **kw) -> torch.Tensor:
+    _plain_linear(lin)
     return ops.linear(x, lin.weight, lin.bias, **kw)
 
 
@@ -169,7 +209,11 @@ def _cross_attn(attn: nn.Module, x: torch.Tensor, ctx: torch.Tensor, num_mot_ref
     if num_mot_ref != 1:
         raise NotImplementedError("num_mot_ref > 1 is rejected by the reference block itself (transformer_wan_mot.py:611)")
     heads = attn.heads
-    img_len = ctx.shape[1] - TEXT_CONTEXT_LEN * num_mot_ref
+    # the reference splits off the image tokens only when the module has the added projections (:47-52, :127-129); a text-only block
+    # attends over the whole context, whatever its length
+    img_len = ctx.shape[1] - TEXT_CONTEXT_LEN * num_mot_ref if getattr(attn, "add_k_proj", None) is not None else 0
+    if img_len < 0:
+        raise ValueError(f"context of {ctx.shape[1]} tokens is shorter than the {TEXT_CONTEXT_LEN * num_mot_ref} text tokens the I2V cross-attention expects")
     ctx_img, ctx_txt = ctx[:, :img_len], ctx[:, img_len:]
     inner = attn.to_q.weight.shape[0]
     hd = inner // heads
@@ -196,7 +240,7 @@ def _cross_attn(attn: nn.Module, x: torch.Tensor, ctx: torch.Tensor, num_mot_ref
     qh = _heads_view(q, heads)
     o = ops.attention(qh, _heads_view(kv[..., :inner], heads), _heads_view(kv[..., inner:], heads))
     o = _token_major(o)
-    if img_len > 0 and getattr(attn, "add_k_proj", None) is not None:
+    if img_len > 0:
         kvi = _cached(attn, "kv_img", (ctx,), image_kv)
         o_img = _token_major(ops.attention(qh, _heads_view(kvi[..., :inner], heads), _heads_view(kvi[..., inner:], heads)))
         o = o + o_img  # two independent softmaxes summed in bf16 (:186)
