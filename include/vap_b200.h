@@ -8,7 +8,11 @@
  *
  * Conventions
  *   - all pointers are DEVICE pointers owned by the caller (PyTorch allocates every buffer incl. outputs);
- *     the library never allocates, frees, synchronises a stream or keeps state between calls;
+ *     the library never allocates, frees or synchronises a stream.  The only state it keeps between calls is per-device
+ *     bookkeeping that does not change results: which devices have been opted in to the kernels' dynamic shared memory
+ *     (cudaFuncSetAttribute is a per-device setting), the SM count / cluster occupancy of each device, and the driver's
+ *     tensor-map entry point.  Developer switches (VAP_ATTN_*, VAP_GEMM_* environment variables) select among kernels
+ *     that compute the same function; a process may drive several GPUs (set the device before the call);
  *   - bf16 tensors are `uint16_t`-sized elements (torch.bfloat16); vectors of per-channel parameters
  *     (norm weights, modulation, gates, RoPE tables) are fp32;
  *   - sizes/strides are in ELEMENTS; the innermost dimension is contiguous;
@@ -25,7 +29,7 @@
 extern "C" {
 #endif
 
-#define VAP_B200_VERSION 302 /* major*10000 + minor*100 + patch */
+#define VAP_B200_VERSION 400 /* major*10000 + minor*100 + patch */
 
 /* Library version (VAP_B200_VERSION of the build). */
 int vap_version(void);
@@ -154,6 +158,15 @@ int vap_attention_bwd(const void* q, const void* k, const void* v, const void* o
  *     multiples of 8, all pointers 16-byte aligned. */
 int vap_cfg_flow_match_step(const void* noise_cond, const void* noise_uncond, const void* sample, int sample_is_f32, void* out, int64_t batch,
                             int64_t inner, int64_t out_batch_stride, float guidance_scale, float dt, void* stream);
+
+/* (5b) adaLN modulation vectors of a Wan block in one launch (W1):
+ *   out[b, c, :] = float(table[c, :]) + float(temb[b, c, :])   (+ 1 when bit c of plus_one_mask is set)      fp32 [batch, chunks, d]
+ * table [chunks, d] and temb [batch, chunks, d] are contiguous, bf16 (is_f32 = 0) or fp32 (1).  The six chunks are
+ * shift / scale / gate / c_shift / c_scale / c_gate; mask 0b010010 yields (1 + scale) and (1 + c_scale) ready for
+ * vap_adaln_layernorm's scale1p.
+ *     Ref: transformer_wan_mot.py:606-616 ((scale_shift_table + temb.float()).chunk(6)), :620-622, :680-689 ("1 + scale"). */
+int vap_wan_modulation(const void* table, int table_is_f32, const void* temb, int temb_is_f32, float* out, int64_t batch, int chunks, int d,
+                       int plus_one_mask, void* stream);
 
 /* (6) Bring-up probe for the tcgen05 descriptors: one CTA computes D[128,N] = A[128,K] * B, fp32 out.
  *     a_in_tmem: bit 0: 0 = A from shared memory (K-major, SWIZZLE_128B), 1 = A staged to TMEM as packed bf16;

@@ -167,8 +167,17 @@ def cfg_flow_match_step(noise_cond, noise_uncond, sample, *, guidance_scale, dt,
     return out
 
 
+def wan_modulation(table, temb, plus_one_mask=0b010010):
+    """vap_wan_modulation: (table + temb.float()) with 1 added to the masked chunks, fp32 (transformer_wan_mot.py:606-608, 620-622)."""
+    mod = table.float() + temb.float()
+    for c in range(mod.shape[1]):
+        if (plus_one_mask >> c) & 1:
+            mod[:, c] += 1
+    return mod
+
+
 def install(vap) -> None:
     """Replace the kernel wrappers of `vap.ops` by the stand-ins (one test process only)."""
-    for name in ("adaln_layernorm", "qk_norm_rope_", "attention", "attention_bwd", "linear", "ulysses_pack", "ulysses_unpack", "cfg_flow_match_step"):
+    for name in ("adaln_layernorm", "qk_norm_rope_", "attention", "attention_bwd", "linear", "ulysses_pack", "ulysses_unpack", "cfg_flow_match_step", "wan_modulation"):
         setattr(vap.ops, name, globals()[name])
     vap.ops.sm_count = lambda: 148

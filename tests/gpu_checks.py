@@ -96,12 +96,29 @@ def check_layernorm_cog(rows=226, d=3072, nmod=2):
     return dict(err=err, mismatch_frac=mism)
 
 
-def check_qk_wan(S=300, H=40, D=128):
+def check_wan_modulation():
+    """vap_wan_modulation == (scale_shift_table + temb.float()) with the "+ 1" of the scale chunks, bit for bit (fp32 adds), for the bf16 and
+    the fp32 (from_pretrained keeps scale_shift_table in fp32) parameter."""
+    d = 5120
+    res = {}
+    for tdt in (torch.bfloat16, torch.float32):
+        table = _randn((1, 6, d), 90, d ** -0.5, tdt).to(DEV)
+        temb = _randn((2, 6, d), 91, 0.5).to(DEV)
+        ref = table.float() + temb.float()
+        ref[:, 1] = 1 + ref[:, 1]
+        ref[:, 4] = 1 + ref[:, 4]
+        got = ops.wan_modulation(table, temb)
+        res[str(tdt)] = bool(torch.equal(got, ref))
+    assert all(res.values()), f"wan modulation is not bit-exact: {res}"
+    return res
+
+
+def check_qk_wan(S=300, H=40, D=128, grid=(3, 10, 10)):
     d = H * D
     qkv = _randn((1, S, 3 * d), 13, 1.0)
     wq = (1 + _randn((d,), 14, 0.1, torch.float32)).to(torch.bfloat16)
     wk = (1 + _randn((d,), 15, 0.1, torch.float32)).to(torch.bfloat16)
-    frames, gh, gw = 3, 10, 10
+    frames, gh, gw = grid
     freqs = wan_oracle.wan_rope(D, (1, 2, 2), 1024, (frames, 2 * gh, 2 * gw), ref=True)  # [1,1,300,64] complex128, negative t
     assert freqs.shape[2] == S
     q, k = qkv[..., :d], qkv[..., d:2 * d]
@@ -585,18 +602,28 @@ def check_attention_bwd(B=1, H=2, Lq=300, Lkv=300, D=128, joint_layout=True, see
     return dict(dq=errs[0], dk=errs[1], dv=errs[2], seam=max(errs_seam))
 
 
-def check_attention_bwd_split2(**kw):
-    """The same checks with two sets of elementwise warps (VAP_ATTN_BWD_SPLIT=2; read once per process, so this check must run in its own
-    process — tools/gpu_diag.py does that)."""
-    os.environ["VAP_ATTN_BWD_SPLIT"] = "2"
-    return check_attention_bwd(**kw)
+def _with_env(env, fn, **kw):
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        return fn(**kw)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
 
 
-def check_attention_bwd_prefetch(**kw):
-    """dQ kernel with S double-buffered (VAP_ATTN_BWD_PREFETCH=1) and both elementwise sets — own process, like the split-2 check."""
-    os.environ["VAP_ATTN_BWD_PREFETCH"] = "1"
-    os.environ["VAP_ATTN_BWD_SPLIT"] = "2"
-    return check_attention_bwd(**kw)
+def check_attention_bwd_split1(**kw):
+    """The backward's simplest configuration — ONE set of elementwise warps, no S prefetch (the defaults are two sets + prefetch; the
+    switches are read per call)."""
+    return _with_env({"VAP_ATTN_BWD_SPLIT": "1", "VAP_ATTN_BWD_PREFETCH": "0"}, check_attention_bwd, **kw)
+
+
+def check_attention_bwd_noprefetch(**kw):
+    """Two elementwise sets, dQ kernel without the double-buffered S."""
+    return _with_env({"VAP_ATTN_BWD_SPLIT": "2", "VAP_ATTN_BWD_PREFETCH": "0"}, check_attention_bwd, **kw)
 
 
 def check_cfg_flow_match_step(B=2, inner=16 * 3 * 16 * 16):
@@ -719,7 +746,14 @@ CHECKS = {
     "ln_wan_affine": lambda: check_layernorm_wan(rows=100, d=256, affine=True, modulate=False),
     "ln_wan_batch": lambda: check_layernorm_wan(rows=64, d=3072, batch=2),
     "ln_cog": lambda: check_layernorm_cog(),
+    "wan_modulation": check_wan_modulation,
     "qk_wan": lambda: check_qk_wan(),
+    # >= 1024 rows at d = 5120 / 3072: the staged kernels (bulk-copy ring per warp, per-channel vectors in shared memory); ragged row counts
+    "ln_wan_staged": lambda: check_layernorm_wan(rows=1531, d=5120),
+    "ln_wan_staged_affine": lambda: check_layernorm_wan(rows=1100, d=5120, affine=True, modulate=False),
+    "ln_wan_staged_batch2": lambda: check_layernorm_wan(rows=1033, d=5120, batch=2),
+    "ln_cog_staged": lambda: check_layernorm_cog(rows=1203, d=3072, nmod=2),
+    "qk_wan_staged": lambda: check_qk_wan(S=1200, H=40, D=128, grid=(3, 20, 20)),
     "qk_wan_tiny": lambda: check_qk_wan(S=300, H=2, D=128),
     "qk_cog": lambda: check_qk_cog(),
     "gemm_small": lambda: check_gemm(300, 512, 256, 0),
@@ -758,22 +792,23 @@ CHECKS = {
     "gemm_large": check_gemm_large,
     "attn_full_size": check_attention_full_size,
     "attn_splitkv_sp8_shape": check_attention_splitkv_sp8_shape,
-}
-
-# Checks of code written without GPU access (the round's GPU budget was spent): run by `tools/gpu_diag.py --pending`, promoted into
-# CHECKS (and so into `pytest -m gpu`) once they have passed on a B200.
-CHECKS_PENDING = {
-    "attn_bwd_d128": lambda: check_attention_bwd(1, 2, 300, 300, 128),
+    # first run on a B200 in round 2 (profiles/r02_pending_and_reference_checks.json): the attention backward (dQ / dK / dV on tcgen05 from the
+    # forward's LSE, also through the differentiable joint_sdpa seam), the fused CFG + FlowMatchEuler step, the cached / batched-CFG / fused denoise loops
     "attn_bwd_one_tile": lambda: check_attention_bwd(1, 1, 100, 100, 128, joint_layout=False),
+    "attn_bwd_d128": lambda: check_attention_bwd(1, 2, 300, 300, 128),
     "attn_bwd_d64": lambda: check_attention_bwd(2, 3, 452, 260, 64, joint_layout=False),
     "attn_bwd_tails": lambda: check_attention_bwd(1, 1, 130, 128 * 5 + 7, 128, joint_layout=False),
     "attn_bwd_multi_tile": lambda: check_attention_bwd(1, 2, 1000, 1000, 128),
-    "attn_bwd_split2_d128": lambda: check_attention_bwd_split2(B=1, H=2, Lq=300, Lkv=647, D=128, joint_layout=False),
-    "attn_bwd_prefetch_d128": lambda: check_attention_bwd_prefetch(B=1, H=2, Lq=300, Lkv=647, D=128, joint_layout=False),
-    "attn_bwd_prefetch_d64": lambda: check_attention_bwd_prefetch(B=1, H=2, Lq=452, Lkv=260, D=64, joint_layout=False),
-    "attn_bwd_split2_d64": lambda: check_attention_bwd_split2(B=2, H=3, Lq=452, Lkv=260, D=64, joint_layout=False),
+    "attn_bwd_split1_d128": lambda: check_attention_bwd_split1(B=1, H=2, Lq=300, Lkv=647, D=128, joint_layout=False),
+    "attn_bwd_split1_d64": lambda: check_attention_bwd_split1(B=2, H=3, Lq=452, Lkv=260, D=64, joint_layout=False),
+    "attn_bwd_noprefetch_d128": lambda: check_attention_bwd_noprefetch(B=1, H=2, Lq=300, Lkv=647, D=128, joint_layout=False),
+    "attn_bwd_noprefetch_d64": lambda: check_attention_bwd_noprefetch(B=1, H=2, Lq=452, Lkv=260, D=64, joint_layout=False),
     "cfg_flow_match_step": check_cfg_flow_match_step,
     "wan_denoise_fused": check_wan_denoise_fused,
     "wan_denoise_cached": check_wan_denoise_cached,
     "wan_dead_ref_skip": check_wan_dead_ref_skip,
 }
+
+# Checks of code that has not been on a GPU yet: run by `tools/gpu_diag.py --pending` in a development call, promoted into CHECKS (and so into
+# `pytest -m gpu`) once they have passed on a B200.  Empty: everything written in round 1 without GPU access passed its first hardware run.
+CHECKS_PENDING = {}

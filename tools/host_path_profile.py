@@ -98,6 +98,7 @@ def patch(vap, lib):
 
     ops._need_cuda_bf16 = need_bf16
     ops._need_cuda_f32 = need_f32
+    ops._need_cuda_float = lambda t, name: None
     ops._stream = lambda: 0
     if hasattr(ops, "_dev_check"):
         ops._dev_check = lambda *a, **k: None

@@ -47,6 +47,7 @@ SIGNATURES = {
     "vap_attention_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, _FLOAT_P, c_void_p, c_void_p, c_void_p, _FLOAT_P, c_int, c_int, c_int,
                                   c_int, c_int, c_void_p, c_float, c_void_p]),
     "vap_cfg_flow_match_step": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int64, c_int64, c_float, c_float, c_void_p]),
+    "vap_wan_modulation": (c_int, [c_void_p, c_int, c_void_p, c_int, _FLOAT_P, c_int64, c_int, c_int, c_int, c_void_p]),
     "vap_debug_set_attention_trace": (c_int, [c_void_p]),
     "vap_probe_umma": (c_int, [c_void_p, c_void_p, _FLOAT_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
 }

@@ -359,22 +359,17 @@ static int make_bwd_tmap(CUtensorMap* tm, const AttnTensor& t, int B, int H, int
     return make_tmap_bf16(tm, t.ptr, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
+// Developer switches, read per call.  Defaults = the fastest configuration measured on a B200 (H 40, J 16 384, D 128, tools/kernel_bench.py --bwd,
+// profiles/r02_pending_and_reference_checks.json): one elementwise set 628 TFLOP/s, two sets 661, two sets + S prefetch in the dQ kernel 678; all
+// three are parity-green (tests/gpu_checks.py attn_bwd_*).  VAP_ATTN_BWD_SPLIT=1 / VAP_ATTN_BWD_PREFETCH=0 select the simpler variants.
 static int bwd_prefetch_mode() {
-    static int mode = -1;
-    if (mode < 0) {
-        const char* e = getenv("VAP_ATTN_BWD_PREFETCH");
-        mode = (e && atoi(e) == 1) ? 1 : 0;
-    }
-    return mode;
+    const char* e = getenv("VAP_ATTN_BWD_PREFETCH");
+    return (e && atoi(e) == 0) ? 0 : 1;
 }
 
 static int bwd_split_mode() {
-    static int mode = -1;
-    if (mode < 0) {
-        const char* e = getenv("VAP_ATTN_BWD_SPLIT");
-        mode = (e && atoi(e) == 2) ? 2 : 1;
-    }
-    return mode;
+    const char* e = getenv("VAP_ATTN_BWD_SPLIT");
+    return (e && atoi(e) == 1) ? 1 : 2;
 }
 
 template <int D, int kSplit>
@@ -382,12 +377,9 @@ static int launch_bwd_d(const AttnBwdArgs& a, cudaStream_t stream) {
     using Cfg = BwdCfg<D>;
     static_assert(Cfg::kSmemBytes <= 232448, "shared memory budget");
     static_assert(8 * (2 * Cfg::kStages + 5) <= Cfg::kBarBytes, "barrier area");
-    static bool attr_set = false;
-    if (!attr_set) {
-        VAP_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<D, false, kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-        VAP_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<D, true, kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-        attr_set = true;
-    }
+    static bool opted_in[2][64] = {};
+    if (int rc = smem_opt_in(attn_bwd_kernel<D, false, kSplit>, Cfg::kSmemBytes, opted_in[0])) return rc;
+    if (int rc = smem_opt_in(attn_bwd_kernel<D, true, kSplit>, Cfg::kSmemBytes, opted_in[1])) return rc;
     // 1. delta = rowsum(dO o O)
     {
         const int64_t threads = static_cast<int64_t>(a.B) * a.H * a.Lq * (D / 8);

@@ -769,19 +769,6 @@ static bool attn_row_mode() {
     return e[0] == 'r';
 }
 
-// cudaFuncSetAttribute is per device: remember which devices have been opted in to the large dynamic shared memory (one flag per kernel
-// instantiation and device; a benign race — two threads may both set it)
-template <typename Kernel>
-static int attn_opt_in_smem(Kernel kernel, int bytes, bool (&done)[64]) {
-    int dev = 0;
-    VAP_CHECK_CUDA(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64 || !done[dev]) {
-        VAP_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-        if (dev >= 0 && dev < 64) done[dev] = true;
-    }
-    return 0;
-}
-
 template <int D, int CL, bool ROW>
 static int launch_attn_d(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const AttnParams& p, cudaStream_t stream) {
     using Cfg = AttnCfg<D>;
@@ -790,7 +777,7 @@ static int launch_attn_d(const CUtensorMap& tmQ, const CUtensorMap& tmK, const C
     auto kernel = ROW ? attn_fwd_row_kernel<D, CL> : attn_fwd_kernel<D, CL>;
     constexpr int threads = ROW ? kRowThreads : kAttnThreads;
     static bool opted_in[64] = {};
-    if (int rc = attn_opt_in_smem(kernel, Cfg::kSmemBytes, opted_in)) return rc;
+    if (int rc = smem_opt_in(kernel, Cfg::kSmemBytes, opted_in)) return rc;
     const unsigned q_blocks = static_cast<unsigned>((p.Lq + 2 * kBlockM - 1) / (2 * kBlockM));
     if (CL == 1) {
         const dim3 grid(q_blocks, p.H, p.B * p.kv_splits);

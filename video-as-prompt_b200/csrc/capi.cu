@@ -323,6 +323,13 @@ int vap_cfg_flow_match_step(const void* noise_cond, const void* noise_uncond, co
     return launch_cfg_flow_match_step(p, static_cast<cudaStream_t>(stream));
 }
 
+int vap_wan_modulation(const void* table, int table_is_f32, const void* temb, int temb_is_f32, float* out, int64_t batch, int chunks, int d,
+                       int plus_one_mask, void* stream) {
+    VAP_REQUIRE(table && temb && out, "vap_wan_modulation: null tensor");
+    return launch_wan_modulation(table, table_is_f32, temb, temb_is_f32, out, batch, chunks, d, static_cast<unsigned>(plus_one_mask),
+                                 static_cast<cudaStream_t>(stream));
+}
+
 int vap_debug_set_attention_trace(void* device_buffer) {
     g_attn_trace = static_cast<long long*>(device_buffer);
     return 0;

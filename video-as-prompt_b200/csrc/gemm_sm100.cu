@@ -468,11 +468,8 @@ template <int BN, int MT>
 static int launch_gemm_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams p, cudaStream_t stream) {
     using Cfg = GemmCfg<BN, MT>;
     static_assert(Cfg::kSmemBytes <= 232448, "shared memory budget");
-    static bool attr_set = false;
-    if (!attr_set) {
-        VAP_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, MT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-        attr_set = true;
-    }
+    static bool opted_in[1][64] = {};
+    if (int rc = smem_opt_in(gemm_bf16_kernel<BN, MT, 1>, Cfg::kSmemBytes, opted_in[0])) return rc;
     p.m_blocks = (p.M + kBM * MT - 1) / (kBM * MT);
     p.n_blocks = (p.N + BN - 1) / BN;
     const int tiles = p.m_blocks * p.n_blocks;
@@ -485,8 +482,11 @@ static int launch_gemm_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmPa
 // 128 x 256 tiles in clusters of two CTAs sharing the W tile by TMA multicast
 static int launch_gemm_cluster(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams p, cudaStream_t stream) {
     using Cfg = GemmCfg<256, 1>;
-    static int max_clusters = -1;
-    if (max_clusters < 0) {
+    static int max_clusters_dev[64];  // per device: 0 = not probed yet (the smem opt-in and the occupancy are per-device facts)
+    int dev = 0;
+    VAP_CHECK_CUDA(cudaGetDevice(&dev));
+    int& max_clusters = max_clusters_dev[dev & 63];
+    if (max_clusters == 0) {
         VAP_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<256, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         cudaLaunchConfig_t probe{};
         probe.gridDim = dim3(static_cast<unsigned>(sm_count() / 2 * 2));
@@ -498,7 +498,7 @@ static int launch_gemm_cluster(const CUtensorMap& tmA, const CUtensorMap& tmB, G
         probe.attrs = &attr, probe.numAttrs = 1;
         int n = 0;
         VAP_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm_bf16_kernel<256, 1, 2>, &probe));
-        max_clusters = n;
+        max_clusters = n > 0 ? n : -1;
     }
     VAP_REQUIRE(max_clusters > 0, "gemm_bf16: no 2-CTA cluster fits on this device");
     p.m_blocks = (p.M + kBM - 1) / kBM;
@@ -523,7 +523,10 @@ static int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, Gemm
     using Cfg = GemmPairCfg;
     static_assert(Cfg::kSmemBytes <= 232448, "shared memory budget");
     static_assert(2 * Cfg::kStages + 5 <= 32, "barrier area");
-    static int max_clusters = -1;
+    static int max_clusters_dev[64];  // per device: 0 = not probed yet
+    int dev = 0;
+    VAP_CHECK_CUDA(cudaGetDevice(&dev));
+    int& max_clusters = max_clusters_dev[dev & 63];
     cudaLaunchConfig_t cfg{};
     cfg.blockDim = dim3(kGemmThreads);
     cfg.dynamicSmemBytes = Cfg::kSmemBytes;
@@ -532,12 +535,12 @@ static int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, Gemm
     attr.id = cudaLaunchAttributeClusterDimension;
     attr.val.clusterDim.x = 2, attr.val.clusterDim.y = 1, attr.val.clusterDim.z = 1;
     cfg.attrs = &attr, cfg.numAttrs = 1;
-    if (max_clusters < 0) {
+    if (max_clusters == 0) {
         VAP_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         cfg.gridDim = dim3(static_cast<unsigned>(sm_count() / 2 * 2));
         int n = 0;
         VAP_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm_bf16_pair_kernel, &cfg));
-        max_clusters = n;
+        max_clusters = n > 0 ? n : -1;
     }
     VAP_REQUIRE(max_clusters > 0, "gemm_bf16: no 2-CTA cluster fits on this device");
     p.m_blocks = (p.M + kBM - 1) / kBM;

@@ -144,6 +144,187 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (MAXV <= 5) ? 4 : 3) adal
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Staged variants for wide rows (d = 256 NV): persistent CTAs, one per SM, eight warps; every warp owns a private ring of kStages
+// row buffers in shared memory that it fills itself with cp.async.bulk (one bulk copy per token row, completion on the warp's own
+// mbarriers) — so the loads of row k+1 are in flight while row k is being reduced, normalised and stored, with no dependence between
+// warps and ~80 KB of reads outstanding per SM all the time.  The per-channel fp32 vectors (modulation / affine / norm weights) are
+// staged in shared memory ONCE per CTA instead of being re-read through L1 for every row.  The row itself is pulled from shared
+// memory into registers once (NV 16-byte vectors per lane) and the mean / variance / normalise passes run on the registers.
+// The CTAs of a launch never straddle a batch: CTA (b, c) works on the rows of batch b only, so its staged modulation vectors hold.
+// ------------------------------------------------------------------------------------------
+constexpr int kStagedWarps = 8;
+
+__device__ __forceinline__ void bulk_load_row(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4_u32(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
+struct StagedRows {  // the contiguous row range [r0, r1) of one batch this CTA works on
+    int64_t r0, r1, batch;
+    __device__ __forceinline__ StagedRows(int64_t rows, int64_t rows_per_batch, int ctas_per_batch) {
+        batch = blockIdx.x / ctas_per_batch;
+        const int c = blockIdx.x - static_cast<int>(batch) * ctas_per_batch;
+        const int64_t b0 = batch * rows_per_batch;
+        const int64_t nb = (rows - b0 < rows_per_batch) ? rows - b0 : rows_per_batch;
+        const int64_t chunk = (nb + ctas_per_batch - 1) / ctas_per_batch;
+        r0 = b0 + c * chunk;
+        r1 = r0 + chunk < b0 + nb ? r0 + chunk : b0 + nb;
+    }
+};
+
+template <int NV, int kStages>
+__global__ void __launch_bounds__(kStagedWarps * 32, 1) adaln_layernorm_staged_kernel(LnParams p, int ctas_per_batch) {
+    extern __shared__ __align__(128) uint8_t ln_smem[];
+    constexpr int d = 256 * NV;
+    constexpr uint32_t row_bytes = d * 2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const StagedRows rg(p.rows, p.rows_per_batch, ctas_per_batch);
+    // layout: [fp32 vectors that exist: (scale1p | shift) (ln_w | ln_b)] [ring: warp x stage x row] [mbarriers]
+    const uint32_t n_vec = (p.scale1p ? 2u : 0u) + (p.ln_w ? 2u : 0u);
+    float* vec_mod = reinterpret_cast<float*>(ln_smem);                 // scale1p, shift
+    float* vec_aff = vec_mod + (p.scale1p ? 2 * d : 0);                 // ln_w, ln_b
+    const uint32_t ring = smem_u32(ln_smem) + n_vec * d * sizeof(float) + static_cast<uint32_t>(warp) * kStages * row_bytes;
+    const uint32_t bars = smem_u32(ln_smem) + n_vec * d * sizeof(float) + kStagedWarps * kStages * row_bytes + static_cast<uint32_t>(warp) * kStages * 8u;
+    const float* srcs[4] = {p.scale1p ? p.scale1p + rg.batch * p.mod_stride : nullptr, p.shift ? p.shift + rg.batch * p.mod_stride : nullptr, p.ln_w, p.ln_b};
+    float* dsts[4] = {vec_mod, vec_mod + d, vec_aff, vec_aff + d};
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+        if (srcs[t])
+            for (int c = threadIdx.x * 4; c < d; c += kStagedWarps * 32 * 4) *reinterpret_cast<float4*>(dsts[t] + c) = *reinterpret_cast<const float4*>(srcs[t] + c);
+    if (lane == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(bars + 8u * s, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    const int64_t first = rg.r0 + warp;
+    auto issue = [&](int64_t k) {  // row first + 8 k into stage k % kStages
+        const int64_t r = first + kStagedWarps * k;
+        if (r < rg.r1 && lane == 0) {
+            const uint32_t st = static_cast<uint32_t>(k % kStages);
+            mbar_arrive_expect_tx(bars + 8u * st, row_bytes);
+            bulk_load_row(ring + st * row_bytes, p.x + r * p.x_stride, row_bytes, bars + 8u * st);
+        }
+    };
+#pragma unroll
+    for (int k = 0; k < kStages - 1; ++k) issue(k);
+    const float inv_d = 1.f / static_cast<float>(d);
+    for (int64_t k = 0;; ++k) {
+        const int64_t row = first + kStagedWarps * k;
+        if (row >= rg.r1) break;
+        __syncwarp();  // every lane has finished reading the stage that is refilled next
+        issue(k + kStages - 1);
+        const uint32_t st = static_cast<uint32_t>(k % kStages);
+        mbar_wait(bars + 8u * st, static_cast<uint32_t>(k / kStages) & 1u);
+        uint4 raw[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) raw[i] = ld_shared_v4_u32(ring + st * row_bytes + (lane + 32 * i) * 16);
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const uint32_t* u = reinterpret_cast<const uint32_t*>(&raw[i]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = bf16x2_to_float2(u[j]);
+                sum += f.x + f.y;
+            }
+        }
+        const float mean = warp_sum(sum) * inv_d;
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const uint32_t* u = reinterpret_cast<const uint32_t*>(&raw[i]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = bf16x2_to_float2(u[j]);
+                const float a = f.x - mean, b = f.y - mean;
+                sq += a * a + b * b;
+            }
+        }
+        const float rstd = rsqrtf(warp_sum(sq) * inv_d + p.eps);
+        __nv_bfloat16* orow = p.out + row * p.out_stride;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = 8 * (lane + 32 * i);
+            const uint32_t* u = reinterpret_cast<const uint32_t*>(&raw[i]);
+            float y[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = bf16x2_to_float2(u[j]);
+                y[2 * j] = (f.x - mean) * rstd;
+                y[2 * j + 1] = (f.y - mean) * rstd;
+            }
+            if (p.ln_w) {
+                const float4 w0 = *reinterpret_cast<const float4*>(vec_aff + c), w1 = *reinterpret_cast<const float4*>(vec_aff + c + 4);
+                const float4 b0 = *reinterpret_cast<const float4*>(vec_aff + d + c), b1 = *reinterpret_cast<const float4*>(vec_aff + d + c + 4);
+                const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) y[j] = y[j] * w[j] + b[j];
+            }
+            if (p.cog_rounding) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) y[j] = bf16_round(y[j]);
+            }
+            if (p.scale1p) {
+                const float4 s0 = *reinterpret_cast<const float4*>(vec_mod + c), s1 = *reinterpret_cast<const float4*>(vec_mod + c + 4);
+                const float4 h0 = *reinterpret_cast<const float4*>(vec_mod + d + c), h1 = *reinterpret_cast<const float4*>(vec_mod + d + c + 4);
+                const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                const float h[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+                if (p.cog_rounding) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) y[j] = bf16_round(y[j] * sc[j]) + h[j];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) y[j] = y[j] * sc[j] + h[j];
+                }
+            }
+            uint4 o;
+            o.x = pack_bf16x2(y[0], y[1]);
+            o.y = pack_bf16x2(y[2], y[3]);
+            o.z = pack_bf16x2(y[4], y[5]);
+            o.w = pack_bf16x2(y[6], y[7]);
+            st_v4(orow + c, o);
+        }
+    }
+}
+
+// Launch plan of a staged kernel: batches x CTAs per batch (about one CTA per SM in total), or 0 CTAs when the shape does not qualify.
+static int staged_ctas_per_batch(int64_t rows, int64_t rows_per_batch, int64_t* nbatch) {
+    const int64_t rpb = rows_per_batch > 0 && rows_per_batch < rows ? rows_per_batch : rows;
+    *nbatch = (rows + rpb - 1) / rpb;
+    if (*nbatch > 64 || rows < 16 * kStagedWarps * 8) return 0;  // few rows: the per-CTA staging of the vectors would not amortise
+    int per = static_cast<int>(sm_count() / *nbatch);
+    if (per < 1) per = 1;
+    const int64_t max_useful = (rpb + kStagedWarps * 4 - 1) / (kStagedWarps * 4);  // at least ~4 rows per warp
+    if (per > max_useful) per = static_cast<int>(max_useful);
+    return per;
+}
+
+template <int NV, int kStages>
+static int launch_ln_staged(const LnParams& p, int ctas_per_batch, int64_t nbatch, cudaStream_t stream) {
+    const int n_vec = (p.scale1p ? 2 : 0) + (p.ln_w ? 2 : 0);
+    const int smem = n_vec * 256 * NV * 4 + kStagedWarps * kStages * 256 * NV * 2 + kStagedWarps * kStages * 8;
+    if (smem > 232448) return 1;  // does not fit (e.g. d = 5120 with affine AND modulation): the caller takes the register kernel
+    static bool opted_in[64] = {};
+    if (int rc = smem_opt_in(adaln_layernorm_staged_kernel<NV, kStages>, 232448, opted_in)) return rc;
+    adaln_layernorm_staged_kernel<NV, kStages><<<static_cast<unsigned>(nbatch * ctas_per_batch), kStagedWarps * 32, smem, stream>>>(p, ctas_per_batch);
+    VAP_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static bool staged_disabled() {
+    const char* e = getenv("VAP_NORM_STAGED");
+    return e && e[0] == '0';
+}
+
 int launch_adaln_layernorm(const LnParams& p, cudaStream_t stream) {
     VAP_REQUIRE(p.d % 8 == 0 && p.d >= 8 && p.d <= 8192, "adaln_layernorm: d=%d must be a multiple of 8 and <= 8192", p.d);
     VAP_REQUIRE(p.x_stride % 8 == 0 && p.out_stride % 8 == 0, "adaln_layernorm: row strides must be multiples of 8 elements");
@@ -151,6 +332,17 @@ int launch_adaln_layernorm(const LnParams& p, cudaStream_t stream) {
     VAP_REQUIRE((p.scale1p == nullptr) == (p.shift == nullptr), "adaln_layernorm: scale1p and shift must both be given or both null");
     if (p.rows == 0) return 0;
     const int nvec = p.d / 8;
+    if ((p.d == 5120 || p.d == 4096 || p.d == 3072) && !staged_disabled() && (reinterpret_cast<uintptr_t>(p.x) & 15) == 0) {
+        int64_t nbatch = 1;
+        LnParams q = p;
+        if (!p.scale1p || p.mod_stride == 0 || p.rows_per_batch <= 0) q.rows_per_batch = p.rows;  // one set of vectors for all rows
+        const int per = staged_ctas_per_batch(q.rows, q.rows_per_batch, &nbatch);
+        if (per > 0) {
+            const int rc = p.d == 5120 ? launch_ln_staged<20, 2>(q, per, nbatch, stream)
+                         : p.d == 4096 ? launch_ln_staged<16, 2>(q, per, nbatch, stream) : launch_ln_staged<12, 3>(q, per, nbatch, stream);
+            if (rc <= 0) return rc;
+        }
+    }
     const dim3 block(kWarpsPerBlock * 32);
     if (nvec <= 32 * 8) {  // d <= 2048: one warp per row
         const unsigned grid = static_cast<unsigned>((p.rows + kWarpsPerBlock - 1) / kWarpsPerBlock);
@@ -332,6 +524,125 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (MAXV <= 5) ? 4 : 3) qk_n
     }
 }
 
+
+// Staged variant of the Wan mode (RMSNorm across all heads + RoPE, in place, no scatter): same structure as
+// adaln_layernorm_staged_kernel — one work item = (token row, q or k), a private bulk-copy ring per warp, the two norm-weight vectors
+// staged in shared memory once per CTA.  Lane l always owns channels 8 l .. 8 l + 7 of a head (256 i mod D == 0), so its four
+// (cos, sin) pairs are one float4 each per row.
+template <int NV, int kStages>
+__global__ void __launch_bounds__(kStagedWarps * 32, 1) qk_norm_rope_staged_kernel(QkParams p, int ctas_per_batch) {
+    extern __shared__ __align__(128) uint8_t qk_smem[];
+    constexpr int d = 256 * NV;
+    constexpr uint32_t row_bytes = d * 2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_which = p.k ? 2 : 1;
+    const StagedRows rg(p.rows, p.rows_per_batch, ctas_per_batch);
+    float* vec = reinterpret_cast<float*>(qk_smem);  // wq | wk
+    const uint32_t ring = smem_u32(qk_smem) + 2u * d * sizeof(float) + static_cast<uint32_t>(warp) * kStages * row_bytes;
+    const uint32_t bars = smem_u32(qk_smem) + 2u * d * sizeof(float) + kStagedWarps * kStages * row_bytes + static_cast<uint32_t>(warp) * kStages * 8u;
+    for (int c = threadIdx.x * 4; c < d; c += kStagedWarps * 32 * 4) {
+        *reinterpret_cast<float4*>(vec + c) = *reinterpret_cast<const float4*>(p.wq + c);
+        if (p.k) *reinterpret_cast<float4*>(vec + d + c) = *reinterpret_cast<const float4*>(p.wk + c);
+    }
+    if (lane == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(bars + 8u * s, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    const int64_t n_items = (rg.r1 - rg.r0) * n_which;  // item t of this CTA: row r0 + t / n_which, tensor t % n_which
+    auto item_ptr = [&](int64_t t) -> __nv_bfloat16* {
+        const int64_t row = rg.r0 + t / n_which;
+        return ((t % n_which) == 0 ? p.q : p.k) + row * p.row_stride;
+    };
+    auto issue = [&](int64_t k) {
+        const int64_t t = warp + kStagedWarps * k;
+        if (t < n_items && lane == 0) {
+            const uint32_t st = static_cast<uint32_t>(k % kStages);
+            mbar_arrive_expect_tx(bars + 8u * st, row_bytes);
+            bulk_load_row(ring + st * row_bytes, item_ptr(t), row_bytes, bars + 8u * st);
+        }
+    };
+#pragma unroll
+    for (int k = 0; k < kStages - 1; ++k) issue(k);
+    const int ch = (8 * lane) % p.head_dim;  // channel offset inside the head, the same for every vector of this lane
+    const float inv_d = 1.f / static_cast<float>(d);
+    for (int64_t k = 0;; ++k) {
+        const int64_t t = warp + kStagedWarps * k;
+        if (t >= n_items) break;
+        __syncwarp();
+        issue(k + kStages - 1);
+        const int64_t row = rg.r0 + t / n_which;
+        const int which = static_cast<int>(t % n_which);
+        const int64_t pos = row - rg.batch * p.rows_per_batch;
+        const bool rotate = (p.cos != nullptr) && pos >= p.rope_row0 && (pos - p.rope_row0) < p.rope_rows;
+        float4 c4 = make_float4(1.f, 1.f, 1.f, 1.f), s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rotate) {
+            const int64_t off = (pos - p.rope_row0) * (p.head_dim >> 1) + (ch >> 1);
+            c4 = *reinterpret_cast<const float4*>(p.cos + off);
+            s4 = *reinterpret_cast<const float4*>(p.sin + off);
+        }
+        const float cs[4] = {c4.x, c4.y, c4.z, c4.w}, sn[4] = {s4.x, s4.y, s4.z, s4.w};
+        const uint32_t st = static_cast<uint32_t>(k % kStages);
+        mbar_wait(bars + 8u * st, static_cast<uint32_t>(k / kStages) & 1u);
+        uint4 raw[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) raw[i] = ld_shared_v4_u32(ring + st * row_bytes + (lane + 32 * i) * 16);
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const uint32_t* u = reinterpret_cast<const uint32_t*>(&raw[i]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = bf16x2_to_float2(u[j]);
+                sq += f.x * f.x + f.y * f.y;
+            }
+        }
+        const float rs = rsqrtf(warp_sum(sq) * inv_d + p.eps);
+        __nv_bfloat16* xr = item_ptr(t);
+        const float* w = vec + which * d;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = 8 * (lane + 32 * i);
+            const uint32_t* u = reinterpret_cast<const uint32_t*>(&raw[i]);
+            const float4 w0 = *reinterpret_cast<const float4*>(w + c), w1 = *reinterpret_cast<const float4*>(w + c + 4);
+            const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+            float y[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = bf16x2_to_float2(u[j]);
+                y[2 * j] = bf16_round(bf16_round(f.x * rs) * ww[2 * j]);
+                y[2 * j + 1] = bf16_round(bf16_round(f.y * rs) * ww[2 * j + 1]);
+            }
+            if (rotate) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float xr_ = y[2 * j], xi_ = y[2 * j + 1];
+                    y[2 * j] = xr_ * cs[j] - xi_ * sn[j];
+                    y[2 * j + 1] = xi_ * cs[j] + xr_ * sn[j];
+                }
+            }
+            uint4 o;
+            o.x = pack_bf16x2(y[0], y[1]);
+            o.y = pack_bf16x2(y[2], y[3]);
+            o.z = pack_bf16x2(y[4], y[5]);
+            o.w = pack_bf16x2(y[6], y[7]);
+            st_v4(xr + c, o);
+        }
+    }
+}
+
+template <int NV, int kStages>
+static int launch_qk_staged(const QkParams& p, int ctas_per_batch, int64_t nbatch, cudaStream_t stream) {
+    constexpr int smem = 2 * 256 * NV * 4 + kStagedWarps * kStages * 256 * NV * 2 + kStagedWarps * kStages * 8;
+    static_assert(smem <= 232448, "shared memory budget");
+    static bool opted_in[64] = {};
+    if (int rc = smem_opt_in(qk_norm_rope_staged_kernel<NV, kStages>, smem, opted_in)) return rc;
+    qk_norm_rope_staged_kernel<NV, kStages><<<static_cast<unsigned>(nbatch * ctas_per_batch), kStagedWarps * 32, smem, stream>>>(p, ctas_per_batch);
+    VAP_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int launch_qk_norm_rope(const QkParams& p, int cog_mode, cudaStream_t stream) {
     const int d = p.heads * p.head_dim;
     VAP_REQUIRE(p.head_dim == 64 || p.head_dim == 128 || p.head_dim == 32 || p.head_dim == 256,
@@ -347,6 +658,14 @@ int launch_qk_norm_rope(const QkParams& p, int cog_mode, cudaStream_t stream) {
         VAP_REQUIRE(p.nsplit <= 8 && p.heads % p.nsplit == 0, "qkv_scatter: %d heads are not divisible by %d ranks (max 8)", p.heads, p.nsplit);
         VAP_REQUIRE(p.k && p.v, "qkv_scatter: q, k and v are required");
         for (int s = 0; s < p.nsplit; ++s) VAP_REQUIRE(p.dst[s] && (reinterpret_cast<uintptr_t>(p.dst[s]) & 15) == 0, "qkv_scatter: bad destination %d", s);
+    }
+    if (!cog_mode && p.nsplit == 0 && (d == 5120 || d == 4096) && 256 % p.head_dim == 0 && !staged_disabled() &&
+        (reinterpret_cast<uintptr_t>(p.q) & 15) == 0 && (!p.k || (reinterpret_cast<uintptr_t>(p.k) & 15) == 0)) {
+        int64_t nbatch = 1;
+        QkParams q = p;
+        if (p.rows_per_batch <= 0 || p.rows_per_batch > p.rows) q.rows_per_batch = p.rows;
+        const int per = staged_ctas_per_batch(q.rows, q.rows_per_batch, &nbatch);
+        if (per > 0) return d == 5120 ? launch_qk_staged<20, 2>(q, per, nbatch, stream) : launch_qk_staged<16, 2>(q, per, nbatch, stream);
     }
     const int64_t items = p.rows * (p.nsplit > 0 ? 3 : (p.k ? 2 : 1));
     const dim3 block(kWarpsPerBlock * 32);
@@ -460,5 +779,42 @@ int launch_cfg_flow_match_step(const StepParams& p, cudaStream_t stream) {
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// W1: the adaLN modulation of a Wan block, (scale_shift_table[1, C, d] + temb[B, C, d].float()).chunk(C) with the "+ 1" of the two scale
+// chunks folded in (transformer_wan_mot.py:606-616, 620-622, 680-689) — one launch instead of three eager ones per stream and block.
+//   out[b, c, :] = float(table[c, :]) + float(temb[b, c, :]) (+ 1 when bit c of plus_one_mask is set)        fp32, like the reference
+// table / temb are bf16 or fp32 (a from_pretrained model keeps scale_shift_table in fp32, a .to(bfloat16) one does not).
+// ------------------------------------------------------------------------------------------------------------------------
+template <bool kTableF32, bool kTembF32>
+__global__ void __launch_bounds__(256) wan_modulation_kernel(const void* table, const void* temb, float* out, int64_t batch, int chunks, int d, unsigned plus_one_mask) {
+    const int64_t per = static_cast<int64_t>(chunks) * d;
+    const int64_t total = batch * per;
+    for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t e = idx % per;
+        const int c = static_cast<int>(e / d);
+        const float t = kTableF32 ? static_cast<const float*>(table)[e] : __bfloat162float(static_cast<const __nv_bfloat16*>(table)[e]);
+        const float m = kTembF32 ? static_cast<const float*>(temb)[idx] : __bfloat162float(static_cast<const __nv_bfloat16*>(temb)[idx]);
+        float v = __fadd_rn(t, m);
+        if ((plus_one_mask >> c) & 1u) v = __fadd_rn(1.f, v);
+        out[idx] = v;
+    }
+}
+
+int launch_wan_modulation(const void* table, int table_is_f32, const void* temb, int temb_is_f32, float* out, int64_t batch, int chunks, int d,
+                          unsigned plus_one_mask, cudaStream_t stream) {
+    VAP_REQUIRE(batch >= 0 && chunks > 0 && chunks <= 32 && d > 0, "wan_modulation: bad shape batch=%lld chunks=%d d=%d", static_cast<long long>(batch), chunks, d);
+    const int64_t total = batch * chunks * d;
+    if (total == 0) return 0;
+    const unsigned blocks = static_cast<unsigned>((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+    if (table_is_f32) {
+        if (temb_is_f32) wan_modulation_kernel<true, true><<<blocks, 256, 0, stream>>>(table, temb, out, batch, chunks, d, plus_one_mask);
+        else wan_modulation_kernel<true, false><<<blocks, 256, 0, stream>>>(table, temb, out, batch, chunks, d, plus_one_mask);
+    } else {
+        if (temb_is_f32) wan_modulation_kernel<false, true><<<blocks, 256, 0, stream>>>(table, temb, out, batch, chunks, d, plus_one_mask);
+        else wan_modulation_kernel<false, false><<<blocks, 256, 0, stream>>>(table, temb, out, batch, chunks, d, plus_one_mask);
+    }
+    VAP_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
 
 }  // namespace vap

@@ -156,11 +156,8 @@ int launch_probe_umma(const __nv_bfloat16* A, const __nv_bfloat16* B, ProbeParam
         if (make_tmap_bf16(&tmB, B, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return -3;
     }
     const int smem = 2 * 16384 + 65536 + 1024 + 64;
-    static bool attr_set = false;
-    if (!attr_set) {
-        VAP_CHECK_CUDA(cudaFuncSetAttribute(probe_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
-    }
+    static bool opted_in[1][64] = {};
+    if (int rc = smem_opt_in(probe_umma_kernel, smem, opted_in[0])) return rc;
     probe_umma_kernel<<<1, 128, smem, stream>>>(tmA, tmB, p);
     VAP_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -37,6 +37,20 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
                    const uint32_t* box, CUtensorMapSwizzle swizzle);
 int sm_count();
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-DEVICE setting: remember, per kernel instantiation, which devices have been
+// opted in (a process may drive several GPUs).  The only state the library keeps besides the SM-count cache and the driver entry point;
+// a race between two threads merely sets the attribute twice.
+template <typename Kernel>
+inline int smem_opt_in(Kernel kernel, int bytes, bool (&done)[64]) {
+    int dev = 0;
+    VAP_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !done[dev]) {
+        VAP_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        if (dev >= 0 && dev < 64) done[dev] = true;
+    }
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // small helpers
 // ------------------------------------------------------------------------------------------

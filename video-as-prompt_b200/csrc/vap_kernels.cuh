@@ -122,6 +122,10 @@ struct StepParams {
 };
 int launch_cfg_flow_match_step(const StepParams& p, cudaStream_t stream);
 
+// W1: out[b, c, :] = float(table[c, :]) + float(temb[b, c, :]) (+ 1 for the chunks in plus_one_mask), fp32
+int launch_wan_modulation(const void* table, int table_is_f32, const void* temb, int temb_is_f32, float* out, int64_t batch, int chunks, int d,
+                          unsigned plus_one_mask, cudaStream_t stream);
+
 struct ProbeParams {
     const __nv_bfloat16* A;  // [128, K] row-major (used directly when a_in_tmem)
     float* Dout;             // [128, N]

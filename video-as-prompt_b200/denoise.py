@@ -34,15 +34,16 @@ def flow_match_step(model_output: torch.Tensor, sample: torch.Tensor, sigma: tor
 @torch.no_grad()
 def wan_denoise(model, latents: torch.Tensor, condition: torch.Tensor, latents_ref: torch.Tensor, condition_ref: torch.Tensor, cond_kwargs: dict,
                 uncond_kwargs: Optional[dict], num_steps: int, shift: float = 3.0, guidance_scale: float = 5.0, dtype=torch.bfloat16,
-                fused_step: bool = False, cache_context: bool = True, batch_cfg: bool = False) -> torch.Tensor:
+                fused_step: bool = True, cache_context: bool = True, batch_cfg: bool = False) -> torch.Tensor:
     """Run `num_steps` denoise steps of the Wan VAP pipeline loop on `model` (ours or the reference's after install()).
     cache_context: the text / CLIP context embeddings and every block's cross-attention K / V are the same at every step and in both
     guidance passes; compute them once per loop (wan.context_cache; identical results — the cached tensors are what would be recomputed).
     batch_cfg: run the conditional and the unconditional pass of a step as ONE B = 2 forward (what the CogVideoX pipeline does,
     pipeline_cogvideox_image2video_mot.py:972-1001) instead of the Wan pipeline's two sequential B = 1 forwards (:815-861): every weight
     is read once per step and the per-stream GEMMs see twice the rows.  Same arithmetic per sample.
-    fused_step: classifier-free guidance + scheduler update in ONE kernel (ops.cfg_flow_match_step) instead of seven torch
-    elementwise launches — same rounding points (opt-in until its GPU parity check has run, tests/gpu_checks.py)."""
+    fused_step (default): classifier-free guidance + scheduler update in ONE kernel (ops.cfg_flow_match_step) instead of seven torch
+    elementwise launches — same rounding points, bit-exact with the torch expressions on a B200 (tests/gpu_checks.py cfg_flow_match_step,
+    wan_denoise_fused); fused_step=False keeps the torch expressions."""
     dev = latents.device
     timesteps, sigmas = flow_match_schedule(num_steps, shift, device=dev)
     if fused_step:

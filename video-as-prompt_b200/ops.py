@@ -43,6 +43,14 @@ def _need_cuda_bf16(t: torch.Tensor, name: str) -> None:
         raise TypeError(f"{name} must be torch.bfloat16, got {t.dtype}")
 
 
+def _need_cuda_float(t: torch.Tensor, name: str) -> None:
+    """A contiguous CUDA tensor that is either bf16 or fp32 (parameters a from_pretrained model keeps in fp32)."""
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise VapError(f"{name} must be a CUDA tensor: the VAP kernels are CUDA-only (sm_100a); there is no CPU fallback")
+    if t.dtype not in (torch.float32, torch.bfloat16) or not t.is_contiguous():
+        raise TypeError(f"{name} must be a contiguous float32 or bfloat16 tensor, got {t.dtype}")
+
+
 def _need_cuda_f32(t: Optional[torch.Tensor], name: str) -> int:
     if t is None:
         return 0
@@ -176,7 +184,7 @@ def attention_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, o: torch.Te
                   scale: Optional[float] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """Gradients of `attention` (vap_attention_bwd): q / o / dout [B,H,Lq,D], k / v [B,H,Lkv,D] (any batch/head/token strides, D
     contiguous), lse [B,H,Lq] fp32 from ``attention(..., return_lse=True)``.  Returns dq, dk, dv with the logical shapes of q, k, v,
-    laid out token-major like the forward's output.  Pending its first GPU run (tests/gpu_checks.py:CHECKS_PENDING)."""
+    laid out token-major like the forward's output.  Parity on a B200: tests/gpu_checks.py attn_bwd_* (max-abs relative 2-5e-3 per gradient)."""
     for t, n in ((q, "q"), (k, "k"), (v, "v"), (o, "o"), (dout, "dout")):
         _need_cuda_bf16(t, n)
         if t.dim() != 4 or t.stride(-1) != 1:
@@ -431,6 +439,20 @@ def cfg_flow_match_step(noise_cond: torch.Tensor, noise_uncond: Optional[torch.T
     rc = _lib.load().vap_cfg_flow_match_step(noise_cond.data_ptr(), noise_uncond.data_ptr() if noise_uncond is not None else 0, sample.data_ptr(),
                                              int(sample.dtype == torch.float32), out.data_ptr(), B, inner, obs, float(guidance_scale), float(dt), _stream())
     _lib.check(rc, "vap_cfg_flow_match_step")
+    return out
+
+
+def wan_modulation(table: torch.Tensor, temb: torch.Tensor, plus_one_mask: int = 0b010010) -> torch.Tensor:
+    """(table[1, C, d] + temb[B, C, d].float()) with 1 added to the chunks in `plus_one_mask`, fp32 [B, C, d] (vap_wan_modulation): the six
+    adaLN vectors of a Wan block — shift, 1 + scale, gate, c_shift, 1 + c_scale, c_gate — in one launch."""
+    _need_cuda_float(table, "table"), _need_cuda_float(temb, "temb")
+    C, d = table.shape[-2], table.shape[-1]
+    if table.numel() != C * d or temb.dim() != 3 or temb.shape[1:] != (C, d):
+        raise ValueError(f"table {tuple(table.shape)} / temb {tuple(temb.shape)}: expected [1, C, d] and [B, C, d]")
+    out = torch.empty(temb.shape, dtype=torch.float32, device=temb.device)
+    rc = _lib.load().vap_wan_modulation(table.data_ptr(), int(table.dtype == torch.float32), temb.data_ptr(), int(temb.dtype == torch.float32), out.data_ptr(),
+                                        temb.shape[0], C, d, int(plus_one_mask), _stream())
+    _lib.check(rc, "vap_wan_modulation")
     return out
 
 

@@ -282,9 +282,7 @@ def _sp_p2p(x: torch.Tensor, rows: int, heads: int, head_dim: int):
 # ----------------------------------------------------------------------------------------------
 def _modulation(table: torch.Tensor, temb: torch.Tensor):
     """(scale_shift_table + temb.float()).chunk(6, dim=1) (:606-608) -> fp32 [B,1,d] views; scale chunks come back as 1+scale."""
-    mod = table + temb.float()  # fresh fp32 [B,6,d]
-    mod[:, 1] += 1  # (1 + scale_msa), fp32 like the reference
-    mod[:, 4] += 1  # (1 + c_scale_msa)
+    mod = ops.wan_modulation(table.detach(), temb.contiguous())  # fp32 [B,6,d]: table + temb.float(), + 1 on the two scale chunks — one launch
     shift, scale1p, gate, c_shift, c_scale1p, c_gate = mod.chunk(6, dim=1)  # views sharing one batch stride
     return shift, scale1p, gate, c_shift, c_scale1p, c_gate
 
