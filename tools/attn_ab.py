@@ -49,6 +49,7 @@ def main():
     ap.add_argument("--rounds", type=int, default=2)
     ap.add_argument("--shapes", default="wan,cog")
     ap.add_argument("--only", default="", help="comma list of library names (default: all)")
+    ap.add_argument("--cl", default="0", help="comma list of VAP_ATTN_CLUSTER values to run (0 = no cluster, 2 = K/V multicast pairs)")
     a = ap.parse_args()
     libs = {"intree": os.path.join(ROOT, "video-as-prompt_b200", "libvap_b200.so")}
     for f in sorted(glob.glob(os.path.join(ROOT, "build_variants", "libvap_*.so"))):
@@ -57,9 +58,9 @@ def main():
         libs = {k: v for k, v in libs.items() if k in a.only.split(",")}
     variants = []
     for name in libs:
-        modes = ["lane16", "row"] if name == "intree" else ["row"]
+        modes = ["row"] if name.startswith("row") else ["lane16"] if name.startswith("l16") else ["lane16", "row"]
         for m in modes:
-            for cl in ("0", "2"):
+            for cl in a.cl.split(","):
                 variants.append((name, m, cl))
     res = {}
     data = {}

@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--only", default="")
     ap.add_argument("--timeout", type=int, default=180)
     ap.add_argument("--pending", action="store_true")
+    ap.add_argument("--stop-on-fail", action="store_true", help="stop at the first failing check (a trapping kernel costs its whole watchdog time per check)")
     ap.add_argument("--reference", action="store_true", help="run tests/ref_gpu_checks.CHECKS (parity against the staged reference on the GPU)")
     a = ap.parse_args()
     if a.check:
@@ -61,6 +62,8 @@ def main():
             open(os.path.join(OUT, f"diag_{n}.log"), "w").write((e.stdout or b"").decode(errors="replace") + (e.stderr or b"").decode(errors="replace"))
         summary.append(rec)
         print(json.dumps(rec), flush=True)
+        if a.stop_on_fail and not rec["ok"]:
+            break
     json.dump(summary, open(os.path.join(OUT, "diag_reference.json" if a.reference else "diag_pending.json" if a.pending else "diag.json"), "w"), indent=1)
     bad = [r["name"] for r in summary if not r["ok"]]
     print(f"{len(summary) - len(bad)}/{len(summary)} checks passed; failing: {bad}")

@@ -51,6 +51,22 @@ constexpr float kSumTrigger = 256.0f;  // 2^kRescaleThreshold
 #ifndef VAP_ATTN_LEADER_WAIT
 #define VAP_ATTN_LEADER_WAIT 1
 #endif
+// Which waits of the critical chain busy-poll (mbarrier.test_wait) instead of suspending in try_wait: bit 0 = the MMA issuer's waits for P,
+// bit 1 = the softmax warps' wait for S.
+#ifndef VAP_ATTN_SPIN
+#define VAP_ATTN_SPIN 0
+#endif
+#define VAP_MMA_WAIT(bar, par) do { if (VAP_ATTN_SPIN & 1) mbar_wait_spin(bar, par); else mbar_wait(bar, par); } while (0)
+#define VAP_SM_WAIT(bar, par) do { if (VAP_ATTN_SPIN & 2) mbar_wait_spin(bar, par); else mbar_wait(bar, par); } while (0)
+#ifndef VAP_ATTN_L16_EARLYLD
+#define VAP_ATTN_L16_EARLYLD 0  // 16-lane kernel: issue the TMEM load of the second score half before the first half's P store / publish
+#endif
+#ifndef VAP_ATTN_L16_DEFER
+#define VAP_ATTN_L16_DEFER 0    // 16-lane kernel: publish P half 0 from inside the second half's pass (its store latency hides behind MUFU work)
+#endif
+#ifndef VAP_ATTN_MMA_ORDER
+#define VAP_ATTN_MMA_ORDER 1  // 1: the issuer's bookkeeping waits / releases are kept off the P -> PV path (see attn_mma_warp)
+#endif
 #ifndef VAP_ATTN_TRACE
 #define VAP_ATTN_TRACE 0  // 1: clock64() stamps of CTA (0,0,0) when a trace buffer is installed (tools/attn_trace.py)
 #endif
@@ -211,6 +227,7 @@ __device__ __forceinline__ void attn_mma_warp(const AttnSmem<D>& sm, uint32_t tm
     commit(sm.s_full(1));
     release(sm.kv_empty(stage));
     advance();
+#if VAP_ATTN_MMA_ORDER == 0
     for (int j = 0; j < n_kv; ++j) {
         const uint32_t par = j & 1;
         const int v_stage = stage;
@@ -226,12 +243,12 @@ __device__ __forceinline__ void attn_mma_warp(const AttnSmem<D>& sm, uint32_t tm
         TRM(1);
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-            mbar_wait(sm.p_full(i, 0), par);
+            VAP_MMA_WAIT(sm.p_full(i, 0), par);
             tc_fence_after();
             TRM(2 + 2 * i);
             issue_pv_half(i, 0, kv_smem + v_stage * Cfg::kTileBytes, j > 0 ? 1u : 0u);
             commit(sm.pv_half(i));
-            mbar_wait(sm.p_full(i, 1), par);
+            VAP_MMA_WAIT(sm.p_full(i, 1), par);
             tc_fence_after();
             issue_pv_half(i, 1, kv_smem + v_stage * Cfg::kTileBytes, 1u);
             if (has_next) {
@@ -245,6 +262,65 @@ __device__ __forceinline__ void attn_mma_warp(const AttnSmem<D>& sm, uint32_t tm
         release(sm.kv_empty(v_stage));
         if (has_next) release(sm.kv_empty(k_stage));
     }
+#else
+    // Issue order with the issuer's own serial latencies (mbarrier round trips, commits — ~100 clk each) taken off the path that decides when
+    // the tensor pipe gets its next MMAs.  A clock64 timeline of the order above (profiles/r02_attn_trace_d128.txt) shows the pipe idle for
+    // ~650 of every ~2980 clk between the last QK of tile 1 and the first PV of tile 0 of the next step, although that P had been ready for
+    // ~700 clk: the issuer was releasing ring slots, waiting (successfully, but one round trip each) for the next V and K, then for P.  Here
+    //   * the operands of step j+1 (V_{j+1}, K_{j+2}) are waited for inside step j, in the slack before tile 1's second P half;
+    //   * the ring slots of step j are released after the FIRST MMAs of step j+1 have been issued (the commit then covers them as well);
+    // so that between "QK_1(j+1) issued" and "PV_0(j+1) half 0 issued" there is one wait — for P itself.
+    int v_stage = stage;
+    mbar_wait(sm.kv_full(stage), phase);  // V_0
+    advance();
+    int k_stage = stage;
+    if (n_kv > 1) {
+        mbar_wait(sm.kv_full(stage), phase);  // K_1
+        advance();
+    }
+    int prev_v = -1, prev_k = -1;
+    for (int j = 0; j < n_kv; ++j) {
+        const uint32_t par = j & 1;
+        const bool has_next = (j + 1 < n_kv);
+        int next_v = 0, next_k = 0;
+        TRM(0);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            VAP_MMA_WAIT(sm.p_full(i, 0), par);
+            tc_fence_after();
+            TRM(2 + 2 * i);
+            issue_pv_half(i, 0, kv_smem + v_stage * Cfg::kTileBytes, j > 0 ? 1u : 0u);
+            commit(sm.pv_half(i));
+            if (i == 0) {  // the previous step's slots: every MMA that read them was issued before this commit
+                if (prev_v >= 0) release(sm.kv_empty(prev_v));
+                if (prev_k >= 0) release(sm.kv_empty(prev_k));
+            } else if (has_next) {  // next step's operands, while the softmax of tile 1 works on its second half
+                next_v = stage;
+                mbar_wait(sm.kv_full(stage), phase);  // V_{j+1}
+                advance();
+                next_k = stage;
+                if (j + 2 < n_kv) {
+                    mbar_wait(sm.kv_full(stage), phase);  // K_{j+2}
+                    advance();
+                }
+            }
+            VAP_MMA_WAIT(sm.p_full(i, 1), par);
+            tc_fence_after();
+            issue_pv_half(i, 1, kv_smem + v_stage * Cfg::kTileBytes, 1u);
+            if (has_next) {
+                issue_qk(i, kv_smem + k_stage * Cfg::kTileBytes);
+                commit(sm.s_full(i));  // also covers PV_i(j): O_i is quiescent when the softmax sees S_i(j+1)
+            } else {
+                commit(sm.o_done(i));
+            }
+            TRM(3 + 2 * i);
+        }
+        prev_v = v_stage, prev_k = has_next ? k_stage : -1;
+        v_stage = next_v, k_stage = next_k;
+    }
+    if (prev_v >= 0) release(sm.kv_empty(prev_v));
+    if (prev_k >= 0) release(sm.kv_empty(prev_k));
+#endif
 }
 
 // Work-item coordinates of a CTA: (batch, head, 256 query rows) and — split-KV: grid z = batch * kv_splits + split — its KV tile range.
@@ -337,17 +413,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             // Only ONE warp of the tile's eight polls the mbarrier; the others block on a named barrier, which costs no issue
             // slots.  (Eight polling warps executed 39 % of the kernel's instructions and competed with the other tile's
             // softmax for the same schedulers, profiles/r01_attn_v5_in_step.json.)
-            if ((sw & 7) == 0) mbar_wait(s_full(i), j & 1);
+            if ((sw & 7) == 0) VAP_SM_WAIT(s_full(i), j & 1);
             named_bar_sync(1 + i, 256);
 #else
-            mbar_wait(s_full(i), j & 1);
+            VAP_SM_WAIT(s_full(i), j & 1);
 #endif
             tc_fence_after();
             TR(1);
+            uint32_t sr[32];  // sr[4g + e]: columns 64 ch + 8 g + 2 cp + (e & 1) of row0 (e < 2) / row0 + 8 (e >= 2)
+            bool p0_pending = false;  // VAP_ATTN_L16_DEFER: half 0 of P is stored but not yet published
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch) {
-                uint32_t sr[32];  // sr[4g + e]: columns 64 ch + 8 g + 2 cp + (e & 1) of row0 (e < 2) / row0 + 8 (e >= 2)
-                tmem_ld_16x256b_x8(s_col + 64 * ch, sr);
+                if (ch == 0 || !VAP_ATTN_L16_EARLYLD) tmem_ld_16x256b_x8(s_col + 64 * ch, sr);
                 tmem_ld_wait();
                 if (ch == 0) TR(2);
                 const int valid = p.Lkv - (j0 + j) * kBlockN - 64 * ch - 2 * cp;  // this thread's column 8 g + e is inside the sequence iff 8 g + e < valid
@@ -384,6 +461,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                         }
                         ls[r] = add_f32x2(ls[r], pack_f32x2(p0, p1));
                         pk[e] = pack_bf16x2(p0, p1);
+                        if (VAP_ATTN_L16_DEFER && ch == 1 && e == 7 && p0_pending) {
+                            // half 0's P store has had half a pass of MUFU work to land: publish it now (before any wait on pv_half below)
+                            tmem_st_wait();
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(p_full(i, 0));
+                            p0_pending = false;
+                        }
                     }
                     // Vote: does any score of this half-tile sit more than 2^8 above the reference?  The MUFU pairs are judged by
                     // their results (a p > 2^8 makes this thread's partial row sum > 2^8; ex2.approx overflows cleanly to +inf), the
@@ -445,12 +530,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 if (ch == 0) TR(3);
                 l2[0] = add_f32x2(l2[0], ls[0]);
                 l2[1] = add_f32x2(l2[1], ls[1]);
+                // the second half's scores travel while the first half's P is stored and published (the pass above is done with sr)
+                if (VAP_ATTN_L16_EARLYLD && ch == 0) tmem_ld_16x256b_x8(s_col + 64, sr);
                 tmem_st_16x128b_x8(s_col + 32 * ch, pk);
                 if (ch == 1) TR(5);
-                tmem_st_wait();  // covers the rescaled O columns too
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(p_full(i, ch));
+                if (VAP_ATTN_L16_DEFER && ch == 0) {
+                    p0_pending = true;  // published from inside the second half's pass
+                } else {
+                    tmem_st_wait();  // covers the rescaled O columns too
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(p_full(i, ch));
+                }
             }
             TR(6);
         }
@@ -527,7 +618,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 // trigger at 2^8, lazy O rescale, P published in two 64-column halves.  Fewer warps (8 instead of 16 softmax warps share the four
 // schedulers with nothing but each other) leave issue slots for the FMA-pipe exp2 polynomial (kPoly of every 8 pairs), which is what
 // takes load off the MUFU — at D = 128 the MUFU needs 2048 clk per pair of tile steps against 2048 clk of MMAs.
-// Register budget: setmaxnreg moves registers from warps 0-3 (96) to the softmax warps (208): 128 x 96 + 256 x 208 = 65536.
+// Register budget: the kernel launches with 168 registers per thread (384 threads); setmaxnreg.dec takes warps 0-3 down to 72 and the
+// registers they RELEASE — 128 x (168 - 72) = 12288, the only pool setmaxnreg.inc can draw from (the SM's unallocated remainder does not
+// count: a first version asking for 2 x 128 x 40 = 10240 against 9216 released spun forever in USETMAXREG.TRY_ALLOC) — take the eight
+// softmax warps up to 216: 256 x (216 - 168) = 12288.
 // ------------------------------------------------------------------------------------------------------------------------
 constexpr int kRowThreads = 384;
 constexpr int kRowFirstSoftmaxWarp = 4;
@@ -538,7 +632,7 @@ constexpr int kRowFirstSoftmaxWarp = 4;
 #define VAP_ATTN_ROW_POLY_D64 2
 #endif
 #ifndef VAP_ATTN_ROW_PREFETCH
-#define VAP_ATTN_ROW_PREFETCH 1  // 1: the whole 128-column score row is loaded at the top of a step (128 registers), 0: 64 columns per half
+#define VAP_ATTN_ROW_PREFETCH 0  // 1: the whole 128-column score row is loaded at the top of a step (128 registers), 0: 64 columns per half
 #endif
 
 template <int D, int CL>
@@ -571,7 +665,7 @@ attn_fwd_row_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int cta_rank = (CL == 2) ? static_cast<int>(cluster_ctarank()) : 0;
 
     if (warp < kRowFirstSoftmaxWarp) {
-        setmaxnreg_dec<96>();
+        setmaxnreg_dec<72>();
         const AttnWork wk(p);  // recomputed per role: values carried across the setmaxnreg split get spilled
         if (warp == 0) {
             attn_producer_warp<D, CL>(sm, &tmQ, &tmK, &tmV, wk.q0, wk.head, wk.batch, wk.j0, wk.n_kv, cta_rank);
@@ -579,7 +673,7 @@ attn_fwd_row_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             attn_mma_warp<D, CL>(sm, tmem_base, wk.n_kv, nullptr);
         }
     } else {
-        setmaxnreg_inc<208>();
+        setmaxnreg_inc<216>();
         const AttnWork wk(p);
         const int i = (warp - kRowFirstSoftmaxWarp) >> 2;  // Q tile
         const int q = warp & 3;                            // TMEM lane quarter this warp may touch
@@ -596,7 +690,7 @@ attn_fwd_row_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         uint64_t l2 = 0ull;        // packed partial sums of this row
 
         for (int j = 0; j < wk.n_kv; ++j) {
-            mbar_wait(sm.s_full(i), j & 1);  // QK_i(j) complete, and with it PV_i(j-1): O_i is quiescent until our first p_full arrive
+            VAP_SM_WAIT(sm.s_full(i), j & 1);  // QK_i(j) complete, and with it PV_i(j-1): O_i is quiescent until our first p_full arrive
             tc_fence_after();
             uint32_t sc[VAP_ATTN_ROW_PREFETCH ? 4 : 2][32];
             if (VAP_ATTN_ROW_PREFETCH) {

@@ -214,13 +214,11 @@ __global__ void __launch_bounds__(kStagedWarps * 32, 1) adaln_layernorm_staged_k
         }
     };
 #pragma unroll
-    for (int k = 0; k < kStages - 1; ++k) issue(k);
+    for (int k = 0; k < kStages; ++k) issue(k);
     const float inv_d = 1.f / static_cast<float>(d);
     for (int64_t k = 0;; ++k) {
         const int64_t row = first + kStagedWarps * k;
         if (row >= rg.r1) break;
-        __syncwarp();  // every lane has finished reading the stage that is refilled next
-        issue(k + kStages - 1);
         const uint32_t st = static_cast<uint32_t>(k % kStages);
         mbar_wait(bars + 8u * st, static_cast<uint32_t>(k / kStages) & 1u);
         uint4 raw[NV];
@@ -236,6 +234,10 @@ __global__ void __launch_bounds__(kStagedWarps * 32, 1) adaln_layernorm_staged_k
                 sum += f.x + f.y;
             }
         }
+        // The row now lives in registers (the sum above consumed every vector, so the shared-memory reads have completed): the stage is
+        // refilled at once with the row kStages ahead, which keeps kStages rows per warp in flight while this one is being processed.
+        __syncwarp();
+        issue(k + kStages);
         const float mean = warp_sum(sum) * inv_d;
         float sq = 0.f;
 #pragma unroll
@@ -564,14 +566,12 @@ __global__ void __launch_bounds__(kStagedWarps * 32, 1) qk_norm_rope_staged_kern
         }
     };
 #pragma unroll
-    for (int k = 0; k < kStages - 1; ++k) issue(k);
+    for (int k = 0; k < kStages; ++k) issue(k);
     const int ch = (8 * lane) % p.head_dim;  // channel offset inside the head, the same for every vector of this lane
     const float inv_d = 1.f / static_cast<float>(d);
     for (int64_t k = 0;; ++k) {
         const int64_t t = warp + kStagedWarps * k;
         if (t >= n_items) break;
-        __syncwarp();
-        issue(k + kStages - 1);
         const int64_t row = rg.r0 + t / n_which;
         const int which = static_cast<int>(t % n_which);
         const int64_t pos = row - rg.batch * p.rows_per_batch;
@@ -598,6 +598,8 @@ __global__ void __launch_bounds__(kStagedWarps * 32, 1) qk_norm_rope_staged_kern
                 sq += f.x * f.x + f.y * f.y;
             }
         }
+        __syncwarp();  // the row is in registers (sq consumed every vector): refill its stage with the item kStages ahead
+        issue(k + kStages);
         const float rs = rsqrtf(warp_sum(sq) * inv_d + p.eps);
         __nv_bfloat16* xr = item_ptr(t);
         const float* w = vec + which * d;

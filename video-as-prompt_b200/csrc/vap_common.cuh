@@ -123,7 +123,7 @@ __device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
 // (whose softmax warps spend a third of their time in this loop) 5 % of its throughput.  -DVAP_MBAR_VERBOSE brings the message
 // back for bring-up.
 #ifndef VAP_MBAR_SPIN_LIMIT
-#define VAP_MBAR_SPIN_LIMIT (1u << 24)
+#define VAP_MBAR_SPIN_LIMIT (1u << 21)  // ~9 s of try_wait rounds (4.3 us each, measured): no legitimate wait comes near it
 #endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 #if defined(VAP_MBAR_UNBOUNDED)
@@ -141,6 +141,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         }
     }
 #endif
+}
+
+// Busy-polling wait (mbarrier.test_wait never suspends the thread): lower wake-up latency than try_wait at the price of issue slots —
+// for the one or two warps of a kernel that sit on its critical dependency chain.
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_test_wait(bar, parity)) {
+        if (++spins > (VAP_MBAR_SPIN_LIMIT << 6)) __trap();
+    }
 }
 
 // mbar_wait that returns 0 through an asm output: make a computation depend on the returned value to keep the compiler
