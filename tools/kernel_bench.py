@@ -160,8 +160,10 @@ def main():
     ap.add_argument("--mem", action="store_true")
     ap.add_argument("--bwd", action="store_true", help="attention backward (not part of the default set)")
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--sp", action="store_true", help="joint-attention shapes one rank sees under P-way Ulysses (H/P heads over the full joint sequence), "
+                    "P = 2 / 4 / 8, incl. the automatic split-KV path at 5 heads (BASELINE.json configs[4] at 1/2/4/8 GPUs)")
     a = ap.parse_args()
-    if not (a.attn or a.gemm or a.mem or a.bwd):
+    if not (a.attn or a.gemm or a.mem or a.bwd or a.sp):
         a.attn = a.gemm = a.mem = True
     results = []
     if a.attn:
@@ -169,6 +171,12 @@ def main():
                                                                        (40, 65536, 128), (5, 151200, 128), (48, 35552, 64)]
         for H, J, D in cases:
             attn_case(H, J, D, results)
+    if a.sp:
+        for J in (8192, 16384, 32768, 40560, 65536, 131072, 151200):
+            for P in (2, 4, 8):
+                if J * (40 // P) <= 40560 * 40:  # keep every case under ~30 ms
+                    attn_case(40 // P, J, 128, results)
+                    results[-1]["ulysses_ranks"] = P
     if a.bwd:
         for H, J, D in ([(40, 16384, 128)] if a.quick else [(40, 16384, 128), (40, 40560, 128), (48, 35552, 64)]):
             attn_bwd_case(H, J, D, results)

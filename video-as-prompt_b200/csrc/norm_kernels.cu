@@ -194,10 +194,14 @@ __global__ void __launch_bounds__(kStagedWarps * 32, 1) adaln_layernorm_staged_k
     const uint32_t bars = smem_u32(ln_smem) + n_vec * d * sizeof(float) + kStagedWarps * kStages * row_bytes + static_cast<uint32_t>(warp) * kStages * 8u;
     const float* srcs[4] = {p.scale1p ? p.scale1p + rg.batch * p.mod_stride : nullptr, p.shift ? p.shift + rg.batch * p.mod_stride : nullptr, p.ln_w, p.ln_b};
     float* dsts[4] = {vec_mod, vec_mod + d, vec_aff, vec_aff + d};
+    // Shared-memory layout of a staged vector: the 8 channels of 16-byte data vector v are split into two float4 halves, lo[v] at float
+    // offset 4 v and hi[v] at d / 2 + 4 v, so that the 32 lanes of a warp read 32 CONSECUTIVE float4 (a lane-strided 32-byte read would hit
+    // every bank twice: the vectors are 4x the bytes of the data and shared-memory bandwidth is what bounds this kernel after HBM).
 #pragma unroll
     for (int t = 0; t < 4; ++t)
         if (srcs[t])
-            for (int c = threadIdx.x * 4; c < d; c += kStagedWarps * 32 * 4) *reinterpret_cast<float4*>(dsts[t] + c) = *reinterpret_cast<const float4*>(srcs[t] + c);
+            for (int f = threadIdx.x; f < d / 4; f += kStagedWarps * 32)
+                *reinterpret_cast<float4*>(dsts[t] + (f & 1) * (d / 2) + (f >> 1) * 4) = *reinterpret_cast<const float4*>(srcs[t] + 4 * f);
     if (lane == 0) {
         for (int s = 0; s < kStages; ++s) mbar_init(bars + 8u * s, 1);
         fence_mbar_init();
@@ -264,8 +268,8 @@ __global__ void __launch_bounds__(kStagedWarps * 32, 1) adaln_layernorm_staged_k
                 y[2 * j + 1] = (f.y - mean) * rstd;
             }
             if (p.ln_w) {
-                const float4 w0 = *reinterpret_cast<const float4*>(vec_aff + c), w1 = *reinterpret_cast<const float4*>(vec_aff + c + 4);
-                const float4 b0 = *reinterpret_cast<const float4*>(vec_aff + d + c), b1 = *reinterpret_cast<const float4*>(vec_aff + d + c + 4);
+                const float4 w0 = *reinterpret_cast<const float4*>(vec_aff + c / 2), w1 = *reinterpret_cast<const float4*>(vec_aff + d / 2 + c / 2);
+                const float4 b0 = *reinterpret_cast<const float4*>(vec_aff + d + c / 2), b1 = *reinterpret_cast<const float4*>(vec_aff + d + d / 2 + c / 2);
                 const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
                 const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
@@ -276,8 +280,8 @@ __global__ void __launch_bounds__(kStagedWarps * 32, 1) adaln_layernorm_staged_k
                 for (int j = 0; j < 8; ++j) y[j] = bf16_round(y[j]);
             }
             if (p.scale1p) {
-                const float4 s0 = *reinterpret_cast<const float4*>(vec_mod + c), s1 = *reinterpret_cast<const float4*>(vec_mod + c + 4);
-                const float4 h0 = *reinterpret_cast<const float4*>(vec_mod + d + c), h1 = *reinterpret_cast<const float4*>(vec_mod + d + c + 4);
+                const float4 s0 = *reinterpret_cast<const float4*>(vec_mod + c / 2), s1 = *reinterpret_cast<const float4*>(vec_mod + d / 2 + c / 2);
+                const float4 h0 = *reinterpret_cast<const float4*>(vec_mod + d + c / 2), h1 = *reinterpret_cast<const float4*>(vec_mod + d + d / 2 + c / 2);
                 const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
                 const float h[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
                 if (p.cog_rounding) {
@@ -542,9 +546,10 @@ __global__ void __launch_bounds__(kStagedWarps * 32, 1) qk_norm_rope_staged_kern
     float* vec = reinterpret_cast<float*>(qk_smem);  // wq | wk
     const uint32_t ring = smem_u32(qk_smem) + 2u * d * sizeof(float) + static_cast<uint32_t>(warp) * kStages * row_bytes;
     const uint32_t bars = smem_u32(qk_smem) + 2u * d * sizeof(float) + kStagedWarps * kStages * row_bytes + static_cast<uint32_t>(warp) * kStages * 8u;
-    for (int c = threadIdx.x * 4; c < d; c += kStagedWarps * 32 * 4) {
-        *reinterpret_cast<float4*>(vec + c) = *reinterpret_cast<const float4*>(p.wq + c);
-        if (p.k) *reinterpret_cast<float4*>(vec + d + c) = *reinterpret_cast<const float4*>(p.wk + c);
+    for (int f = threadIdx.x; f < d / 4; f += kStagedWarps * 32) {  // split lo / hi layout, see adaln_layernorm_staged_kernel
+        const int o = (f & 1) * (d / 2) + (f >> 1) * 4;
+        *reinterpret_cast<float4*>(vec + o) = *reinterpret_cast<const float4*>(p.wq + 4 * f);
+        if (p.k) *reinterpret_cast<float4*>(vec + d + o) = *reinterpret_cast<const float4*>(p.wk + 4 * f);
     }
     if (lane == 0) {
         for (int s = 0; s < kStages; ++s) mbar_init(bars + 8u * s, 1);
@@ -607,7 +612,7 @@ __global__ void __launch_bounds__(kStagedWarps * 32, 1) qk_norm_rope_staged_kern
         for (int i = 0; i < NV; ++i) {
             const int c = 8 * (lane + 32 * i);
             const uint32_t* u = reinterpret_cast<const uint32_t*>(&raw[i]);
-            const float4 w0 = *reinterpret_cast<const float4*>(w + c), w1 = *reinterpret_cast<const float4*>(w + c + 4);
+            const float4 w0 = *reinterpret_cast<const float4*>(w + c / 2), w1 = *reinterpret_cast<const float4*>(w + d / 2 + c / 2);
             const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
             float y[8];
 #pragma unroll
