@@ -75,6 +75,14 @@ int vap_attention_fwd(const void* q, const void* k, const void* v, void* o, floa
                       int64_t q_sb, int64_t q_sh, int64_t q_sl, int64_t k_sb, int64_t k_sh, int64_t k_sl, int64_t v_sb,
                       int64_t v_sh, int64_t v_sl, int64_t o_sb, int64_t o_sh, int64_t o_sl, float scale, void* stream);
 
+/* (3a) vap_attention_fwd whose epilogue ADDS to the output already in `o`:  o <- bf16(float(o) + float(bf16(softmax(QK^T) V))) —
+ *     the bf16 tensor add of the reference's two cross-attention softmaxes (image tokens + text tokens), fused into the second
+ *     launch.  Same arguments as vap_attention_fwd.
+ *     Ref: transformer_wan_mot.py:163-186 (hidden_states = hidden_states_img + hidden_states). */
+int vap_attention_fwd_accumulate(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int Lq, int Lkv, int D,
+                      int64_t q_sb, int64_t q_sh, int64_t q_sl, int64_t k_sb, int64_t k_sh, int64_t k_sl, int64_t v_sb,
+                      int64_t v_sh, int64_t v_sl, int64_t o_sb, int64_t o_sh, int64_t o_sl, float scale, void* stream);
+
 /* (4) Linear layer  C[M,N] = epilogue(A[M,K] @ W[N,K]^T + bias[N])  (bf16 in/out, fp32 accumulate).
  *     Ref: nn.Linear call sites transformer_wan_mot.py:214-216, 241-243; attention.py:1245-1251 (FeedForward);
  *          attention_processor.py:2923-2925, 2952.

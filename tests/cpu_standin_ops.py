@@ -80,7 +80,7 @@ def qk_norm_rope_(q, k, *, heads, head_dim, wq, wk=None, bq=None, bk=None, cos=N
         t.copy_(y.to(BF16).reshape(t.shape))
 
 
-def attention(q, k, v, *, scale=None, out=None, return_lse=False):
+def attention(q, k, v, *, scale=None, out=None, return_lse=False, accumulate=False):
     B, H, Lq, D = q.shape
     if scale is None or scale == D ** -0.5:
         o = oc.sdpa_explicit_fp32(q, k, v).to(BF16)  # [B, H, Lq, D]
@@ -89,7 +89,7 @@ def attention(q, k, v, *, scale=None, out=None, return_lse=False):
     res = torch.empty((B, Lq, H, D), dtype=BF16).transpose(1, 2)  # token-major memory like the kernel's output
     res.copy_(o)
     if out is not None:
-        out.copy_(res)
+        out.copy_(out + res if accumulate else res)  # accumulate: the bf16 tensor add of vap_attention_fwd_accumulate
         res = out
     if return_lse:
         s = torch.matmul(q.float(), k.float().transpose(-1, -2)) * (scale or D ** -0.5)

@@ -245,6 +245,22 @@ def check_attention(B=1, H=2, Lq=300, Lkv=300, D=128, joint_layout=True, seed=30
     return dict(err=err, lse_err=lse_err)
 
 
+def check_attention_accumulate(D=128, H=3, Lq=700, kv=(257, 512)):
+    """vap_attention_fwd_accumulate (the cross-attention's second softmax added to the first in the epilogue) must equal two plain launches
+    followed by torch's bf16 tensor add — bit for bit — in both softmax organisations' epilogues."""
+    q = _randn((1, H, Lq, D), 45).to(DEV)
+    ks = [_randn((1, H, n, D), 46 + t).to(DEV) for t, n in enumerate(kv)]
+    vs = [_randn((1, H, n, D), 48 + t).to(DEV) for t, n in enumerate(kv)]
+    want = ops.attention(q, ks[0], vs[0]) + ops.attention(q, ks[1], vs[1])
+    got = ops.attention(q, ks[0], vs[0])
+    ops.attention(q, ks[1], vs[1], out=got, accumulate=True)
+    ref = ocommon.sdpa_explicit_fp32(q.cpu(), ks[0].cpu(), vs[0].cpu()).to(torch.bfloat16) + ocommon.sdpa_explicit_fp32(q.cpu(), ks[1].cpu(), vs[1].cpu()).to(torch.bfloat16)
+    err = rel_err(got, ref)
+    assert torch.equal(got, want), f"accumulate epilogue differs from two launches + bf16 add: {rel_err(got, want)}"
+    assert err < 1e-2, f"accumulated cross-attention vs the oracle: {err}"
+    return dict(bit_exact=True, err=err)
+
+
 def check_attention_peaky(D=128):
     """Scores with a large dynamic range (exercises the lazy O-rescale path: the running max keeps growing by > 2^8)."""
     H, L = 2, 1024
@@ -771,6 +787,8 @@ CHECKS = {
     "attn_cross_512": lambda: check_attention(1, 2, 300, 512, 128, joint_layout=False),
     "attn_one_tile": lambda: check_attention(1, 1, 64, 100, 128, joint_layout=False),
     "attn_peaky": lambda: check_attention_peaky(),
+    "attn_accumulate": lambda: check_attention_accumulate(),
+    "attn_accumulate_d64": lambda: check_attention_accumulate(D=64, H=2, Lq=300, kv=(100, 226)),
     "attn_splitkv_2": lambda: check_attention_splitkv(1, 2, 300, 1000, 128, 2),
     "attn_splitkv_3_d64": lambda: check_attention_splitkv(2, 3, 452, 900, 64, 3),
     "attn_splitkv_uneven": lambda: check_attention_splitkv(1, 1, 130, 128 * 5 + 7, 128, 4),

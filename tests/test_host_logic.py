@@ -261,12 +261,13 @@ def test_wan_mot_block_launch_sequence(tmp_path):
     """One Wan MoT block = 37 launches (SURVEY §8a W1-W9 on both streams): the two streams' adaLN modulation vectors (one launch each), per
     stream LN -> fused-QKV GEMM -> q/k norm + RoPE into the
     JOINT buffer, ONE attention over [target | ref], per stream O-projection with the gated-residual epilogue, then per stream the
-    cross-attention (q / text kv / image kv projections, three norms, two attentions, ungated residual epilogue) and the FFN (GELU and
+    cross-attention (q / text kv / image kv projections, three norms, two attentions — the second accumulating into the first's output —,
+    ungated residual epilogue) and the FFN (GELU and
     gated-residual epilogues); + the output head's LayerNorm.  No pack / cat / transpose kernels of ours in between."""
     calls = _recorded_calls("wan", 1, tmp_path)
     names = [c[0].replace("vap_", "") for c in calls]
-    ln, gemm, qk, att, mod = "adaln_layernorm", "gemm_bf16", "qk_norm_rope", "attention_fwd", "wan_modulation"
-    tail = [ln, gemm, qk, gemm, qk, att, gemm, qk, att, gemm, ln, gemm, gemm]
+    ln, gemm, qk, att, mod, acc = "adaln_layernorm", "gemm_bf16", "qk_norm_rope", "attention_fwd", "wan_modulation", "attention_fwd_accumulate"
+    tail = [ln, gemm, qk, gemm, qk, att, gemm, qk, acc, gemm, ln, gemm, gemm]  # the image softmax is added to the text one in its epilogue
     assert names == [mod, mod, ln, ln, gemm, qk, gemm, qk, att, gemm, gemm] + tail + tail + [ln]
     # the joint attention reads q, k, v of BOTH streams as strided views of one [J, 3d] buffer: J = 2 x 32 rows, row stride 3 * 256
     joint = [c for c in calls if c[0] == "vap_attention_fwd"][0]

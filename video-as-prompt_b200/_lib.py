@@ -32,6 +32,8 @@ SIGNATURES = {
                                  _FLOAT_P, c_int64, c_int64, c_int64, c_float, c_int, c_void_p]),
     "vap_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, _FLOAT_P, c_int, c_int, c_int, c_int, c_int] + [c_int64] * 12
                           + [c_float, c_void_p]),
+    "vap_attention_fwd_accumulate": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, _FLOAT_P, c_int, c_int, c_int, c_int, c_int] + [c_int64] * 12
+                                     + [c_float, c_void_p]),
     "vap_qkv_scatter": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int64, _FLOAT_P, _FLOAT_P, _FLOAT_P, _FLOAT_P, _FLOAT_P,
                                 _FLOAT_P, c_int64, c_int64, c_int64, c_float, c_int, c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p]),
     "vap_attention_fwd_scatter": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, _FLOAT_P, c_int, c_int, c_int, c_int, c_int]

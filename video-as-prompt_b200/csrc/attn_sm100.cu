@@ -58,9 +58,6 @@ constexpr float kSumTrigger = 256.0f;  // 2^kRescaleThreshold
 #endif
 #define VAP_MMA_WAIT(bar, par) do { if (VAP_ATTN_SPIN & 1) mbar_wait_spin(bar, par); else mbar_wait(bar, par); } while (0)
 #define VAP_SM_WAIT(bar, par) do { if (VAP_ATTN_SPIN & 2) mbar_wait_spin(bar, par); else mbar_wait(bar, par); } while (0)
-#ifndef VAP_ATTN_DECOUPLE_D64
-#define VAP_ATTN_DECOUPLE_D64 1
-#endif
 #ifndef VAP_ATTN_MMA_ORDER
 #define VAP_ATTN_MMA_ORDER 1  // 1: the issuer's bookkeeping waits / releases are kept off the P -> PV path (see attn_mma_warp)
 #endif
@@ -78,11 +75,13 @@ struct AttnCfg {
     static constexpr int kSmemBytes = 2 * kTileBytes + kKvStages * kTileBytes + kBarBytes + 1024;
     static constexpr int kTmemCols = 512;
     static constexpr int kColS0 = 0, kColS1 = 128, kColO0 = 256, kColO1 = 256 + D;
-    // D = 64 leaves 128 TMEM columns free: P gets columns of its own (kDecoupled), so that S_i is reusable as soon as the softmax has READ
-    // it — QK_i(j+1) no longer waits for PV_i(j).  At D = 128 S | S | O | O fill all 512 columns and P has to alias S.
-    static constexpr bool kDecoupled = (D == 64) && (VAP_ATTN_DECOUPLE_D64 != 0);
-    static constexpr int kColP0 = 384, kColP1 = 448;
 };
+
+// bf16(float(a) + float(b)) per element of a packed pair: what a bf16 tensor add computes
+__device__ __forceinline__ uint32_t add_bf16x2_as_tensors(uint32_t a, uint32_t b) {
+    const float2 fa = bf16x2_to_float2(a), fb = bf16x2_to_float2(b);
+    return pack_bf16x2(fa.x + fb.x, fa.y + fb.y);
+}
 
 // Shared-memory map of one CTA: Q tiles | K/V ring | mbarriers.
 template <int D>
@@ -98,9 +97,7 @@ struct AttnSmem {
     __device__ __forceinline__ uint32_t p_full(int i, int c) const { return bar_base + 8u * (2 * Cfg::kKvStages + 3 + 2 * i + c); }  // half c of P_i(j) in TMEM
     __device__ __forceinline__ uint32_t pv_half(int i) const { return bar_base + 8u * (2 * Cfg::kKvStages + 7 + i); }           // the PV MMAs of half 0 have completed
     __device__ __forceinline__ uint32_t o_done(int i) const { return bar_base + 8u * (2 * Cfg::kKvStages + 9 + i); }
-    __device__ __forceinline__ uint32_t s_free(int i) const { return bar_base + 8u * (2 * Cfg::kKvStages + 11 + i); }           // decoupled: the softmax has read S_i(j)
-    __device__ __forceinline__ uint32_t p_free(int i) const { return bar_base + 8u * (2 * Cfg::kKvStages + 13 + i); }           // decoupled: PV_i(j) has completed
-    __device__ __forceinline__ uint32_t tmem_ptr_addr() const { return bar_base + 8u * (2 * Cfg::kKvStages + 15); }
+    __device__ __forceinline__ uint32_t tmem_ptr_addr() const { return bar_base + 8u * (2 * Cfg::kKvStages + 11); }
     // one thread: p_arrivals = softmax warps per Q tile (each arrives once per published half)
     __device__ __forceinline__ void init_barriers(int cluster_size, int p_arrivals) const {
         for (int s = 0; s < Cfg::kKvStages; ++s) {
@@ -114,8 +111,6 @@ struct AttnSmem {
             mbar_init(p_full(i, 1), p_arrivals);
             mbar_init(pv_half(i), 1);
             mbar_init(o_done(i), 1);
-            mbar_init(s_free(i), p_arrivals);
-            mbar_init(p_free(i), 1);
         }
         fence_mbar_init();
     }
@@ -328,126 +323,6 @@ __device__ __forceinline__ void attn_mma_warp(const AttnSmem<D>& sm, uint32_t tm
 #endif
 }
 
-// MMA issuer of the DECOUPLED layout (D = 64: P has TMEM columns of its own).  Per step j, both tiles in lock step:
-//   PV_i(j) half 0            when p_full(i, 0)            (A = P_i from its own columns)
-//   QK_i(j+1)                 when s_free(i): the softmax warps have pulled S_i(j) into registers — half a softmax pass BEFORE P_i(j) is complete
-//   PV_i(j) half 1, commit p_free(i)   when p_full(i, 1)   (p_free: the softmax may overwrite P_i / rescale O_i)
-// so S_i(j+1) is waiting in TMEM when the softmax of step j ends and the softmax warps never idle: at D = 64 the MUFU (2048 clk of exp2 per
-// pair of tile steps against ~1700 clk of MMAs) is the pipe to keep busy.  Ring-slot bookkeeping as in attn_mma_warp (VAP_ATTN_MMA_ORDER 1).
-template <int D, int CL>
-__device__ __forceinline__ void attn_mma_warp_decoupled(const AttnSmem<D>& sm, uint32_t tmem_base, int n_kv) {
-    using Cfg = AttnCfg<D>;
-    constexpr uint32_t idesc_qk = make_idesc_bf16(kBlockM, kBlockN, 0, 0);
-    constexpr uint32_t idesc_pv = make_idesc_bf16(kBlockM, D, 0, 1);
-    const uint32_t col_s[2] = {tmem_base + Cfg::kColS0, tmem_base + Cfg::kColS1};
-    const uint32_t col_o[2] = {tmem_base + Cfg::kColO0, tmem_base + Cfg::kColO1};
-    const uint32_t col_p[2] = {tmem_base + Cfg::kColP0, tmem_base + Cfg::kColP1};
-    const uint32_t q_smem = sm.q_smem, kv_smem = sm.kv_smem;
-    auto issue_qk = [&](int i, uint32_t k_addr) {
-        const uint32_t q_addr = q_smem + i * Cfg::kTileBytes;
-        if (elect_one()) {
-#pragma unroll
-            for (int k = 0; k < D / 16; ++k) {
-                const uint32_t off = (k >> 2) * Cfg::kHalfBytes + (k & 3) * 32;
-                umma_ss(col_s[i], make_smem_desc(q_addr + off, 0, 1024, kLayoutSw128), make_smem_desc(k_addr + off, 0, 1024, kLayoutSw128), idesc_qk,
-                        k != 0 ? 1u : 0u);
-            }
-        }
-        __syncwarp();
-    };
-    auto issue_pv_half = [&](int i, int c, uint32_t v_addr, uint32_t accumulate) {
-        if (elect_one()) {
-#pragma unroll
-            for (int kk = 0; kk < kBlockN / 32; ++kk) {
-                const int k = 4 * c + kk;
-                umma_ts(col_o[i], col_p[i] + 8 * k, make_smem_desc(v_addr + k * 2048, Cfg::kHalfBytes, 1024, kLayoutSw128), idesc_pv, k != 0 ? 1u : accumulate);
-            }
-        }
-        __syncwarp();
-    };
-    auto commit = [&](uint32_t bar) {
-        if (elect_one()) umma_commit(bar);
-        __syncwarp();
-    };
-    auto release = [&](uint32_t bar) {
-        if (elect_one()) {
-            if (CL == 2) umma_commit_multicast(bar, 3);
-            else umma_commit(bar);
-        }
-        __syncwarp();
-    };
-    int stage = 0;
-    uint32_t phase = 0;
-    auto advance = [&]() {
-        if (++stage == Cfg::kKvStages) {
-            stage = 0;
-            phase ^= 1;
-        }
-    };
-    mbar_wait(sm.q_full(), 0);
-    mbar_wait(sm.kv_full(stage), phase);  // K_0
-    tc_fence_after();
-    issue_qk(0, kv_smem + stage * Cfg::kTileBytes);
-    commit(sm.s_full(0));
-    issue_qk(1, kv_smem + stage * Cfg::kTileBytes);
-    commit(sm.s_full(1));
-    release(sm.kv_empty(stage));
-    advance();
-    int v_stage = stage;
-    mbar_wait(sm.kv_full(stage), phase);  // V_0
-    advance();
-    int k_stage = stage;
-    if (n_kv > 1) {
-        mbar_wait(sm.kv_full(stage), phase);  // K_1
-        advance();
-    }
-    int prev_v = -1, prev_k = -1;
-    for (int j = 0; j < n_kv; ++j) {
-        const uint32_t par = j & 1;
-        const bool has_next = (j + 1 < n_kv);
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            mbar_wait(sm.p_full(i, 0), par);
-            tc_fence_after();
-            issue_pv_half(i, 0, kv_smem + v_stage * Cfg::kTileBytes, j > 0 ? 1u : 0u);
-            commit(sm.pv_half(i));
-        }
-        if (prev_v >= 0) release(sm.kv_empty(prev_v));
-        if (prev_k >= 0) release(sm.kv_empty(prev_k));
-        if (has_next) {
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                mbar_wait(sm.s_free(i), par);
-                tc_fence_after();
-                issue_qk(i, kv_smem + k_stage * Cfg::kTileBytes);
-                commit(sm.s_full(i));
-            }
-        }
-        int next_v = 0, next_k = 0;
-        if (has_next) {  // next step's operands, in the slack before the second P halves
-            next_v = stage;
-            mbar_wait(sm.kv_full(stage), phase);  // V_{j+1}
-            advance();
-            next_k = stage;
-            if (j + 2 < n_kv) {
-                mbar_wait(sm.kv_full(stage), phase);  // K_{j+2}
-                advance();
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            mbar_wait(sm.p_full(i, 1), par);
-            tc_fence_after();
-            issue_pv_half(i, 1, kv_smem + v_stage * Cfg::kTileBytes, 1u);
-            commit(has_next ? sm.p_free(i) : sm.o_done(i));
-        }
-        prev_v = v_stage, prev_k = has_next ? k_stage : -1;
-        v_stage = next_v, k_stage = next_k;
-    }
-    if (prev_v >= 0) release(sm.kv_empty(prev_v));
-    if (prev_k >= 0) release(sm.kv_empty(prev_k));
-}
-
 // Work-item coordinates of a CTA: (batch, head, 256 query rows) and — split-KV: grid z = batch * kv_splits + split — its KV tile range.
 struct AttnWork {
     int q0, head, batch, j0, n_kv;
@@ -504,10 +379,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (warp == 0) {
             attn_producer_warp<D, CL>(sm, &tmQ, &tmK, &tmV, q0, head, batch, j0, n_kv, cta_rank);
         } else if (warp == 1) {
-            if constexpr (Cfg::kDecoupled)
-                attn_mma_warp_decoupled<D, CL>(sm, tmem_base, n_kv);
-            else
-                attn_mma_warp<D, CL>(sm, tmem_base, n_kv, (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) ? p.trace + 1024 : nullptr);
+            attn_mma_warp<D, CL>(sm, tmem_base, n_kv, (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) ? p.trace + 1024 : nullptr);
         }
     } else {
         // ===== softmax + epilogue warps =====
@@ -520,8 +392,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32 + hl * 16) << 16;
         const uint32_t s_col = tmem_base + lane_addr + (i == 0 ? Cfg::kColS0 : Cfg::kColS1);
         const uint32_t o_col = tmem_base + lane_addr + (i == 0 ? Cfg::kColO0 : Cfg::kColO1);
-        // where this tile's P goes: its own columns (decoupled, D = 64) or columns [0, 64) of its S tile
-        const uint32_t p_col = Cfg::kDecoupled ? tmem_base + lane_addr + (i == 0 ? Cfg::kColP0 : Cfg::kColP1) : s_col;
         const float c = p.scale_log2;
         const uint64_t c2 = pack_f32x2(c, c);
         const float thr_off = kRescaleThreshold / c;
@@ -550,17 +420,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #endif
             tc_fence_after();
             TR(1);
-            bool p_free_seen = (j == 0);  // decoupled: PV_i(j-1) has completed (P_i may be overwritten, O_i is quiescent)
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch) {
                 uint32_t sr[32];  // sr[4g + e]: columns 64 ch + 8 g + 2 cp + (e & 1) of row0 (e < 2) / row0 + 8 (e >= 2)
                 tmem_ld_16x256b_x8(s_col + 64 * ch, sr);
                 tmem_ld_wait();
-                if (Cfg::kDecoupled && ch == 1) {  // S_i(j) is in registers: the MMA warp may overwrite it with S_i(j+1)
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(sm.s_free(i));
-                }
                 if (ch == 0) TR(2);
                 const int valid = p.Lkv - (j0 + j) * kBlockN - 64 * ch - 2 * cp;  // this thread's column 8 g + e is inside the sequence iff 8 g + e < valid
                 if (valid < 58) {
@@ -635,10 +499,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                         if (ch > 0) {  // the PV MMAs of this step's first half must have left O_i
                             mbar_wait(pv_half(i), j & 1);
                             tc_fence_after();
-                        } else if (Cfg::kDecoupled && !p_free_seen) {  // aliased layout: s_full(i) already implied PV_i(j-1) done
-                            mbar_wait(sm.p_free(i), (j - 1) & 1);
-                            tc_fence_after();
-                            p_free_seen = true;
                         }
                         const float f0 = ex2_approx((m_used[0] - mn0) * c), f1 = ex2_approx((m_used[1] - mn1) * c);
                         l2[0] = mul_f32x2(l2[0], pack_f32x2(f0, f0));
@@ -664,12 +524,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 // P is published the moment it is stored: PV of the first half has to be out of the way before the second half ends.  (Tried on a
                 // B200 and slower: loading the second half's scores before this store, 1404 -> 1312 TFLOP/s, and publishing half 0 from inside the
                 // second half's pass to hide the store latency, -> 1185: every clock P half 0 is late moves its PV into the tail, profiles/r02_attn_ab.json.)
-                if (Cfg::kDecoupled && !p_free_seen) {  // PV_i(j-1) still reads the previous P from these columns
-                    mbar_wait(sm.p_free(i), (j - 1) & 1);
-                    tc_fence_after();
-                    p_free_seen = true;
-                }
-                tmem_st_16x128b_x8(p_col + 32 * ch, pk);
+                tmem_st_16x128b_x8(s_col + 32 * ch, pk);
                 if (ch == 1) TR(5);
                 tmem_st_wait();  // covers the rescaled O columns too
                 tc_fence_before();
@@ -716,9 +571,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     if (row[r] < p.Lq) {
                         __nv_bfloat16* orow = obase[r] + 32 * g4;
 #pragma unroll
-                        for (int g = 0; g < 4; ++g)
-                            *reinterpret_cast<uint32_t*>(orow + 8 * g) =
-                                pack_bf16x2(__uint_as_float(ov[4 * g + 2 * r]) * inv_l[r], __uint_as_float(ov[4 * g + 2 * r + 1]) * inv_l[r]);
+                        for (int g = 0; g < 4; ++g) {
+                            uint32_t w = pack_bf16x2(__uint_as_float(ov[4 * g + 2 * r]) * inv_l[r], __uint_as_float(ov[4 * g + 2 * r + 1]) * inv_l[r]);
+                            if (p.accumulate) w = add_bf16x2_as_tensors(*reinterpret_cast<const uint32_t*>(orow + 8 * g), w);
+                            *reinterpret_cast<uint32_t*>(orow + 8 * g) = w;
+                        }
                     }
                 }
             }
@@ -949,6 +806,11 @@ attn_fwd_row_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                         o.y = pack_bf16x2(__uint_as_float(ov[8 * v + 2]) * inv_l, __uint_as_float(ov[8 * v + 3]) * inv_l);
                         o.z = pack_bf16x2(__uint_as_float(ov[8 * v + 4]) * inv_l, __uint_as_float(ov[8 * v + 5]) * inv_l);
                         o.w = pack_bf16x2(__uint_as_float(ov[8 * v + 6]) * inv_l, __uint_as_float(ov[8 * v + 7]) * inv_l);
+                        if (p.accumulate) {
+                            const uint4 prev = *reinterpret_cast<const uint4*>(orow + 32 * g + 8 * v);
+                            o.x = add_bf16x2_as_tensors(prev.x, o.x), o.y = add_bf16x2_as_tensors(prev.y, o.y);
+                            o.z = add_bf16x2_as_tensors(prev.z, o.z), o.w = add_bf16x2_as_tensors(prev.w, o.w);
+                        }
                         st_v4(orow + 32 * g + 8 * v, o);
                     }
                 }
@@ -1000,7 +862,7 @@ template <int D, int CL, bool ROW>
 static int launch_attn_d(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const AttnParams& p, cudaStream_t stream) {
     using Cfg = AttnCfg<D>;
     static_assert(Cfg::kSmemBytes <= 232448, "shared memory budget");
-    static_assert(2 * Cfg::kKvStages + 16 <= Cfg::kBarBytes / 8, "barrier area");
+    static_assert(2 * Cfg::kKvStages + 12 <= Cfg::kBarBytes / 8, "barrier area");
     auto kernel = ROW ? attn_fwd_row_kernel<D, CL> : attn_fwd_kernel<D, CL>;
     constexpr int threads = ROW ? kRowThreads : kAttnThreads;
     static bool opted_in[64] = {};
@@ -1050,6 +912,7 @@ int launch_attention_fwd(const AttnTensor& q, const AttnTensor& k, const AttnTen
         VAP_REQUIRE((reinterpret_cast<uintptr_t>(p.o) & 15) == 0 && p.o_sl % 8 == 0 && p.o_sh % 8 == 0 && p.o_sb % 8 == 0,
                     "attention: output must be 16-byte aligned with strides that are multiples of 8 elements");
     }
+    VAP_REQUIRE(!p.accumulate || (p.kv_splits == 1 && p.o_rows_per_peer == 0), "attention: accumulate needs the plain output mode (no split-KV, no peers)");
     if (p.Lq == 0) return 0;
     const bool cluster = attn_cluster_mode() == 2 && p.Lq > 2 * kBlockM;
     CUtensorMap tmQ, tmK, tmV;

@@ -179,10 +179,10 @@ int vap_qkv_scatter(const void* q, const void* k, const void* v, int64_t rows, i
     return launch_qk_norm_rope(p, mode, static_cast<cudaStream_t>(stream));
 }
 
-int vap_attention_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int Lq, int Lkv, int D, int64_t q_sb,
-                      int64_t q_sh, int64_t q_sl, int64_t k_sb, int64_t k_sh, int64_t k_sl, int64_t v_sb, int64_t v_sh, int64_t v_sl,
-                      int64_t o_sb, int64_t o_sh, int64_t o_sl, float scale, void* stream) {
-    VAP_REQUIRE(q && k && v && o, "vap_attention_fwd: null tensor");
+static int attention_fwd_plain(const char* who, int accumulate, const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int Lq, int Lkv, int D,
+                               int64_t q_sb, int64_t q_sh, int64_t q_sl, int64_t k_sb, int64_t k_sh, int64_t k_sl, int64_t v_sb, int64_t v_sh, int64_t v_sl,
+                               int64_t o_sb, int64_t o_sh, int64_t o_sl, float scale, void* stream) {
+    VAP_REQUIRE(q && k && v && o, "%s: null tensor", who);
     AttnParams p{};
     p.B = B, p.H = H, p.Lq = Lq, p.Lkv = Lkv;
     p.o = static_cast<__nv_bfloat16*>(o);
@@ -191,10 +191,25 @@ int vap_attention_fwd(const void* q, const void* k, const void* v, void* o, floa
     p.scale = scale;
     p.scale_log2 = scale * 1.4426950408889634f;
     p.trace = g_attn_trace;
+    p.accumulate = accumulate;
     const AttnTensor tq{static_cast<const __nv_bfloat16*>(q), q_sb, q_sh, q_sl};
     const AttnTensor tk{static_cast<const __nv_bfloat16*>(k), k_sb, k_sh, k_sl};
     const AttnTensor tv{static_cast<const __nv_bfloat16*>(v), v_sb, v_sh, v_sl};
     return launch_attention_fwd(tq, tk, tv, p, D, static_cast<cudaStream_t>(stream));
+}
+
+int vap_attention_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int Lq, int Lkv, int D, int64_t q_sb,
+                      int64_t q_sh, int64_t q_sl, int64_t k_sb, int64_t k_sh, int64_t k_sl, int64_t v_sb, int64_t v_sh, int64_t v_sl,
+                      int64_t o_sb, int64_t o_sh, int64_t o_sl, float scale, void* stream) {
+    return attention_fwd_plain("vap_attention_fwd", 0, q, k, v, o, lse, B, H, Lq, Lkv, D, q_sb, q_sh, q_sl, k_sb, k_sh, k_sl, v_sb, v_sh, v_sl, o_sb, o_sh, o_sl,
+                               scale, stream);
+}
+
+int vap_attention_fwd_accumulate(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int Lq, int Lkv, int D, int64_t q_sb,
+                                 int64_t q_sh, int64_t q_sl, int64_t k_sb, int64_t k_sh, int64_t k_sl, int64_t v_sb, int64_t v_sh, int64_t v_sl,
+                                 int64_t o_sb, int64_t o_sh, int64_t o_sl, float scale, void* stream) {
+    return attention_fwd_plain("vap_attention_fwd_accumulate", 1, q, k, v, o, lse, B, H, Lq, Lkv, D, q_sb, q_sh, q_sl, k_sb, k_sh, k_sl, v_sb, v_sh, v_sl, o_sb,
+                               o_sh, o_sl, scale, stream);
 }
 
 int vap_attention_fwd_scatter(const void* q, const void* k, const void* v, void* const* o_peers, int npeers, int o_rows_per_peer, float* lse,

@@ -63,6 +63,9 @@ struct AttnParams {
     //     launch_attention_combine merges the partials.  Fills the SMs when B * H * ceil(Lq / 256) is a poor multiple of their number.
     int kv_splits;
     int64_t o_split_stride, lse_split_stride;  // elements
+    // --- accumulate != 0 (plain mode only): o <- bf16(float(o) + float(bf16(O / l))), the bf16 tensor add the reference performs on the
+    //     outputs of its two cross-attention softmaxes (transformer_wan_mot.py:186), fused into the second launch's epilogue
+    int accumulate;
 };
 struct AttnTensor {
     const __nv_bfloat16* ptr;

@@ -147,11 +147,14 @@ def qk_norm_rope_(q: torch.Tensor, k: Optional[torch.Tensor], *, heads: int, hea
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: Optional[float] = None, out: Optional[torch.Tensor] = None,
-              return_lse: bool = False):
+              return_lse: bool = False, accumulate: bool = False):
     """Non-causal, unmasked attention.  q [B,H,Lq,D], k/v [B,H,Lkv,D] (any batch/head/token strides, D contiguous).
 
     Returns O with logical shape [B,H,Lq,D] laid out token-major ([B,Lq,H,D] memory), so that
-    ``o.transpose(1, 2).flatten(2, 3)`` — what every reference processor does next — is a free view."""
+    ``o.transpose(1, 2).flatten(2, 3)`` — what every reference processor does next — is a free view.
+    accumulate=True (needs `out`): the result is ADDED to what `out` holds, as a bf16 tensor add (vap_attention_fwd_accumulate)."""
+    if accumulate and out is None:
+        raise ValueError("accumulate=True adds to an existing output: pass out=")
     for t, n in ((q, "q"), (k, "k"), (v, "v")):
         _need_cuda_bf16(t, n)
         if t.dim() != 4 or t.stride(-1) != 1:
@@ -160,7 +163,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: Optio
     Lkv = k.shape[2]
     if k.shape != (B, H, Lkv, D) or v.shape != (B, H, Lkv, D):
         raise ValueError(f"q {tuple(q.shape)}, k {tuple(k.shape)}, v {tuple(v.shape)} are inconsistent")
-    if not return_lse and Lq > 0:
+    if not return_lse and not accumulate and Lq > 0:
         splits = _auto_kv_splits(B, H, Lq, Lkv)
         if splits > 1:  # the work items are a poor multiple of the SM count: cut the KV sequence and merge (see attention_kv_splits)
             return attention_splitkv(q, k, v, splits, scale=scale, out=out)
@@ -173,10 +176,11 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: Optio
     if scale is None:
         scale = D ** -0.5
     lib = _lib.load()
-    rc = lib.vap_attention_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr() if lse is not None else 0, B, H, Lq,
-                               Lkv, D, q.stride(0), q.stride(1), q.stride(2), k.stride(0), k.stride(1), k.stride(2), v.stride(0),
-                               v.stride(1), v.stride(2), out.stride(0), out.stride(1), out.stride(2), float(scale), _stream())
-    _lib.check(rc, "vap_attention_fwd")
+    fn = lib.vap_attention_fwd_accumulate if accumulate else lib.vap_attention_fwd
+    rc = fn(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr() if lse is not None else 0, B, H, Lq,
+            Lkv, D, q.stride(0), q.stride(1), q.stride(2), k.stride(0), k.stride(1), k.stride(2), v.stride(0),
+            v.stride(1), v.stride(2), out.stride(0), out.stride(1), out.stride(2), float(scale), _stream())
+    _lib.check(rc, "vap_attention_fwd_accumulate" if accumulate else "vap_attention_fwd")
     return (out, lse) if return_lse else out
 
 

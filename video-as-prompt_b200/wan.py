@@ -239,12 +239,11 @@ def _cross_attn(attn: nn.Module, x: torch.Tensor, ctx: torch.Tensor, num_mot_ref
     kv = _cached(attn, "kv", (ctx,), text_kv)  # keyed on the whole context tensor: ctx_txt / ctx_img are fresh views of it
     qh = _heads_view(q, heads)
     o = ops.attention(qh, _heads_view(kv[..., :inner], heads), _heads_view(kv[..., inner:], heads))
-    o = _token_major(o)
     if img_len > 0:
         kvi = _cached(attn, "kv_img", (ctx,), image_kv)
-        o_img = _token_major(ops.attention(qh, _heads_view(kvi[..., :inner], heads), _heads_view(kvi[..., inner:], heads)))
-        o = o + o_img  # two independent softmaxes summed in bf16 (:186)
-    return o
+        # two independent softmaxes summed as bf16 tensors (:186): the second launch's epilogue adds to the first one's output
+        ops.attention(qh, _heads_view(kvi[..., :inner], heads), _heads_view(kvi[..., inner:], heads), out=o, accumulate=True)
+    return _token_major(o)
 
 
 def _joint_attention(qkv: torch.Tensor, heads: int) -> torch.Tensor:
