@@ -39,6 +39,19 @@ def cosine(a, b):
     return (torch.dot(a, b) / (a.norm() * b.norm())).item()
 
 
+def _with_env(env, fn, **kw):
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        return fn(**kw)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
 def _randn(shape, seed, scale=1.0, dtype=torch.bfloat16):
     g = torch.Generator().manual_seed(seed)
     return (torch.randn(shape, generator=g) * scale).to(dtype)
@@ -545,10 +558,12 @@ def check_ulysses_p2p_emulated(P=4, L=96, H=8, D=128, mode=0):
         bq, bk = (torch.randn(D, generator=g) * 0.1).to(DEV), (torch.randn(D, generator=g) * 0.1).to(DEV)
     ang = torch.rand((J, D // 2), generator=g) * 6.28
     cos, sin = torch.cos(ang).to(DEV).contiguous(), torch.sin(ang).to(DEV).contiguous()
-    # reference: one device, no exchange
+    # reference: one device, no exchange.  The scatter mode runs on the register kernel; the in-place reference is pinned to the same kernel
+    # (VAP_NORM_STAGED is read per call) because the staged kernel sums a row's squares in another order — equal within fp32 rounding
+    # (qk_wan_staged checks it against the oracle), but this check is about the exchange and asks for bit-exactness.
     ref_qkv = qkv.clone()
-    ops.qk_norm_rope_(ref_qkv[:, :d], ref_qkv[:, d:2 * d], heads=H, head_dim=D, wq=wq, wk=wk, bq=bq, bk=bk, cos=cos, sin=sin, rows_per_batch=J, eps=1e-6,
-                      mode=mode)
+    _with_env({"VAP_NORM_STAGED": "0"}, ops.qk_norm_rope_, q=ref_qkv[:, :d], k=ref_qkv[:, d:2 * d], heads=H, head_dim=D, wq=wq, wk=wk, bq=bq, bk=bk, cos=cos,
+              sin=sin, rows_per_batch=J, eps=1e-6, mode=mode)
     q, k, v = (ref_qkv[None, :, i * d:(i + 1) * d].unflatten(2, (H, D)).transpose(1, 2) for i in range(3))
     o_ref = ops.attention(q, k, v).transpose(1, 2).flatten(2, 3)[0]  # [J, d]
     # emulated ranks
@@ -616,19 +631,6 @@ def check_attention_bwd(B=1, H=2, Lq=300, Lkv=300, D=128, joint_layout=True, see
     errs_seam = [rel_err(t.grad, b) for t, b in zip(leaves, ref)]
     assert max(errs) <= tol and max(errs_seam) <= tol, f"attention bwd B={B} H={H} Lq={Lq} Lkv={Lkv} D={D}: dq/dk/dv rel err {errs}, via autograd {errs_seam}"
     return dict(dq=errs[0], dk=errs[1], dv=errs[2], seam=max(errs_seam))
-
-
-def _with_env(env, fn, **kw):
-    old = {k: os.environ.get(k) for k in env}
-    os.environ.update(env)
-    try:
-        return fn(**kw)
-    finally:
-        for k, v in old.items():
-            if v is None:
-                os.environ.pop(k, None)
-            else:
-                os.environ[k] = v
 
 
 def check_attention_bwd_split1(**kw):

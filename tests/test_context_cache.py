@@ -106,3 +106,29 @@ def test_context_cache_is_bit_exact_and_skips_the_constant_projections():
     assert res["batch_cfg_launches_cache_0"] < res["sequential_launches"], res
     # the expert stream of the last MoT block loses its O-projection, 4 cross-attention projections and 2 FFN GEMMs
     assert res["dead_skip_exact"] and res["dead_skip_linears"][0] - res["dead_skip_linears"][1] == 7, res
+
+
+def test_cache_entries_die_with_their_inputs():
+    """An entry holds only weak references to its input tensors: once the input is gone (a shell that builds a fresh context tensor every forward,
+    like the reference's) the entry is purged at the next lookup — nothing stays pinned, and a new tensor at the same address cannot hit it."""
+    import gc
+    import importlib
+    vap = importlib.import_module("video-as-prompt_b200")
+    wan = vap.wan
+    owner = torch.nn.Linear(2, 2)
+    calls = []
+
+    def compute():
+        calls.append(1)
+        return torch.zeros(1)
+
+    with wan.context_cache():
+        a = torch.randn(4, 8)
+        wan._cached(owner, "kv", (a, None), compute)
+        wan._cached(owner, "kv", (a, None), compute)
+        assert len(calls) == 1 and len(owner.__dict__["_vap_ctx_cache"]["kv"]) == 1
+        del a
+        gc.collect()
+        b = torch.randn(4, 8)  # may or may not reuse a's storage: either way it must miss
+        wan._cached(owner, "kv", (b, None), compute)
+        assert len(calls) == 2 and len(owner.__dict__["_vap_ctx_cache"]["kv"]) == 1  # the dead entry was purged, not kept beside the new one

@@ -77,6 +77,9 @@ def load() -> ctypes.CDLL:
 
 
 def check(rc: int, what: str) -> None:
+    """rc != 0 -> VapError with the library's message.  (A kernel that dies LATER with "unspecified launch failure" hit the mbarrier watchdog —
+    a protocol bug; `python video-as-prompt_b200/csrc/build.py --debug` builds libvap_b200_debug.so, which prints the barrier, block and thread
+    before it traps: re-run with VAP_B200_LIB pointing at it.)"""
     if rc != 0:
         msg = load().vap_last_error().decode("utf-8", "replace")
         raise VapError(f"{what} failed (rc={rc}): {msg}")

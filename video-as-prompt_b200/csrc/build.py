@@ -1,6 +1,7 @@
 """Build libvap_b200.so in-tree with nvcc for sm_100a (no torch / pybind involvement: the boundary is a plain C ABI).
 
     python video-as-prompt_b200/csrc/build.py [--force] [--verbose]
+    python video-as-prompt_b200/csrc/build.py --debug      # libvap_b200_debug.so: mbarrier watchdog timeouts print before they trap
 
 Objects are compiled in parallel (one nvcc per translation unit) and linked into
 ``video-as-prompt_b200/libvap_b200.so``.  A content hash of the sources + flags is stored next to the library so
@@ -81,6 +82,35 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+def build_debug() -> Path:
+    """libvap_b200_debug.so: the same sources with -DVAP_MBAR_VERBOSE — a kernel whose mbarrier wait times out (a protocol bug; the product build
+    traps silently because a printf in that path costs the attention kernel 5 % of its throughput) prints the barrier, block and thread first.
+    Select it with VAP_B200_LIB=<path> when a launch dies with "unspecified launch failure"."""
+    out = PKG / "libvap_b200_debug.so"
+    dbg = BUILD / "debug"
+    dbg.mkdir(parents=True, exist_ok=True)
+
+    def compile_one(src: str):
+        obj = dbg / (Path(src).stem + ".o")
+        return src, obj, subprocess.run([NVCC, *FLAGS, "-DVAP_MBAR_VERBOSE", "-c", str(CSRC / src), "-o", str(obj)], capture_output=True, text=True)
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        results = list(ex.map(compile_one, SOURCES))
+    for src, _, r in results:
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError(f"nvcc failed on {src}")
+    r = subprocess.run([NVCC, "-shared", "-o", str(out), *[str(o) for _, o, _ in results], "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart_static", "-ldl",
+                        "-lpthread", "-lrt"], capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("link failed")
+    return out
+
+
 if __name__ == "__main__":
+    if "--debug" in sys.argv:
+        print(f"compiled: {build_debug()}")
+        sys.exit(0)
     lib = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
     print(f"{LAST_BUILD}: {lib}")

@@ -121,7 +121,8 @@ __device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
 // Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU box.  The bound is a spin counter and a bare
 // trap: a printf in the timeout path costs a stack frame and registers in every kernel that waits, and in the attention kernel
 // (whose softmax warps spend a third of their time in this loop) 5 % of its throughput.  -DVAP_MBAR_VERBOSE brings the message
-// back for bring-up.
+// back: `python video-as-prompt_b200/csrc/build.py --debug` builds libvap_b200_debug.so with it (select with VAP_B200_LIB=...), the
+// library to re-run a launch with that died with "unspecified launch failure".
 #ifndef VAP_MBAR_SPIN_LIMIT
 #define VAP_MBAR_SPIN_LIMIT (1u << 21)  // ~9 s of try_wait rounds (4.3 us each, measured): no legitimate wait comes near it
 #endif

@@ -41,6 +41,11 @@ def _need_cuda_bf16(t: torch.Tensor, name: str) -> None:
         raise VapError(f"{name} is on {t.device}: the VAP kernels are CUDA-only (sm_100a); there is no CPU fallback")
     if t.dtype != torch.bfloat16:
         raise TypeError(f"{name} must be torch.bfloat16, got {t.dtype}")
+    if t.device.index != torch.cuda.current_device():
+        # the launch goes to the CURRENT device's stream: a process that drives several GPUs (e.g. an accelerate device_map) must select the
+        # tensor's device first, as torch's own kernels do internally
+        raise VapError(f"{name} lives on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}: "
+                       f"wrap the call in `with torch.cuda.device({t.device.index}):`")
 
 
 def _need_cuda_float(t: torch.Tensor, name: str) -> None:

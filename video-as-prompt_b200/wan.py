@@ -17,6 +17,7 @@ Data layout of one MoT block on the device (B = 1 per CFG pass, S target tokens,
 from __future__ import annotations
 
 import math
+import weakref
 from typing import Any, Dict, List, Optional, Tuple, Union
 
 import torch
@@ -33,7 +34,7 @@ TEXT_CONTEXT_LEN = 512  # hardcoded by the reference (:126-127)
 # context cache: inside a denoise loop the text / CLIP context of a stream is the same tensor at every step and
 # in both classifier-free-guidance passes, so its embedding and every block's cross-attention K / V (projection + RMSNorm) can be
 # computed once.  Off by default (a benchmark step recomputes everything); `with context_cache():` around the loop turns it on.
-# Entries are keyed by the identity of the INPUT tensor (storage pointer, version counter, shape) and hold a reference to it, so a
+# Entries are keyed by the identity of the INPUT tensor (storage pointer, version counter, shape) and die with it (weak references), so a
 # recycled allocation can never alias; at most `_CTX_SLOTS` contexts (conditional + unconditional) are kept per module.
 # ----------------------------------------------------------------------------------------------
 _CTX_CACHE_ON = [False]
@@ -67,17 +68,21 @@ def _tensor_key(*tensors):
 
 
 def _cached(owner: nn.Module, slot: str, inputs, compute):
-    """compute() memoised on the identity of `inputs` while the context cache is on (LRU of _CTX_SLOTS entries per owner and slot)."""
+    """compute() memoised on the identity of `inputs` while the context cache is on (LRU of _CTX_SLOTS entries per owner and slot).
+    An entry lives only as long as its input tensors do (weak references, checked before any key comparison): a recycled allocation can
+    therefore never alias a dead entry, and a shell that hands the blocks a FRESH context tensor at every forward (the reference's own
+    forward concatenates image and text embeddings anew, transformer_wan_mot.py:979-982) never hits but also pins nothing beyond one forward."""
     if not _CTX_CACHE_ON[0]:
         return compute()
     entries = owner.__dict__.setdefault("_vap_ctx_cache", {}).setdefault(slot, [])
+    entries[:] = [e for e in entries if all(r is None or r() is not None for r in e[1])]
     key = _tensor_key(*inputs)
     for n, (k, _, val) in enumerate(entries):
         if k == key:
             entries.append(entries.pop(n))
             return val
     val = compute()
-    entries.append((key, tuple(inputs), val))  # the inputs are kept alive: their addresses cannot be reused while the entry exists
+    entries.append((key, tuple(None if t is None else weakref.ref(t) for t in inputs), val))
     del entries[:-_CTX_SLOTS]
     return val
 
