@@ -274,6 +274,20 @@ def check_attention_accumulate(D=128, H=3, Lq=700, kv=(257, 512)):
     return dict(bit_exact=True, err=err)
 
 
+def check_attention_variants():
+    """The two opt-in organisations of the forward kernel — one thread per query row (VAP_ATTN_SOFTMAX=row) and the CTA-pair kernel on
+    tcgen05.mma cta_group::2 (VAP_ATTN_PAIR=1, D = 128) — against the oracle on the shapes the default kernel is checked on (the switches are
+    read per call).  Both are measured slower or equal and stay opt-in; this keeps them correct."""
+    res = {}
+    for name, env in (("row", {"VAP_ATTN_SOFTMAX": "row"}), ("pair", {"VAP_ATTN_PAIR": "1"})):
+        res[name + "_d128"] = _with_env(env, check_attention, B=1, H=3, Lq=1000, Lkv=1000, D=128)["err"]
+        res[name + "_cross"] = _with_env(env, check_attention, B=1, H=2, Lq=600, Lkv=257, D=128, joint_layout=False)["err"]
+        res[name + "_peaky"] = _with_env(env, check_attention_peaky)["err"]
+        res[name + "_splitkv"] = _with_env(env, check_attention_splitkv, B=1, H=2, Lq=300, Lkv=1000, D=128, splits=2)["err"]
+    res["row_d64"] = _with_env({"VAP_ATTN_SOFTMAX": "row"}, check_attention, B=2, H=4, Lq=452, Lkv=452, D=64)["err"]
+    return res
+
+
 def check_attention_peaky(D=128):
     """Scores with a large dynamic range (exercises the lazy O-rescale path: the running max keeps growing by > 2^8)."""
     H, L = 2, 1024
@@ -789,6 +803,7 @@ CHECKS = {
     "attn_cross_512": lambda: check_attention(1, 2, 300, 512, 128, joint_layout=False),
     "attn_one_tile": lambda: check_attention(1, 1, 64, 100, 128, joint_layout=False),
     "attn_peaky": lambda: check_attention_peaky(),
+    "attn_variants_row_pair": check_attention_variants,
     "attn_accumulate": lambda: check_attention_accumulate(),
     "attn_accumulate_d64": lambda: check_attention_accumulate(D=64, H=2, Lq=300, kv=(100, 226)),
     "attn_splitkv_2": lambda: check_attention_splitkv(1, 2, 300, 1000, 128, 2),

@@ -4,7 +4,7 @@
     python tools/attn_ab.py [--rounds 2] [--shapes wan,cog,sp8] > gpurun_out/attn_ab.json   # on the GPU
 
 Every library (the in-tree one + build_variants/libvap_*.so) is loaded with ctypes and timed in each run-time mode
-(VAP_ATTN_SOFTMAX = lane16 | row, VAP_ATTN_CLUSTER = 0 | 2; both are read per call) on the joint-attention shapes of
+(VAP_ATTN_SOFTMAX = lane16 | row, VAP_ATTN_PAIR = 0 | 1, VAP_ATTN_CLUSTER = 0 | 2; all read per call) on the joint-attention shapes of
 BASELINE.json configs #2/#3, round-robin over `--rounds` rounds (thermal / power-cap drift hits every variant alike), beside
 torch SDPA's cuDNN backend on the same box.  Each variant is checked against torch SDPA on two heads before it is timed.
 """
@@ -58,7 +58,7 @@ def main():
         libs = {k: v for k, v in libs.items() if k in a.only.split(",")}
     variants = []
     for name in libs:
-        modes = ["row"] if name.startswith("row") else ["lane16"] if name.startswith("l16") else ["lane16", "row"]
+        modes = ["row"] if name.startswith("row") else ["lane16"] if name.startswith("l16") else ["pair"] if name.startswith("pair") else ["lane16", "pair", "row"]
         for m in modes:
             for cl in a.cl.split(","):
                 variants.append((name, m, cl))
@@ -85,7 +85,8 @@ def main():
     for rnd in range(a.rounds):
         for name, mode, cl in variants:
             use_lib(libs[name])
-            os.environ["VAP_ATTN_SOFTMAX"] = mode
+            os.environ["VAP_ATTN_SOFTMAX"] = "row" if mode == "row" else "lane16"
+            os.environ["VAP_ATTN_PAIR"] = "1" if mode == "pair" else "0"  # CTA-pair kernel (cta_group::2), D = 128 only
             os.environ["VAP_ATTN_CLUSTER"] = cl
             for sh, (q, k, v, ref, tail, flop) in data.items():
                 key = f"{sh}/{name}/{mode}/cl{cl}"
@@ -110,6 +111,7 @@ def main():
                     sys.exit(3)
         print(json.dumps({"round": rnd, **{k: v for k, v in res.items()}}), flush=True)
     os.environ.pop("VAP_ATTN_SOFTMAX", None)
+    os.environ.pop("VAP_ATTN_PAIR", None)
     os.environ.pop("VAP_ATTN_CLUSTER", None)
     best = {}
     for key, r in res.items():

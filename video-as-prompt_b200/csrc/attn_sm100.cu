@@ -338,24 +338,234 @@ struct AttnWork {
     }
 };
 
+// The softmax + epilogue warps of the 16-lane organisation (warps kFirstSoftmaxWarp ..), shared by the one-CTA kernel and the CTA-pair kernel
+// (kRemoteP: P is published on the LEADER CTA's barriers, where the pair's only MMA issuer waits).
+template <int D, bool kRemoteP, typename Smem>
+__device__ __forceinline__ void attn_softmax_lane16(const Smem& sm, const AttnParams& p, const AttnWork& wk, uint32_t tmem_base, int warp, int lane) {
+    using Cfg = AttnCfg<D>;
+    constexpr int kPolyPairs = (D == 128) ? VAP_ATTN_POLY_PAIRS_D128 : VAP_ATTN_POLY_PAIRS_D64;
+    const int q0 = wk.q0, head = wk.head, batch = wk.batch, j0 = wk.j0, n_kv = wk.n_kv;
+    const unsigned split = wk.split;
+    // ===== softmax + epilogue warps =====
+    const int sw = warp - kFirstSoftmaxWarp;
+    const int i = sw >> 3;         // Q tile
+    const int q = warp & 3;        // TMEM lane quarter this warp may touch
+    const int hl = (sw >> 2) & 1;  // which 16 lanes of the quarter
+    const int cp = lane & 3;       // column phase inside a quad
+    const int row0_in_tile = q * 32 + hl * 16 + (lane >> 2);  // this thread's rows: row0 and row0 + 8
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32 + hl * 16) << 16;
+    const uint32_t s_col = tmem_base + lane_addr + (i == 0 ? Cfg::kColS0 : Cfg::kColS1);
+    const uint32_t o_col = tmem_base + lane_addr + (i == 0 ? Cfg::kColO0 : Cfg::kColO1);
+    const float c = p.scale_log2;
+    const uint64_t c2 = pack_f32x2(c, c);
+    const float thr_off = kRescaleThreshold / c;
+    float m_used[2] = {-INFINITY, -INFINITY};  // the reference the accumulators of row r are scaled by (lazily updated)
+    float thr[2] = {-INFINITY, -INFINITY};     // m_used + 8 / c : a score above it forces a reference update
+    uint64_t nmc2[2] = {0ull, 0ull};           // packed (-m_used c, -m_used c)
+    uint64_t l2[2] = {0ull, 0ull};             // packed partial row sums of this thread's columns
+    long long* tr = (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && q == 0 && hl == 0 && lane == 0) ? p.trace + i * 512 : nullptr;
+#if VAP_ATTN_TRACE
+#define TR(k) do { if (tr && j < 64) tr[j * 8 + (k)] = clock64(); } while (0)
+#else
+#define TR(k) do { } while (0)
+#endif
+    for (int j = 0; j < n_kv; ++j) {
+        TR(0);
+        // s_full(i) phase j: QK_i(j) is complete, and with it PV_i(j-1) (issued earlier by the same thread), so O_i is
+        // quiescent until the first p_full arrive below
+#if VAP_ATTN_LEADER_WAIT
+        // Only ONE warp of the tile's eight polls the mbarrier; the others block on a named barrier, which costs no issue
+        // slots.  (Eight polling warps executed 39 % of the kernel's instructions and competed with the other tile's
+        // softmax for the same schedulers, profiles/r01_attn_v5_in_step.json.)
+        if ((sw & 7) == 0) VAP_SM_WAIT(sm.s_full(i), j & 1);
+        named_bar_sync(1 + i, 256);
+#else
+        VAP_SM_WAIT(sm.s_full(i), j & 1);
+#endif
+        tc_fence_after();
+        TR(1);
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            uint32_t sr[32];  // sr[4g + e]: columns 64 ch + 8 g + 2 cp + (e & 1) of row0 (e < 2) / row0 + 8 (e >= 2)
+            tmem_ld_16x256b_x8(s_col + 64 * ch, sr);
+            tmem_ld_wait();
+            if (ch == 0) TR(2);
+            const int valid = p.Lkv - (j0 + j) * kBlockN - 64 * ch - 2 * cp;  // this thread's column 8 g + e is inside the sequence iff 8 g + e < valid
+            if (valid < 58) {
+#pragma unroll
+                for (int g = 0; g < 8; ++g)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (8 * g + (e & 1) >= valid) sr[4 * g + e] = __float_as_uint(-INFINITY);
+            }
+#define SF(x) __uint_as_float(sr[x])
+            // p = 2^(s*c - m*c) is computed SPECULATIVELY against the current reference; the warp votes afterwards on whether
+            // any score sat more than 2^8 above it.  Only when the vote fires (always at the
+            // very first half-tile, rarely later) the reference is updated and the pass repeated — so the common step has
+            // no max -> exp dependency.  Packed FFMA2 for the scale/shift, MUFU.EX2 for most pairs and the FMA-pipe
+            // polynomial for kPolyPairs of every 8 pairs (tools/softmax_pipe_probe.cu: MUFU.EX2 costs 8 clk per warp
+            // instruction, the polynomial 9 clk per element of FMA pipe: they only pay off side by side).
+            uint32_t pk[16];  // pk[2g] = row0, pk[2g+1] = row0 + 8 : packed P column 32 ch + 4 g + cp
+            uint64_t ls[2];
+#pragma unroll 1
+            for (int pass = 0;; ++pass) {  // at most two passes: the second one runs against the refreshed reference
+                ls[0] = 0ull, ls[1] = 0ull;
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {  // pair e: group g = e / 2, row r = e & 1
+                    const int r = e & 1;
+                    const uint64_t x2 = fma_f32x2(pack_f32x2(SF(2 * e), SF(2 * e + 1)), c2, nmc2[r]);
+                    float x0, x1, p0, p1;
+                    unpack_f32x2(x2, x0, x1);
+                    if ((e & 7) < kPolyPairs) {
+                        ex2_poly_x2(x0, x1, p0, p1);
+                    } else {
+                        p0 = ex2_approx(x0);
+                        p1 = ex2_approx(x1);
+                    }
+                    ls[r] = add_f32x2(ls[r], pack_f32x2(p0, p1));
+                    pk[e] = pack_bf16x2(p0, p1);
+                }
+                // Vote: does any score of this half-tile sit more than 2^8 above the reference?  The MUFU pairs are judged by
+                // their results (a p > 2^8 makes this thread's partial row sum > 2^8; ex2.approx overflows cleanly to +inf), the
+                // polynomial pairs by their scores (the exponent-field arithmetic is only valid for x < 128).  A false positive
+                // merely refreshes the reference.  The very first half-tile always votes yes (no reference yet).
+                float lo0, hi0, lo1, hi1;
+                unpack_f32x2(ls[0], lo0, hi0);
+                unpack_f32x2(ls[1], lo1, hi1);
+                bool need = (lo0 + hi0 > kSumTrigger) || (lo1 + hi1 > kSumTrigger) || (m_used[0] == -INFINITY);
+                if constexpr (kPolyPairs > 0) {
+                    float pm0 = -INFINITY, pm1 = -INFINITY;
+#pragma unroll
+                    for (int e = 0; e < 16; ++e)
+                        if ((e & 7) < kPolyPairs) {
+                            if (e & 1) pm1 = fmax3(pm1, SF(2 * e), SF(2 * e + 1));
+                            else pm0 = fmax3(pm0, SF(2 * e), SF(2 * e + 1));
+                        }
+                    need = need || (pm0 > thr[0]) || (pm1 > thr[1]);
+                }
+                if (pass == 1 || !__any_sync(0xffffffffu, need)) break;
+                float mx0 = fmax3(SF(0), SF(1), SF(4)), mx1 = fmax3(SF(2), SF(3), SF(6));
+                mx0 = fmax3(mx0, SF(5), SF(8)), mx1 = fmax3(mx1, SF(7), SF(10));
+#pragma unroll
+                for (int g = 2; g < 7; ++g) {
+                    mx0 = fmax3(mx0, SF(4 * g + 1), SF(4 * g + 4));
+                    mx1 = fmax3(mx1, SF(4 * g + 3), SF(4 * g + 6));
+                }
+                mx0 = fmaxf(mx0, SF(29));
+                mx1 = fmaxf(mx1, SF(31));
+                // ---- reference update: quad-reduce the row maxima, rescale this warp's 16 rows of O, repeat the pass ----
+                mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+                mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+                mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+                mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+                const float mn0 = fmaxf(m_used[0], mx0), mn1 = fmaxf(m_used[1], mx1);
+                if (j > 0 || ch > 0) {
+                    if (ch > 0) {  // the PV MMAs of this step's first half must have left O_i
+                        mbar_wait(sm.pv_half(i), j & 1);
+                        tc_fence_after();
+                    }
+                    const float f0 = ex2_approx((m_used[0] - mn0) * c), f1 = ex2_approx((m_used[1] - mn1) * c);
+                    l2[0] = mul_f32x2(l2[0], pack_f32x2(f0, f0));
+                    l2[1] = mul_f32x2(l2[1], pack_f32x2(f1, f1));
+#pragma unroll 1
+                    for (int g = 0; g < D / 32; ++g) {
+                        uint32_t ov[16];
+                        tmem_ld_16x256b_x4(o_col + 32 * g, ov);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * ((e & 2) ? f1 : f0));
+                        tmem_st_16x256b_x4(o_col + 32 * g, ov);
+                    }
+                }
+                m_used[0] = mn0, m_used[1] = mn1;
+                thr[0] = mn0 + thr_off, thr[1] = mn1 + thr_off;
+                nmc2[0] = pack_f32x2(-mn0 * c, -mn0 * c), nmc2[1] = pack_f32x2(-mn1 * c, -mn1 * c);
+            }
+#undef SF
+            if (ch == 0) TR(3);
+            l2[0] = add_f32x2(l2[0], ls[0]);
+            l2[1] = add_f32x2(l2[1], ls[1]);
+            // P is published the moment it is stored: PV of the first half has to be out of the way before the second half ends.  (Tried on a
+            // B200 and slower: loading the second half's scores before this store, 1404 -> 1312 TFLOP/s, and publishing half 0 from inside the
+            // second half's pass to hide the store latency, -> 1185: every clock P half 0 is late moves its PV into the tail, profiles/r02_attn_ab.json.)
+            tmem_st_16x128b_x8(s_col + 32 * ch, pk);
+            if (ch == 1) TR(5);
+            tmem_st_wait();  // covers the rescaled O columns too
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (kRemoteP) mbar_arrive_remote(sm.p_full(i, ch), 0);  // the pair's MMA issuer lives in the leader CTA
+                else mbar_arrive(sm.p_full(i, ch));
+            }
+        }
+        TR(6);
+    }
+    // ===== epilogue: O / l -> bf16 -> global; the quad of a row writes 16 contiguous bytes per 8-column group =====
+    {
+        float l[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            float lo, hi;
+            unpack_f32x2(l2[r], lo, hi);
+            l[r] = lo + hi;
+            l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
+            l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
+        }
+        mbar_wait(sm.o_done(i), 0);
+        tc_fence_after();
+        const float inv_l[2] = {1.f / l[0], 1.f / l[1]};
+        const int row[2] = {q0 + i * kBlockM + row0_in_tile, q0 + i * kBlockM + row0_in_tile + 8};
+        // plain mode: one output tensor; peer mode (Ulysses exchange #2 fused into the epilogue): the query rows of rank r are
+        // stored straight into rank r's output buffer over NVLink
+        __nv_bfloat16* obase[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            if (p.o_rows_per_peer > 0) {
+                const int peer = row[r] / p.o_rows_per_peer;
+                obase[r] = (peer < 8 ? p.o_peer[peer] : p.o_peer[0]) + batch * p.o_sb + head * p.o_sh + 2 * cp +
+                           static_cast<int64_t>(row[r] - peer * p.o_rows_per_peer) * p.o_sl;
+            } else {
+                obase[r] = p.o + static_cast<uint64_t>(split) * static_cast<uint64_t>(p.o_split_stride) + batch * p.o_sb + head * p.o_sh + 2 * cp + static_cast<int64_t>(row[r]) * p.o_sl;
+            }
+        }
+#pragma unroll 1
+        for (int g4 = 0; g4 < D / 32; ++g4) {
+            uint32_t ov[16];
+            tmem_ld_16x256b_x4(o_col + 32 * g4, ov);
+            tmem_ld_wait();
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                if (row[r] < p.Lq) {
+                    __nv_bfloat16* orow = obase[r] + 32 * g4;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        uint32_t w = pack_bf16x2(__uint_as_float(ov[4 * g + 2 * r]) * inv_l[r], __uint_as_float(ov[4 * g + 2 * r + 1]) * inv_l[r]);
+                        if (p.accumulate) w = add_bf16x2_as_tensors(*reinterpret_cast<const uint32_t*>(orow + 8 * g), w);
+                        *reinterpret_cast<uint32_t*>(orow + 8 * g) = w;
+                    }
+                }
+            }
+        }
+        if (p.lse && cp == 0) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+                if (row[r] < p.Lq)
+                    p.lse[static_cast<uint64_t>(split) * static_cast<uint64_t>(p.lse_split_stride) + (static_cast<int64_t>(batch) * p.H + head) * p.Lq + row[r]] = m_used[r] * p.scale + logf(l[r]);
+        }
+    }
+}
+
 template <int D, int CL>
 __global__ void __launch_bounds__(kAttnThreads, 1)  // registers are granted per 4 warps: 18 warps cost 20 -> 96 per thread
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
     using Cfg = AttnCfg<D>;
-    constexpr int kPolyPairs = (D == 128) ? VAP_ATTN_POLY_PAIRS_D128 : VAP_ATTN_POLY_PAIRS_D64;
     extern __shared__ uint8_t smem_raw[];
     const AttnSmem<D> sm((smem_u32(smem_raw) + 1023u) & ~1023u);
-    auto s_full = [&](int i) { return sm.s_full(i); };
-    auto p_full = [&](int i, int c) { return sm.p_full(i, c); };
-    auto pv_half = [&](int i) { return sm.pv_half(i); };
-    auto o_done = [&](int i) { return sm.o_done(i); };
-
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const AttnWork wk(p);
     const int q0 = wk.q0, head = wk.head, batch = wk.batch, j0 = wk.j0, n_kv = wk.n_kv;
-    const unsigned split = wk.split;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQ);
@@ -382,210 +592,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             attn_mma_warp<D, CL>(sm, tmem_base, n_kv, (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) ? p.trace + 1024 : nullptr);
         }
     } else {
-        // ===== softmax + epilogue warps =====
-        const int sw = warp - kFirstSoftmaxWarp;
-        const int i = sw >> 3;         // Q tile
-        const int q = warp & 3;        // TMEM lane quarter this warp may touch
-        const int hl = (sw >> 2) & 1;  // which 16 lanes of the quarter
-        const int cp = lane & 3;       // column phase inside a quad
-        const int row0_in_tile = q * 32 + hl * 16 + (lane >> 2);  // this thread's rows: row0 and row0 + 8
-        const uint32_t lane_addr = static_cast<uint32_t>(q * 32 + hl * 16) << 16;
-        const uint32_t s_col = tmem_base + lane_addr + (i == 0 ? Cfg::kColS0 : Cfg::kColS1);
-        const uint32_t o_col = tmem_base + lane_addr + (i == 0 ? Cfg::kColO0 : Cfg::kColO1);
-        const float c = p.scale_log2;
-        const uint64_t c2 = pack_f32x2(c, c);
-        const float thr_off = kRescaleThreshold / c;
-        float m_used[2] = {-INFINITY, -INFINITY};  // the reference the accumulators of row r are scaled by (lazily updated)
-        float thr[2] = {-INFINITY, -INFINITY};     // m_used + 8 / c : a score above it forces a reference update
-        uint64_t nmc2[2] = {0ull, 0ull};           // packed (-m_used c, -m_used c)
-        uint64_t l2[2] = {0ull, 0ull};             // packed partial row sums of this thread's columns
-        long long* tr = (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && q == 0 && hl == 0 && lane == 0) ? p.trace + i * 512 : nullptr;
-#if VAP_ATTN_TRACE
-#define TR(k) do { if (tr && j < 64) tr[j * 8 + (k)] = clock64(); } while (0)
-#else
-#define TR(k) do { } while (0)
-#endif
-        for (int j = 0; j < n_kv; ++j) {
-            TR(0);
-            // s_full(i) phase j: QK_i(j) is complete, and with it PV_i(j-1) (issued earlier by the same thread), so O_i is
-            // quiescent until the first p_full arrive below
-#if VAP_ATTN_LEADER_WAIT
-            // Only ONE warp of the tile's eight polls the mbarrier; the others block on a named barrier, which costs no issue
-            // slots.  (Eight polling warps executed 39 % of the kernel's instructions and competed with the other tile's
-            // softmax for the same schedulers, profiles/r01_attn_v5_in_step.json.)
-            if ((sw & 7) == 0) VAP_SM_WAIT(s_full(i), j & 1);
-            named_bar_sync(1 + i, 256);
-#else
-            VAP_SM_WAIT(s_full(i), j & 1);
-#endif
-            tc_fence_after();
-            TR(1);
-#pragma unroll
-            for (int ch = 0; ch < 2; ++ch) {
-                uint32_t sr[32];  // sr[4g + e]: columns 64 ch + 8 g + 2 cp + (e & 1) of row0 (e < 2) / row0 + 8 (e >= 2)
-                tmem_ld_16x256b_x8(s_col + 64 * ch, sr);
-                tmem_ld_wait();
-                if (ch == 0) TR(2);
-                const int valid = p.Lkv - (j0 + j) * kBlockN - 64 * ch - 2 * cp;  // this thread's column 8 g + e is inside the sequence iff 8 g + e < valid
-                if (valid < 58) {
-#pragma unroll
-                    for (int g = 0; g < 8; ++g)
-#pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            if (8 * g + (e & 1) >= valid) sr[4 * g + e] = __float_as_uint(-INFINITY);
-                }
-#define SF(x) __uint_as_float(sr[x])
-                // p = 2^(s*c - m*c) is computed SPECULATIVELY against the current reference; the warp votes afterwards on whether
-                // any score sat more than 2^8 above it.  Only when the vote fires (always at the
-                // very first half-tile, rarely later) the reference is updated and the pass repeated — so the common step has
-                // no max -> exp dependency.  Packed FFMA2 for the scale/shift, MUFU.EX2 for most pairs and the FMA-pipe
-                // polynomial for kPolyPairs of every 8 pairs (tools/softmax_pipe_probe.cu: MUFU.EX2 costs 8 clk per warp
-                // instruction, the polynomial 9 clk per element of FMA pipe: they only pay off side by side).
-                uint32_t pk[16];  // pk[2g] = row0, pk[2g+1] = row0 + 8 : packed P column 32 ch + 4 g + cp
-                uint64_t ls[2];
-#pragma unroll 1
-                for (int pass = 0;; ++pass) {  // at most two passes: the second one runs against the refreshed reference
-                    ls[0] = 0ull, ls[1] = 0ull;
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) {  // pair e: group g = e / 2, row r = e & 1
-                        const int r = e & 1;
-                        const uint64_t x2 = fma_f32x2(pack_f32x2(SF(2 * e), SF(2 * e + 1)), c2, nmc2[r]);
-                        float x0, x1, p0, p1;
-                        unpack_f32x2(x2, x0, x1);
-                        if ((e & 7) < kPolyPairs) {
-                            ex2_poly_x2(x0, x1, p0, p1);
-                        } else {
-                            p0 = ex2_approx(x0);
-                            p1 = ex2_approx(x1);
-                        }
-                        ls[r] = add_f32x2(ls[r], pack_f32x2(p0, p1));
-                        pk[e] = pack_bf16x2(p0, p1);
-                    }
-                    // Vote: does any score of this half-tile sit more than 2^8 above the reference?  The MUFU pairs are judged by
-                    // their results (a p > 2^8 makes this thread's partial row sum > 2^8; ex2.approx overflows cleanly to +inf), the
-                    // polynomial pairs by their scores (the exponent-field arithmetic is only valid for x < 128).  A false positive
-                    // merely refreshes the reference.  The very first half-tile always votes yes (no reference yet).
-                    float lo0, hi0, lo1, hi1;
-                    unpack_f32x2(ls[0], lo0, hi0);
-                    unpack_f32x2(ls[1], lo1, hi1);
-                    bool need = (lo0 + hi0 > kSumTrigger) || (lo1 + hi1 > kSumTrigger) || (m_used[0] == -INFINITY);
-                    if constexpr (kPolyPairs > 0) {
-                        float pm0 = -INFINITY, pm1 = -INFINITY;
-#pragma unroll
-                        for (int e = 0; e < 16; ++e)
-                            if ((e & 7) < kPolyPairs) {
-                                if (e & 1) pm1 = fmax3(pm1, SF(2 * e), SF(2 * e + 1));
-                                else pm0 = fmax3(pm0, SF(2 * e), SF(2 * e + 1));
-                            }
-                        need = need || (pm0 > thr[0]) || (pm1 > thr[1]);
-                    }
-                    if (pass == 1 || !__any_sync(0xffffffffu, need)) break;
-                    float mx0 = fmax3(SF(0), SF(1), SF(4)), mx1 = fmax3(SF(2), SF(3), SF(6));
-                    mx0 = fmax3(mx0, SF(5), SF(8)), mx1 = fmax3(mx1, SF(7), SF(10));
-#pragma unroll
-                    for (int g = 2; g < 7; ++g) {
-                        mx0 = fmax3(mx0, SF(4 * g + 1), SF(4 * g + 4));
-                        mx1 = fmax3(mx1, SF(4 * g + 3), SF(4 * g + 6));
-                    }
-                    mx0 = fmaxf(mx0, SF(29));
-                    mx1 = fmaxf(mx1, SF(31));
-                    // ---- reference update: quad-reduce the row maxima, rescale this warp's 16 rows of O, repeat the pass ----
-                    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-                    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-                    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-                    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-                    const float mn0 = fmaxf(m_used[0], mx0), mn1 = fmaxf(m_used[1], mx1);
-                    if (j > 0 || ch > 0) {
-                        if (ch > 0) {  // the PV MMAs of this step's first half must have left O_i
-                            mbar_wait(pv_half(i), j & 1);
-                            tc_fence_after();
-                        }
-                        const float f0 = ex2_approx((m_used[0] - mn0) * c), f1 = ex2_approx((m_used[1] - mn1) * c);
-                        l2[0] = mul_f32x2(l2[0], pack_f32x2(f0, f0));
-                        l2[1] = mul_f32x2(l2[1], pack_f32x2(f1, f1));
-#pragma unroll 1
-                        for (int g = 0; g < D / 32; ++g) {
-                            uint32_t ov[16];
-                            tmem_ld_16x256b_x4(o_col + 32 * g, ov);
-                            tmem_ld_wait();
-#pragma unroll
-                            for (int e = 0; e < 16; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * ((e & 2) ? f1 : f0));
-                            tmem_st_16x256b_x4(o_col + 32 * g, ov);
-                        }
-                    }
-                    m_used[0] = mn0, m_used[1] = mn1;
-                    thr[0] = mn0 + thr_off, thr[1] = mn1 + thr_off;
-                    nmc2[0] = pack_f32x2(-mn0 * c, -mn0 * c), nmc2[1] = pack_f32x2(-mn1 * c, -mn1 * c);
-                }
-#undef SF
-                if (ch == 0) TR(3);
-                l2[0] = add_f32x2(l2[0], ls[0]);
-                l2[1] = add_f32x2(l2[1], ls[1]);
-                // P is published the moment it is stored: PV of the first half has to be out of the way before the second half ends.  (Tried on a
-                // B200 and slower: loading the second half's scores before this store, 1404 -> 1312 TFLOP/s, and publishing half 0 from inside the
-                // second half's pass to hide the store latency, -> 1185: every clock P half 0 is late moves its PV into the tail, profiles/r02_attn_ab.json.)
-                tmem_st_16x128b_x8(s_col + 32 * ch, pk);
-                if (ch == 1) TR(5);
-                tmem_st_wait();  // covers the rescaled O columns too
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(p_full(i, ch));
-            }
-            TR(6);
-        }
-        // ===== epilogue: O / l -> bf16 -> global; the quad of a row writes 16 contiguous bytes per 8-column group =====
-        {
-            float l[2];
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                float lo, hi;
-                unpack_f32x2(l2[r], lo, hi);
-                l[r] = lo + hi;
-                l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
-                l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
-            }
-            mbar_wait(o_done(i), 0);
-            tc_fence_after();
-            const float inv_l[2] = {1.f / l[0], 1.f / l[1]};
-            const int row[2] = {q0 + i * kBlockM + row0_in_tile, q0 + i * kBlockM + row0_in_tile + 8};
-            // plain mode: one output tensor; peer mode (Ulysses exchange #2 fused into the epilogue): the query rows of rank r are
-            // stored straight into rank r's output buffer over NVLink
-            __nv_bfloat16* obase[2];
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                if (p.o_rows_per_peer > 0) {
-                    const int peer = row[r] / p.o_rows_per_peer;
-                    obase[r] = (peer < 8 ? p.o_peer[peer] : p.o_peer[0]) + batch * p.o_sb + head * p.o_sh + 2 * cp +
-                               static_cast<int64_t>(row[r] - peer * p.o_rows_per_peer) * p.o_sl;
-                } else {
-                    obase[r] = p.o + static_cast<uint64_t>(split) * static_cast<uint64_t>(p.o_split_stride) + batch * p.o_sb + head * p.o_sh + 2 * cp + static_cast<int64_t>(row[r]) * p.o_sl;
-                }
-            }
-#pragma unroll 1
-            for (int g4 = 0; g4 < D / 32; ++g4) {
-                uint32_t ov[16];
-                tmem_ld_16x256b_x4(o_col + 32 * g4, ov);
-                tmem_ld_wait();
-#pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    if (row[r] < p.Lq) {
-                        __nv_bfloat16* orow = obase[r] + 32 * g4;
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            uint32_t w = pack_bf16x2(__uint_as_float(ov[4 * g + 2 * r]) * inv_l[r], __uint_as_float(ov[4 * g + 2 * r + 1]) * inv_l[r]);
-                            if (p.accumulate) w = add_bf16x2_as_tensors(*reinterpret_cast<const uint32_t*>(orow + 8 * g), w);
-                            *reinterpret_cast<uint32_t*>(orow + 8 * g) = w;
-                        }
-                    }
-                }
-            }
-            if (p.lse && cp == 0) {
-#pragma unroll
-                for (int r = 0; r < 2; ++r)
-                    if (row[r] < p.Lq)
-                        p.lse[static_cast<uint64_t>(split) * static_cast<uint64_t>(p.lse_split_stride) + (static_cast<int64_t>(batch) * p.H + head) * p.Lq + row[r]] = m_used[r] * p.scale + logf(l[r]);
-            }
-        }
+        attn_softmax_lane16<D, false>(sm, p, wk, tmem_base, warp, lane);
     }
 
     tc_fence_before();
@@ -831,6 +838,226 @@ attn_fwd_row_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 }
 
 
+// ------------------------------------------------------------------------------------------------------------------------
+// CTA-PAIR kernel (D = 128): two CTAs of a cluster — the two SMs of a TPC — work on 512 query rows of one head with tcgen05.mma
+// cta_group::2 (M = 256).  Pair tile i = (Q tile i of CTA 0, Q tile i of CTA 1); each CTA keeps the rows of ITS Q tiles in its own TMEM with
+// the one-CTA layout S0 | S1 | O0 | O1, runs its own 16 softmax warps on them and stores its own rows.  What the pair shares is the B
+// operand: CTA r stages kv rows [64 r, 64 r + 64) of every K tile and head-dim columns [64 r, 64 r + 64) of every V tile — HALF the
+// shared-memory operand bytes per MMA (A 4 KB + B 2 KB instead of 4 + 4: a 128 x 128 x 16 MMA fed from 8 KB of shared memory runs at
+// ~71 clk instead of 64 because it needs the SM's whole 128 B/clk) and half the L2 -> SM traffic, with 16 KB ring stages (eight of them).
+// Protocol (the GEMM pair kernel's): kv_full / q_full / p_full live in the LEADER (CTA 0) and collect both CTAs' TMA bytes resp. the P
+// arrivals of both CTAs' softmax warps (remote mbarrier.arrive); the leader's single MMA warp issues every MMA and its tcgen05.commit
+// multicasts to both CTAs' s_full / pv_half / o_done / kv_empty.
+// ------------------------------------------------------------------------------------------------------------------------
+struct AttnPairSmem {
+    static constexpr int kTileBytes = 128 * 128 * 2;  // one Q tile
+    static constexpr int kSlabBytes = 128 * 64 * 2;   // Q: 128 rows x 64 columns (one 128-byte swizzle slab)
+    static constexpr int kStageBytes = 64 * 128 * 2;  // half a K tile (64 rows x 128 cols = two 8 KB slabs) or half a V tile (128 rows x 64 cols)
+    static constexpr int kStages = 8;
+    static constexpr int kBarBytes = 512;
+    static constexpr int kSmemBytes = 2 * kTileBytes + kStages * kStageBytes + kBarBytes + 1024;
+    uint32_t q_smem, kv_smem, bar_base;
+    __device__ __forceinline__ explicit AttnPairSmem(uint32_t smem_base)
+        : q_smem(smem_base), kv_smem(smem_base + 2 * kTileBytes), bar_base(smem_base + 2 * kTileBytes + kStages * kStageBytes) {}
+    __device__ __forceinline__ uint32_t kv_full(int s) const { return bar_base + 8u * s; }                       // leader: both CTAs' halves have landed
+    __device__ __forceinline__ uint32_t kv_empty(int s) const { return bar_base + 8u * (kStages + s); }          // per CTA: the pair's MMAs have read the slot
+    __device__ __forceinline__ uint32_t q_full() const { return bar_base + 8u * (2 * kStages); }                 // leader
+    __device__ __forceinline__ uint32_t s_full(int i) const { return bar_base + 8u * (2 * kStages + 1 + i); }    // per CTA (multicast commit)
+    __device__ __forceinline__ uint32_t p_full(int i, int c) const { return bar_base + 8u * (2 * kStages + 3 + 2 * i + c); }  // leader: 16 warps
+    __device__ __forceinline__ uint32_t pv_half(int i) const { return bar_base + 8u * (2 * kStages + 7 + i); }   // per CTA
+    __device__ __forceinline__ uint32_t o_done(int i) const { return bar_base + 8u * (2 * kStages + 9 + i); }    // per CTA
+    __device__ __forceinline__ uint32_t tmem_ptr_addr() const { return bar_base + 8u * (2 * kStages + 11); }
+};
+static_assert(2 * AttnPairSmem::kStages + 12 <= AttnPairSmem::kBarBytes / 8, "barrier area");
+
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+    constexpr int D = 128;
+    using Cfg = AttnCfg<D>;
+    using SM = AttnPairSmem;
+    extern __shared__ uint8_t smem_raw[];
+    const SM sm((smem_u32(smem_raw) + 1023u) & ~1023u);
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const AttnWork wk(p);  // q0 = blockIdx.x * 256: this CTA's own 256 query rows
+    const int cta_rank = static_cast<int>(cluster_ctarank());
+    const bool leader = cta_rank == 0;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmK);
+        tma_prefetch_desc(&tmV);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < SM::kStages; ++s) {
+            mbar_init(sm.kv_full(s), 1);   // the leader's producer (arrive + expect_tx of both halves); unused in the peer
+            mbar_init(sm.kv_empty(s), 1);  // the leader's multicast commit
+        }
+        mbar_init(sm.q_full(), 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(sm.s_full(i), 1);
+            mbar_init(sm.p_full(i, 0), kSoftmaxWarps);  // eight softmax warps of EACH CTA; unused in the peer
+            mbar_init(sm.p_full(i, 1), kSoftmaxWarps);
+            mbar_init(sm.pv_half(i), 1);
+            mbar_init(sm.o_done(i), 1);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 0) {
+        tmem_alloc_pair(sm.tmem_ptr_addr(), Cfg::kTmemCols);
+        tmem_relinquish_pair();
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // both CTAs' barriers and TMEM exist before anything crosses the pair
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(sm.tmem_ptr_addr()));
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs): own Q tiles, own half of every K and V tile; all bytes complete on the LEADER's barriers =====
+        if (elect_one()) {
+            if (leader) mbar_arrive_expect_tx(sm.q_full(), 2 * 2 * SM::kTileBytes);
+            for (int t = 0; t < 2; ++t)
+                for (int h = 0; h < 2; ++h)
+                    tma_load_4d_pair(sm.q_smem + t * SM::kTileBytes + h * SM::kSlabBytes, &tmQ, sm.q_full(), h * 64, wk.q0 + t * kBlockM, wk.head, wk.batch);
+        }
+        __syncwarp();
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int j = 0; j < wk.n_kv; ++j) {
+            for (int kv = 0; kv < 2; ++kv) {  // K_j then V_j
+                mbar_wait(sm.kv_empty(stage), phase ^ 1);
+                if (elect_one()) {
+                    if (leader) mbar_arrive_expect_tx(sm.kv_full(stage), 2 * SM::kStageBytes);
+                    const uint32_t dst = sm.kv_smem + stage * SM::kStageBytes;
+                    const int row = (wk.j0 + j) * kBlockN;
+                    if (kv == 0) {  // my 64 kv rows, both 64-column slabs (K-major B operand: N split across the pair)
+                        tma_load_4d_pair(dst, &tmK, sm.kv_full(stage), 0, row + cta_rank * (kBlockN / 2), wk.head, wk.batch);
+                        tma_load_4d_pair(dst + SM::kStageBytes / 2, &tmK, sm.kv_full(stage), 64, row + cta_rank * (kBlockN / 2), wk.head, wk.batch);
+                    } else {  // all 128 kv rows of my 64 head-dim columns (MN-major B operand: N = D split across the pair)
+                        tma_load_4d_pair(dst, &tmV, sm.kv_full(stage), cta_rank * 64, row, wk.head, wk.batch);
+                    }
+                }
+                __syncwarp();
+                if (++stage == SM::kStages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader) {
+            // ===== MMA issuer (leader CTA only), same order as attn_mma_warp =====
+            constexpr uint32_t idesc_qk = make_idesc_bf16(2 * kBlockM, kBlockN, 0, 0);
+            constexpr uint32_t idesc_pv = make_idesc_bf16(2 * kBlockM, D, 0, 1);
+            const uint32_t col_s[2] = {tmem_base + Cfg::kColS0, tmem_base + Cfg::kColS1};
+            const uint32_t col_o[2] = {tmem_base + Cfg::kColO0, tmem_base + Cfg::kColO1};
+            const uint32_t q_smem = sm.q_smem, kv_smem = sm.kv_smem;
+            auto issue_qk = [&](int i, uint32_t k_addr) {
+                const uint32_t q_addr = q_smem + i * SM::kTileBytes;
+                if (elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < D / 16; ++k)
+                        umma_ss_pair(col_s[i], make_smem_desc(q_addr + (k >> 2) * SM::kSlabBytes + (k & 3) * 32, 0, 1024, kLayoutSw128),
+                                     make_smem_desc(k_addr + (k >> 2) * (SM::kStageBytes / 2) + (k & 3) * 32, 0, 1024, kLayoutSw128), idesc_qk, k != 0 ? 1u : 0u);
+                }
+                __syncwarp();
+            };
+            auto issue_pv_half = [&](int i, int c, uint32_t v_addr, uint32_t accumulate) {
+                if (elect_one()) {
+#pragma unroll
+                    for (int kk = 0; kk < kBlockN / 32; ++kk) {
+                        const int k = 4 * c + kk;
+                        umma_ts_pair(col_o[i], col_s[i] + 8 * k, make_smem_desc(v_addr + k * 2048, SM::kStageBytes, 1024, kLayoutSw128), idesc_pv, k != 0 ? 1u : accumulate);
+                    }
+                }
+                __syncwarp();
+            };
+            auto commit = [&](uint32_t bar) {  // arrives on this barrier in BOTH CTAs
+                if (elect_one()) umma_commit_pair(bar, 3);
+                __syncwarp();
+            };
+            int stage = 0;
+            uint32_t phase = 0;
+            auto advance = [&]() {
+                if (++stage == SM::kStages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            };
+            const int n_kv = wk.n_kv;
+            mbar_wait(sm.q_full(), 0);
+            mbar_wait(sm.kv_full(stage), phase);  // K_0
+            tc_fence_after();
+            issue_qk(0, kv_smem + stage * SM::kStageBytes);
+            commit(sm.s_full(0));
+            issue_qk(1, kv_smem + stage * SM::kStageBytes);
+            commit(sm.s_full(1));
+            commit(sm.kv_empty(stage));
+            advance();
+            int v_stage = stage;
+            mbar_wait(sm.kv_full(stage), phase);  // V_0
+            advance();
+            int k_stage = stage;
+            if (n_kv > 1) {
+                mbar_wait(sm.kv_full(stage), phase);  // K_1
+                advance();
+            }
+            int prev_v = -1, prev_k = -1;
+            for (int j = 0; j < n_kv; ++j) {
+                const uint32_t par = j & 1;
+                const bool has_next = (j + 1 < n_kv);
+                int next_v = 0, next_k = 0;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    mbar_wait(sm.p_full(i, 0), par);
+                    tc_fence_after();
+                    issue_pv_half(i, 0, kv_smem + v_stage * SM::kStageBytes, j > 0 ? 1u : 0u);
+                    commit(sm.pv_half(i));
+                    if (i == 0) {
+                        if (prev_v >= 0) commit(sm.kv_empty(prev_v));
+                        if (prev_k >= 0) commit(sm.kv_empty(prev_k));
+                    } else if (has_next) {
+                        next_v = stage;
+                        mbar_wait(sm.kv_full(stage), phase);  // V_{j+1}
+                        advance();
+                        next_k = stage;
+                        if (j + 2 < n_kv) {
+                            mbar_wait(sm.kv_full(stage), phase);  // K_{j+2}
+                            advance();
+                        }
+                    }
+                    mbar_wait(sm.p_full(i, 1), par);
+                    tc_fence_after();
+                    issue_pv_half(i, 1, kv_smem + v_stage * SM::kStageBytes, 1u);
+                    if (has_next) {
+                        issue_qk(i, kv_smem + k_stage * SM::kStageBytes);
+                        commit(sm.s_full(i));
+                    } else {
+                        commit(sm.o_done(i));
+                    }
+                }
+                prev_v = v_stage, prev_k = has_next ? k_stage : -1;
+                v_stage = next_v, k_stage = next_k;
+            }
+            if (prev_v >= 0) commit(sm.kv_empty(prev_v));
+            if (prev_k >= 0) commit(sm.kv_empty(prev_k));
+        }
+    } else {
+        attn_softmax_lane16<D, true>(sm, p, wk, tmem_base, warp, lane);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // no CTA leaves (or frees TMEM) while the pair's MMAs, loads or barrier arrivals may still touch it
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+    }
+}
+
+
 static int make_attn_tmap(CUtensorMap* tm, const AttnTensor& t, int B, int H, int L, int D, int box_rows, const char* name) {
     VAP_REQUIRE((reinterpret_cast<uintptr_t>(t.ptr) & 15) == 0, "attention: %s must be 16-byte aligned", name);
     VAP_REQUIRE(t.sl % 8 == 0 && t.sh % 8 == 0 && t.sb % 8 == 0, "attention: %s strides must be multiples of 8 elements", name);
@@ -852,6 +1079,14 @@ static int attn_cluster_mode() {
 #ifndef VAP_ATTN_DEFAULT_ROW
 #define VAP_ATTN_DEFAULT_ROW 0
 #endif
+#ifndef VAP_ATTN_DEFAULT_PAIR
+#define VAP_ATTN_DEFAULT_PAIR 0
+#endif
+static bool attn_pair_mode() {  // VAP_ATTN_PAIR = 1: the CTA-pair kernel (cta_group::2) for D = 128
+    const char* e = getenv("VAP_ATTN_PAIR");
+    if (!e || !*e) return VAP_ATTN_DEFAULT_PAIR != 0;
+    return e[0] == '1';
+}
 static bool attn_row_mode() {
     const char* e = getenv("VAP_ATTN_SOFTMAX");
     if (!e || !*e) return VAP_ATTN_DEFAULT_ROW != 0;
@@ -887,6 +1122,24 @@ static int launch_attn_d(const CUtensorMap& tmQ, const CUtensorMap& tmK, const C
     return 0;
 }
 
+static int launch_attn_pair(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const AttnParams& p, cudaStream_t stream) {
+    static_assert(AttnPairSmem::kSmemBytes <= 232448, "shared memory budget");
+    static bool opted_in[64] = {};
+    if (int rc = smem_opt_in(attn_fwd_pair_kernel, AttnPairSmem::kSmemBytes, opted_in)) return rc;
+    const unsigned q_blocks = static_cast<unsigned>((p.Lq + 2 * kBlockM - 1) / (2 * kBlockM));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((q_blocks + 1) / 2 * 2, p.H, p.B * p.kv_splits);  // a trailing CTA without query rows still stages its half of K / V and runs its softmax on zeros
+    cfg.blockDim = dim3(kAttnThreads);
+    cfg.dynamicSmemBytes = AttnPairSmem::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2, attr.val.clusterDim.y = 1, attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr, cfg.numAttrs = 1;
+    VAP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, attn_fwd_pair_kernel, tmQ, tmK, tmV, p));
+    return 0;
+}
+
 template <int D>
 static int launch_attn_variant(bool cluster, bool row, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const AttnParams& p, cudaStream_t stream) {
     if (row) return cluster ? launch_attn_d<D, 2, true>(tmQ, tmK, tmV, p, stream) : launch_attn_d<D, 1, true>(tmQ, tmK, tmV, p, stream);
@@ -915,7 +1168,14 @@ int launch_attention_fwd(const AttnTensor& q, const AttnTensor& k, const AttnTen
     VAP_REQUIRE(!p.accumulate || (p.kv_splits == 1 && p.o_rows_per_peer == 0), "attention: accumulate needs the plain output mode (no split-KV, no peers)");
     if (p.Lq == 0) return 0;
     const bool cluster = attn_cluster_mode() == 2 && p.Lq > 2 * kBlockM;
+    const bool pair = attn_pair_mode() && D == 128 && p.Lq > 2 * kBlockM;
     CUtensorMap tmQ, tmK, tmV;
+    if (pair) {  // CTA r stages 64 kv rows of K (box 64 x 64) and 64 head-dim columns of V (box 64 x 128)
+        if (make_attn_tmap(&tmQ, q, p.B, p.H, p.Lq, D, kBlockM, "q")) return -3;
+        if (make_attn_tmap(&tmK, k, p.B, p.H, p.Lkv, D, kBlockN / 2, "k")) return -3;
+        if (make_attn_tmap(&tmV, v, p.B, p.H, p.Lkv, D, kBlockN, "v")) return -3;
+        return launch_attn_pair(tmQ, tmK, tmV, p, stream);
+    }
     if (make_attn_tmap(&tmQ, q, p.B, p.H, p.Lq, D, kBlockM, "q")) return -3;
     if (make_attn_tmap(&tmK, k, p.B, p.H, p.Lkv, D, cluster ? kBlockN / 2 : kBlockN, "k")) return -3;
     if (make_attn_tmap(&tmV, v, p.B, p.H, p.Lkv, D, cluster ? kBlockN / 2 : kBlockN, "v")) return -3;
