@@ -268,7 +268,8 @@ def test_wan_mot_block_launch_sequence(tmp_path):
     names = [c[0].replace("vap_", "") for c in calls]
     ln, gemm, qk, att, mod, acc = "adaln_layernorm", "gemm_bf16", "qk_norm_rope", "attention_fwd", "wan_modulation", "attention_fwd_accumulate"
     tail = [ln, gemm, qk, gemm, qk, att, gemm, qk, acc, gemm, ln, gemm, gemm]  # the image softmax is added to the text one in its epilogue
-    assert names == [mod, mod, ln, ln, gemm, qk, gemm, qk, att, gemm, gemm] + tail + tail + [ln]
+    # issue order: the expert's stream (side CUDA stream on a GPU, streams.py) first, then the target's, in each of the two phases around the attention
+    assert names == [mod] + [mod, ln, gemm, qk] + [ln, gemm, qk] + [att] + [gemm] + tail + [gemm] + tail + [ln]
     # the joint attention reads q, k, v of BOTH streams as strided views of one [J, 3d] buffer: J = 2 x 32 rows, row stride 3 * 256
     joint = [c for c in calls if c[0] == "vap_attention_fwd"][0]
     scal = [x for x in joint[1:] if x not in ("p", None)]
@@ -279,7 +280,7 @@ def test_wan_mot_block_launch_sequence(tmp_path):
     # GEMM epilogues in order: QKV x2 (bias), O-proj x2 (fp32 gated residual), then per stream q / kv / kv_img (bias), to_out (residual add),
     # FFN up (GELU), FFN down (fp32 gated residual)
     epi = [[x for x in c[1:] if x not in ("p", None)][6] for c in calls if c[0] == "vap_gemm_bf16"]
-    assert epi == [0, 0, 2, 2] + [0, 0, 0, 3, 1, 2] * 2
+    assert epi == [0, 0] + [2, 0, 0, 0, 3, 1, 2] * 2
 
 
 def test_cog_mot_block_launch_sequence(tmp_path):
@@ -290,7 +291,7 @@ def test_cog_mot_block_launch_sequence(tmp_path):
     ln, gemm, qk, att = "adaln_layernorm", "gemm_bf16", "qk_norm_rope", "attention_fwd"
     pre = [ln, ln, gemm, qk]
     ffn = [ln, ln, gemm, gemm, gemm]
-    assert names == pre + pre + [att, gemm, gemm] + ffn + [gemm, gemm] + ffn + pre + [att, gemm, gemm] + ffn + [ln, ln]
+    assert names == pre + pre + [att, gemm, gemm] + ffn + [gemm, gemm] + ffn + pre + [att, gemm, gemm] + ffn + [ln, ln]  # per phase: expert stream, then target
     att_calls = [[x for x in c[1:] if x not in ("p", None)] for c in calls if c[0] == "vap_attention_fwd"]
     assert att_calls[0][:5] == [1, 4, 516, 516, 64] and att_calls[1][:5] == [1, 4, 258, 258, 64]  # J = 2 (226 + 32); plain block: 226 + 32
     qk_calls = [[x for x in c[1:] if x not in ("p", None)] for c in calls if c[0] == "vap_qk_norm_rope"]

@@ -49,6 +49,7 @@ def main():
     ap.add_argument("--rounds", type=int, default=2)
     ap.add_argument("--shapes", default="wan,cog")
     ap.add_argument("--only", default="", help="comma list of library names (default: all)")
+    ap.add_argument("--modes", default="", help="comma list restricting the run-time modes (lane16, pair, row)")
     ap.add_argument("--cl", default="0", help="comma list of VAP_ATTN_CLUSTER values to run (0 = no cluster, 2 = K/V multicast pairs)")
     a = ap.parse_args()
     libs = {"intree": os.path.join(ROOT, "video-as-prompt_b200", "libvap_b200.so")}
@@ -60,6 +61,8 @@ def main():
     for name in libs:
         modes = ["row"] if name.startswith("row") else ["lane16"] if name.startswith("l16") else ["pair"] if name.startswith("pair") else ["lane16", "pair", "row"]
         for m in modes:
+            if a.modes and m not in a.modes.split(","):
+                continue
             for cl in a.cl.split(","):
                 variants.append((name, m, cl))
     res = {}

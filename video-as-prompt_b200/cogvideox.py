@@ -23,6 +23,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops, ulysses
+from . import streams as stream_pair
 from .modules import AdaLayerNorm, Attention, CogVideoXLayerNormZero, FeedForward, TimestepEmbedding
 from .rope import Tables, as_tables
 from .wan import _f32, _heads_view, _joint_attention, _linear, _Output, _packed, _sp_p2p, _token_major
@@ -129,18 +130,30 @@ def cog_block_forward(self: nn.Module, hidden_states: torch.Tensor, encoder_hidd
     J = sum(st.T + st.S for st in streams)
     qkv = torch.empty((B, J, 3 * inner), dtype=torch.bfloat16, device=dev)
     px = _sp_p2p(hidden_states, J, heads, hd)  # PeerExchange in peer-memory mode (B == 1), else None
-    for b in range(B):
-        row = 0
-        for st in streams:
-            L = st.T + st.S
+    row0 = [0, streams[0].T + streams[0].S]    # first joint row of each stream
+    # the expert's stream is issued on a side CUDA stream between the joint attentions (streams.py); None: CPU tensors / plain block / switched off
+    ds = stream_pair.dual(dev, max(st.T + st.S for st in streams)) if len(streams) > 1 else None
+
+    def pre(si: int) -> None:
+        st = streams[si]
+        L = st.T + st.S
+        for b in range(B):
             h = torch.empty((L, d), dtype=torch.bfloat16, device=dev)
             m = st.mods_of(st.mods1, b)
             if st.T:
                 _ln_zero(st.norm1, st.e[b], m, True, st.se, h[:st.T])
             if st.S:
                 _ln_zero(st.norm1, st.v[b], m, False, st.sv, h[st.T:])
-            _qkv(st.attn, h, st.T, st.tables, qkv[b, row:row + L], scatter=(px, row) if px is not None else None)
-            row += L
+            _qkv(st.attn, h, st.T, st.tables, qkv[b, row0[si]:row0[si] + L], scatter=(px, row0[si]) if px is not None else None)
+
+    if ds is not None:
+        ds.fork()
+    if len(streams) > 1:
+        with stream_pair.side(ds):
+            pre(1)
+    pre(0)
+    if ds is not None:
+        ds.join()
 
     # ---- joint attention ---------------------------------------------------------------------------------------
     if px is not None:
@@ -149,9 +162,9 @@ def cog_block_forward(self: nn.Module, hidden_states: torch.Tensor, encoder_hidd
         o = _joint_attention(qkv, heads)    # [B, J, inner]; NCCL all-to-alls around the kernel when Ulysses runs in "nccl" mode
 
     # ---- per stream: to_out + gated residual, norm2, FFN + gated residual ------------------------------------------
-    outs = []
-    row = 0
-    for st in streams:
+    def post(si: int):
+        st = streams[si]
+        row = row0[si]
         L = st.T + st.S
         v_out, e_out = torch.empty_like(st.v), torch.empty_like(st.e)
         mods2 = None
@@ -176,8 +189,17 @@ def cog_block_forward(self: nn.Module, hidden_states: torch.Tensor, encoder_hidd
                 _gated(st.ff.net[2], f1[:st.T], e1, m2[:, 5], st.se, e_out[b])
             if st.S:
                 _gated(st.ff.net[2], f1[st.T:], v1, m2[:, 2], st.sv, v_out[b])
-        outs += [v_out, e_out]
-        row += L
+        return [v_out, e_out]
+
+    if ds is not None:
+        ds.fork()
+    outs_r = []
+    if len(streams) > 1:
+        with stream_pair.side(ds):
+            outs_r = post(1)
+    outs = post(0) + outs_r
+    if ds is not None:
+        ds.join()  # `o` (read by the side stream) is still referenced here
     if not self.with_mot_ref:
         return outs[0], outs[1], hidden_states_mot_ref, encoder_hidden_states_mot_ref
     return outs[0], outs[1], outs[2], outs[3]

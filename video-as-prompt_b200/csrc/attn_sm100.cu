@@ -28,6 +28,7 @@
 //     half of the softmax.
 // The last KV tile is masked against Lkv (TMA zero-fills out-of-range K/V rows).
 #include <cstdlib>
+#include <type_traits>
 #include "vap_kernels.cuh"
 
 namespace vap {
@@ -60,6 +61,15 @@ constexpr float kSumTrigger = 256.0f;  // 2^kRescaleThreshold
 #define VAP_SM_WAIT(bar, par) do { if (VAP_ATTN_SPIN & 2) mbar_wait_spin(bar, par); else mbar_wait(bar, par); } while (0)
 #ifndef VAP_ATTN_MMA_ORDER
 #define VAP_ATTN_MMA_ORDER 1  // 1: the issuer's bookkeeping waits / releases are kept off the P -> PV path (see attn_mma_warp)
+#endif
+// Three-stage publish of P (16-lane kernel): half 0 | the first VAP_ATTN_P3_PAIRS pairs per thread of half 1 (4 kv columns each: 12 -> 48
+// columns) | the rest.  What follows the softmax of a tile on its dependency chain is then the PV MMAs of the LAST stage + QK^T of the next
+// step: 1 + 8 MMAs instead of 4 + 8 (D = 128).
+#ifndef VAP_ATTN_P3
+#define VAP_ATTN_P3 0
+#endif
+#ifndef VAP_ATTN_P3_PAIRS
+#define VAP_ATTN_P3_PAIRS 12  // 8 or 12
 #endif
 #ifndef VAP_ATTN_TRACE
 #define VAP_ATTN_TRACE 0  // 1: clock64() stamps of CTA (0,0,0) when a trace buffer is installed (tools/attn_trace.py)
@@ -98,6 +108,8 @@ struct AttnSmem {
     __device__ __forceinline__ uint32_t pv_half(int i) const { return bar_base + 8u * (2 * Cfg::kKvStages + 7 + i); }           // the PV MMAs of half 0 have completed
     __device__ __forceinline__ uint32_t o_done(int i) const { return bar_base + 8u * (2 * Cfg::kKvStages + 9 + i); }
     __device__ __forceinline__ uint32_t tmem_ptr_addr() const { return bar_base + 8u * (2 * Cfg::kKvStages + 11); }
+    __device__ __forceinline__ uint32_t p_last(int i) const { return bar_base + 8u * (2 * Cfg::kKvStages + 12 + i); }  // three-stage publish: the last stage of P_i(j)
+    __device__ __forceinline__ uint32_t pv_mid(int i) const { return bar_base + 8u * (2 * Cfg::kKvStages + 14 + i); }  // three-stage publish: the PV MMAs of stage 1 have completed
     // one thread: p_arrivals = softmax warps per Q tile (each arrives once per published half)
     __device__ __forceinline__ void init_barriers(int cluster_size, int p_arrivals) const {
         for (int s = 0; s < Cfg::kKvStages; ++s) {
@@ -111,6 +123,8 @@ struct AttnSmem {
             mbar_init(p_full(i, 1), p_arrivals);
             mbar_init(pv_half(i), 1);
             mbar_init(o_done(i), 1);
+            mbar_init(p_last(i), p_arrivals);
+            mbar_init(pv_mid(i), 1);
         }
         fence_mbar_init();
     }
@@ -164,7 +178,7 @@ __device__ __forceinline__ void attn_producer_warp(const AttnSmem<D>& sm, const 
 #define TRM(k) do { } while (0)
 #endif
 
-template <int D, int CL>
+template <int D, int CL, bool kP3 = false>
 __device__ __forceinline__ void attn_mma_warp(const AttnSmem<D>& sm, uint32_t tmem_base, int n_kv, long long* trm) {
     using Cfg = AttnCfg<D>;
     constexpr uint32_t idesc_qk = make_idesc_bf16(kBlockM, kBlockN, 0, 0);  // S = Q K^T : A, B K-major
@@ -185,19 +199,22 @@ __device__ __forceinline__ void attn_mma_warp(const AttnSmem<D>& sm, uint32_t tm
         }
         __syncwarp();
     };
-    auto issue_pv_half = [&](int i, int c, uint32_t v_addr, uint32_t accumulate) {
+    // K-steps [k0, k1) of O_i += P_i V (16 kv rows each)
+    auto issue_pv = [&](int i, int k0, int k1, uint32_t v_addr, uint32_t accumulate) {
         if (elect_one()) {
 #pragma unroll
-            for (int kk = 0; kk < kBlockN / 32; ++kk) {
-                const int k = 4 * c + kk;
+            for (int k = 0; k < kBlockN / 16; ++k) {
                 // A: P_i, packed bf16 pairs, 8 TMEM columns per 16 kv;  B: V rows [16k, 16k+16) (2048 B apart),
                 // MN-major: 64-column slabs kHalfBytes apart (LBO), 8-row groups 1024 B apart (SBO)
-                umma_ts(col_o[i], col_s[i] + 8 * k, make_smem_desc(v_addr + k * 2048, Cfg::kHalfBytes, 1024, kLayoutSw128), idesc_pv,
-                        k != 0 ? 1u : accumulate);
+                if (k >= k0 && k < k1)
+                    umma_ts(col_o[i], col_s[i] + 8 * k, make_smem_desc(v_addr + k * 2048, Cfg::kHalfBytes, 1024, kLayoutSw128), idesc_pv,
+                            k != 0 ? 1u : accumulate);
             }
         }
         __syncwarp();
     };
+    auto issue_pv_half = [&](int i, int c, uint32_t v_addr, uint32_t accumulate) { issue_pv(i, 4 * c, 4 * c + 4, v_addr, accumulate); };
+    constexpr int kMid = 4 + VAP_ATTN_P3_PAIRS / 4;  // three-stage publish: stage 1 covers K-steps [4, kMid), the last stage [kMid, 8)
     auto commit = [&](uint32_t bar) {
         if (elect_one()) umma_commit(bar);
         __syncwarp();
@@ -228,6 +245,7 @@ __device__ __forceinline__ void attn_mma_warp(const AttnSmem<D>& sm, uint32_t tm
     release(sm.kv_empty(stage));
     advance();
 #if VAP_ATTN_MMA_ORDER == 0
+    static_assert(!kP3, "the three-stage publish is implemented for VAP_ATTN_MMA_ORDER=1 only");
     for (int j = 0; j < n_kv; ++j) {
         const uint32_t par = j & 1;
         const int v_stage = stage;
@@ -306,7 +324,15 @@ __device__ __forceinline__ void attn_mma_warp(const AttnSmem<D>& sm, uint32_t tm
             }
             VAP_MMA_WAIT(sm.p_full(i, 1), par);
             tc_fence_after();
-            issue_pv_half(i, 1, kv_smem + v_stage * Cfg::kTileBytes, 1u);
+            if constexpr (kP3) {
+                issue_pv(i, 4, kMid, kv_smem + v_stage * Cfg::kTileBytes, 1u);
+                commit(sm.pv_mid(i));
+                VAP_MMA_WAIT(sm.p_last(i), par);
+                tc_fence_after();
+                issue_pv(i, kMid, 8, kv_smem + v_stage * Cfg::kTileBytes, 1u);
+            } else {
+                issue_pv_half(i, 1, kv_smem + v_stage * Cfg::kTileBytes, 1u);
+            }
             if (has_next) {
                 issue_qk(i, kv_smem + k_stage * Cfg::kTileBytes);
                 commit(sm.s_full(i));  // also covers PV_i(j): O_i is quiescent when the softmax sees S_i(j+1)
@@ -343,6 +369,8 @@ struct AttnWork {
 template <int D, bool kRemoteP, typename Smem>
 __device__ __forceinline__ void attn_softmax_lane16(const Smem& sm, const AttnParams& p, const AttnWork& wk, uint32_t tmem_base, int warp, int lane) {
     using Cfg = AttnCfg<D>;
+    constexpr bool kP3 = (VAP_ATTN_P3 != 0) && !kRemoteP;  // three-stage publish of P (the CTA-pair kernel keeps two)
+    static_assert(VAP_ATTN_P3_PAIRS == 8 || VAP_ATTN_P3_PAIRS == 12, "VAP_ATTN_P3_PAIRS");
     constexpr int kPolyPairs = (D == 128) ? VAP_ATTN_POLY_PAIRS_D128 : VAP_ATTN_POLY_PAIRS_D64;
     const int q0 = wk.q0, head = wk.head, batch = wk.batch, j0 = wk.j0, n_kv = wk.n_kv;
     const unsigned split = wk.split;
@@ -407,11 +435,11 @@ __device__ __forceinline__ void attn_softmax_lane16(const Smem& sm, const AttnPa
             // instruction, the polynomial 9 clk per element of FMA pipe: they only pay off side by side).
             uint32_t pk[16];  // pk[2g] = row0, pk[2g+1] = row0 + 8 : packed P column 32 ch + 4 g + cp
             uint64_t ls[2];
-#pragma unroll 1
-            for (int pass = 0;; ++pass) {  // at most two passes: the second one runs against the refreshed reference
+            // pairs [E0, E1) of this half (pair e: group g = e / 2, row r = e & 1) against the current reference; ls = their partial row sums
+            auto pairs = [&](auto e0c, auto e1c) {
                 ls[0] = 0ull, ls[1] = 0ull;
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {  // pair e: group g = e / 2, row r = e & 1
+                for (int e = decltype(e0c)::value; e < decltype(e1c)::value; ++e) {
                     const int r = e & 1;
                     const uint64_t x2 = fma_f32x2(pack_f32x2(SF(2 * e), SF(2 * e + 1)), c2, nmc2[r]);
                     float x0, x1, p0, p1;
@@ -425,10 +453,12 @@ __device__ __forceinline__ void attn_softmax_lane16(const Smem& sm, const AttnPa
                     ls[r] = add_f32x2(ls[r], pack_f32x2(p0, p1));
                     pk[e] = pack_bf16x2(p0, p1);
                 }
-                // Vote: does any score of this half-tile sit more than 2^8 above the reference?  The MUFU pairs are judged by
-                // their results (a p > 2^8 makes this thread's partial row sum > 2^8; ex2.approx overflows cleanly to +inf), the
-                // polynomial pairs by their scores (the exponent-field arithmetic is only valid for x < 128).  A false positive
-                // merely refreshes the reference.  The very first half-tile always votes yes (no reference yet).
+            };
+            // Vote: does any score of these pairs sit more than 2^8 above the reference?  The MUFU pairs are judged by
+            // their results (a p > 2^8 makes this thread's partial row sum > 2^8; ex2.approx overflows cleanly to +inf), the
+            // polynomial pairs by their scores (the exponent-field arithmetic is only valid for x < 128).  A false positive
+            // merely refreshes the reference.  The very first half-tile always votes yes (no reference yet).
+            auto vote = [&](auto e0c, auto e1c) -> bool {
                 float lo0, hi0, lo1, hi1;
                 unpack_f32x2(ls[0], lo0, hi0);
                 unpack_f32x2(ls[1], lo1, hi1);
@@ -436,14 +466,18 @@ __device__ __forceinline__ void attn_softmax_lane16(const Smem& sm, const AttnPa
                 if constexpr (kPolyPairs > 0) {
                     float pm0 = -INFINITY, pm1 = -INFINITY;
 #pragma unroll
-                    for (int e = 0; e < 16; ++e)
+                    for (int e = decltype(e0c)::value; e < decltype(e1c)::value; ++e)
                         if ((e & 7) < kPolyPairs) {
                             if (e & 1) pm1 = fmax3(pm1, SF(2 * e), SF(2 * e + 1));
                             else pm0 = fmax3(pm0, SF(2 * e), SF(2 * e + 1));
                         }
                     need = need || (pm0 > thr[0]) || (pm1 > thr[1]);
                 }
-                if (pass == 1 || !__any_sync(0xffffffffu, need)) break;
+                return __any_sync(0xffffffffu, need);
+            };
+            // Reference update (rare): the row maxima over the WHOLE half (a superset is as good), quad-reduced; the warp rescales its 16 rows
+            // of O (lazy rescale) — after the PV MMAs already issued on this step's published P have left O (`pv_bar`, 0 = none in flight).
+            auto update = [&](uint32_t pv_bar) {
                 float mx0 = fmax3(SF(0), SF(1), SF(4)), mx1 = fmax3(SF(2), SF(3), SF(6));
                 mx0 = fmax3(mx0, SF(5), SF(8)), mx1 = fmax3(mx1, SF(7), SF(10));
 #pragma unroll
@@ -453,15 +487,14 @@ __device__ __forceinline__ void attn_softmax_lane16(const Smem& sm, const AttnPa
                 }
                 mx0 = fmaxf(mx0, SF(29));
                 mx1 = fmaxf(mx1, SF(31));
-                // ---- reference update: quad-reduce the row maxima, rescale this warp's 16 rows of O, repeat the pass ----
                 mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
                 mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
                 mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
                 mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
                 const float mn0 = fmaxf(m_used[0], mx0), mn1 = fmaxf(m_used[1], mx1);
                 if (j > 0 || ch > 0) {
-                    if (ch > 0) {  // the PV MMAs of this step's first half must have left O_i
-                        mbar_wait(sm.pv_half(i), j & 1);
+                    if (pv_bar != 0u) {
+                        mbar_wait(pv_bar, j & 1);
                         tc_fence_after();
                     }
                     const float f0 = ex2_approx((m_used[0] - mn0) * c), f1 = ex2_approx((m_used[1] - mn1) * c);
@@ -480,23 +513,64 @@ __device__ __forceinline__ void attn_softmax_lane16(const Smem& sm, const AttnPa
                 m_used[0] = mn0, m_used[1] = mn1;
                 thr[0] = mn0 + thr_off, thr[1] = mn1 + thr_off;
                 nmc2[0] = pack_f32x2(-mn0 * c, -mn0 * c), nmc2[1] = pack_f32x2(-mn1 * c, -mn1 * c);
+            };
+            auto publish = [&](uint32_t bar) {  // everything stored so far (P, and rescaled O columns) is visible to the MMA issuer
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (kRemoteP) mbar_arrive_remote(bar, 0);  // the pair's MMA issuer lives in the leader CTA
+                    else mbar_arrive(bar);
+                }
+            };
+            using I0 = std::integral_constant<int, 0>;
+            using I16 = std::integral_constant<int, 16>;
+            using IA = std::integral_constant<int, VAP_ATTN_P3_PAIRS>;
+            if (!(kP3 && ch == 1)) {
+#pragma unroll 1
+                for (int pass = 0;; ++pass) {  // at most two passes: the second one runs against the refreshed reference
+                    pairs(I0{}, I16{});
+                    if (pass == 1 || !vote(I0{}, I16{})) break;
+                    update(ch > 0 ? sm.pv_half(i) : 0u);  // ch 1: the PV MMAs of this step's first half must have left O_i
+                }
+                if (ch == 0) TR(3);
+                l2[0] = add_f32x2(l2[0], ls[0]);
+                l2[1] = add_f32x2(l2[1], ls[1]);
+                // P is published the moment it is stored: PV of the first half has to be out of the way before the second half ends.  (Tried on a
+                // B200 and slower: loading the second half's scores before this store, 1404 -> 1312 TFLOP/s, and publishing half 0 from inside the
+                // second half's pass to hide the store latency, -> 1185: every clock P half 0 is late moves its PV into the tail, profiles/r02_attn_ab.json.)
+                tmem_st_16x128b_x8(s_col + 32 * ch, pk);
+                if (ch == 1) TR(5);
+                publish(sm.p_full(i, ch));
+            } else if constexpr (kP3) {
+                // second half in two stages: the first VAP_ATTN_P3_PAIRS pairs are stored at once; their publish (store wait + fence + arrive) is
+                // issued after the LAST pairs' exp work has been issued, which hides the store latency; the last stage is a quarter (or less)
+                // of the half, so that the MMAs behind the softmax on the tile's dependency chain are 8 - kMid PV steps + QK^T.
+#pragma unroll 1
+                for (int pass = 0;; ++pass) {
+                    pairs(I0{}, IA{});
+                    if (pass == 1 || !vote(I0{}, IA{})) break;
+                    update(sm.pv_half(i));
+                }
+                l2[0] = add_f32x2(l2[0], ls[0]);
+                l2[1] = add_f32x2(l2[1], ls[1]);
+                tmem_st_16x128b_x4(s_col + 32, pk);
+                if (VAP_ATTN_P3_PAIRS == 12) tmem_st_16x128b_x2(s_col + 32 + 16, pk + 8);
+#pragma unroll 1
+                for (int pass = 0;; ++pass) {
+                    pairs(IA{}, I16{});
+                    if (pass == 0) publish(sm.p_full(i, 1));
+                    if (pass == 1 || !vote(IA{}, I16{})) break;
+                    update(sm.pv_mid(i));  // stage 1 is published: its PV MMAs (and with them half 0's) must have left O_i
+                }
+                l2[0] = add_f32x2(l2[0], ls[0]);
+                l2[1] = add_f32x2(l2[1], ls[1]);
+                if (VAP_ATTN_P3_PAIRS == 12) tmem_st_16x128b_x2(s_col + 32 + 24, pk + 12);
+                else tmem_st_16x128b_x4(s_col + 32 + 16, pk + 8);
+                TR(5);
+                publish(sm.p_last(i));
             }
 #undef SF
-            if (ch == 0) TR(3);
-            l2[0] = add_f32x2(l2[0], ls[0]);
-            l2[1] = add_f32x2(l2[1], ls[1]);
-            // P is published the moment it is stored: PV of the first half has to be out of the way before the second half ends.  (Tried on a
-            // B200 and slower: loading the second half's scores before this store, 1404 -> 1312 TFLOP/s, and publishing half 0 from inside the
-            // second half's pass to hide the store latency, -> 1185: every clock P half 0 is late moves its PV into the tail, profiles/r02_attn_ab.json.)
-            tmem_st_16x128b_x8(s_col + 32 * ch, pk);
-            if (ch == 1) TR(5);
-            tmem_st_wait();  // covers the rescaled O columns too
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                if (kRemoteP) mbar_arrive_remote(sm.p_full(i, ch), 0);  // the pair's MMA issuer lives in the leader CTA
-                else mbar_arrive(sm.p_full(i, ch));
-            }
         }
         TR(6);
     }
@@ -589,7 +663,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (warp == 0) {
             attn_producer_warp<D, CL>(sm, &tmQ, &tmK, &tmV, q0, head, batch, j0, n_kv, cta_rank);
         } else if (warp == 1) {
-            attn_mma_warp<D, CL>(sm, tmem_base, n_kv, (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) ? p.trace + 1024 : nullptr);
+            attn_mma_warp<D, CL, VAP_ATTN_P3 != 0>(sm, tmem_base, n_kv, (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) ? p.trace + 1024 : nullptr);
         }
     } else {
         attn_softmax_lane16<D, false>(sm, p, wk, tmem_base, warp, lane);
@@ -1097,7 +1171,7 @@ template <int D, int CL, bool ROW>
 static int launch_attn_d(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const AttnParams& p, cudaStream_t stream) {
     using Cfg = AttnCfg<D>;
     static_assert(Cfg::kSmemBytes <= 232448, "shared memory budget");
-    static_assert(2 * Cfg::kKvStages + 12 <= Cfg::kBarBytes / 8, "barrier area");
+    static_assert(2 * Cfg::kKvStages + 16 <= Cfg::kBarBytes / 8, "barrier area");
     auto kernel = ROW ? attn_fwd_row_kernel<D, CL> : attn_fwd_kernel<D, CL>;
     constexpr int threads = ROW ? kRowThreads : kAttnThreads;
     static bool opted_in[64] = {};

@@ -24,7 +24,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops, ulysses
+from . import ops, streams, ulysses
 from .modules import Attention, FeedForward, FP32LayerNorm, PixArtAlphaTextProjection, TimestepEmbedding
 from .rope import Tables, as_tables, wan_rope_tables
 
@@ -336,26 +336,32 @@ def wan_block_forward(self: nn.Module, hidden_states: torch.Tensor, encoder_hidd
 
     if num_mot_ref != 1:
         raise AssertionError("num_mot_ref must be 1 (transformer_wan_mot.py:611)")
-    xr = hidden_states_mot_ref.contiguous()
     attn1_r = self.attn1_mot_ref
-    shift_r, scale1p_r, gate_r, c_shift_r, c_scale1p_r, c_gate_r = _modulation(self.scale_shift_table_mot_ref, temb_mot_ref)
-    tables_r = as_tables(rotary_emb_mot_ref, hd, x.device)
     B, S, d = x.shape
-    Sr = xr.shape[1]
+    Sr = hidden_states_mot_ref.shape[1]
     inner = attn1.to_q.weight.shape[0]
+    # The expert's stream runs on a side CUDA stream between the joint attentions (streams.py): fork -> [expert | target] -> join -> attention
+    # -> fork -> [expert | target] -> join.  ds is None on CPU tensors / when switched off: then everything is issued in the same order on one stream.
+    ds = streams.dual(x.device, max(S, Sr))
 
     # 1. joint self-attention (:620-663)
-    xn = ops.adaln_layernorm(x, eps=eps, rounding=ops.ROUND_WAN, scale1p=scale1p, shift=shift)
-    xn_r = ops.adaln_layernorm(xr, eps=self.norm1_mot_ref.eps, rounding=ops.ROUND_WAN, scale1p=scale1p_r, shift=shift_r)
     qkv = torch.empty((B, S + Sr, 3 * inner), dtype=torch.bfloat16, device=x.device)
-    px = _sp_p2p(x, S + Sr, heads, hd)
-    if px is not None:  # Ulysses over peer memory: both exchanges are fused into the norm/RoPE and attention kernels
-        _self_attn_qkv(attn1, xn, tables, out=qkv[:, :S], scatter=(px, 0))
-        _self_attn_qkv(attn1_r, xn_r, tables_r, out=qkv[:, S:], scatter=(px, S))
+    px = _sp_p2p(x, S + Sr, heads, hd)  # Ulysses over peer memory: both exchanges are fused into the norm/RoPE and attention kernels
+    if ds is not None:
+        ds.fork()
+    with streams.side(ds):
+        xr = hidden_states_mot_ref.contiguous()
+        shift_r, scale1p_r, gate_r, c_shift_r, c_scale1p_r, c_gate_r = _modulation(self.scale_shift_table_mot_ref, temb_mot_ref)
+        tables_r = as_tables(rotary_emb_mot_ref, hd, x.device)
+        xn_r = ops.adaln_layernorm(xr, eps=self.norm1_mot_ref.eps, rounding=ops.ROUND_WAN, scale1p=scale1p_r, shift=shift_r)
+        _self_attn_qkv(attn1_r, xn_r, tables_r, out=qkv[:, S:], scatter=(px, S) if px is not None else None)
+    xn = ops.adaln_layernorm(x, eps=eps, rounding=ops.ROUND_WAN, scale1p=scale1p, shift=shift)
+    _self_attn_qkv(attn1, xn, tables, out=qkv[:, :S], scatter=(px, 0) if px is not None else None)
+    if ds is not None:
+        ds.join()
+    if px is not None:
         o = px.attention().unsqueeze(0)
     else:
-        _self_attn_qkv(attn1, xn, tables, out=qkv[:, :S])
-        _self_attn_qkv(attn1_r, xn_r, tables_r, out=qkv[:, S:])
         if self.__dict__.get("_vap_ref_output_unused", False) and ulysses.current() is None:
             # Last MoT block of a shell whose output head reads the target stream only (:951-987): the expert stream's output is dead,
             # so its query rows, O-projection, cross-attention and FFN are skipped; its K / V still feed the target's attention.
@@ -366,12 +372,17 @@ def wan_block_forward(self: nn.Module, hidden_states: torch.Tensor, encoder_hidd
             x = _stream_tail(self, "", x, encoder_hidden_states, c_shift, c_scale1p, c_gate, eps, 1)
             return x, hidden_states_mot_ref
         o = _joint_attention(qkv, heads)  # [B, J, inner], rows [target | ref]
-    x = _linear(attn1.to_out[0], o[:, :S], epilogue=ops.EPI_GATE_RES_F32, residual=x, gate=gate)
-    xr = _linear(attn1_r.to_out[0], o[:, S:], epilogue=ops.EPI_GATE_RES_F32, residual=xr, gate=gate_r)
 
-    # 2./3. per-stream cross-attention and FFN (:668-697)
+    # 2./3. per stream: output projection + gated residual (:649-663), cross-attention and FFN (:668-697)
+    if ds is not None:
+        ds.fork()
+    with streams.side(ds):
+        xr = _linear(attn1_r.to_out[0], o[:, S:], epilogue=ops.EPI_GATE_RES_F32, residual=xr, gate=gate_r)
+        xr = _stream_tail(self, "_mot_ref", xr, encoder_hidden_states_mot_ref, c_shift_r, c_scale1p_r, c_gate_r, self.norm3_mot_ref.eps, num_mot_ref)
+    x = _linear(attn1.to_out[0], o[:, :S], epilogue=ops.EPI_GATE_RES_F32, residual=x, gate=gate)
     x = _stream_tail(self, "", x, encoder_hidden_states, c_shift, c_scale1p, c_gate, eps, 1)
-    xr = _stream_tail(self, "_mot_ref", xr, encoder_hidden_states_mot_ref, c_shift_r, c_scale1p_r, c_gate_r, self.norm3_mot_ref.eps, num_mot_ref)
+    if ds is not None:
+        ds.join()  # `o` and the contexts the side stream read are still referenced here
     return x, xr
 
 
