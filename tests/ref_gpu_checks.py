@@ -187,6 +187,49 @@ def check_cog_denoise(cfg: dict, latent, steps: int = 4):
     return res
 
 
+def check_train_block_level(family: str, cfg: dict, latent):
+    """Trainer seam at block level (training.py): only the "_mot_ref" parameters train (sft_trainer/trainer.py:154-164); the loss back-propagates
+    (a) through the stock reference (torch autograd everywhere, cuDNN SDPA) and (b) through install(level="block", trainable=True) — fused
+    forward, reference block recomputed in the backward with vap_attention_fwd / vap_attention_bwd in the SDPA slot.  Every trainable tensor
+    must get a gradient with cosine > 0.99 against the stock one; forward + backward times of both are reported."""
+    model = ref_gpu.build_reference(family, cfg, seed=7, device=DEV).train()
+    for name, prm in model.named_parameters():
+        prm.requires_grad_("_mot_ref" in name)
+    inp = _inputs(family, cfg, latent)
+    with torch.no_grad():
+        shape = model(**inp, return_dict=False)[0].shape
+    target = torch.randn(shape, generator=torch.Generator(device=DEV).manual_seed(1), device=DEV)
+
+    def grads():
+        model.zero_grad(set_to_none=True)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = model(**inp, return_dict=False)[0].float()
+        torch.nn.functional.mse_loss(out, target).backward()
+        e1.record()
+        torch.cuda.synchronize()
+        return {n: p.grad.float().clone() for n, p in model.named_parameters() if p.grad is not None}, e0.elapsed_time(e1)
+
+    grads()  # warm-up (cuDNN plans, allocator)
+    ref, ms_stock = grads()
+    vap.install(model, level="block", trainable=True)
+    try:
+        grads()
+        got, ms_ours = grads()
+    finally:
+        vap.uninstall(model)
+    cos = {}
+    for n in ref:
+        a, b = ref[n].double().flatten(), got[n].double().flatten()
+        if a.norm() > 0:
+            cos[n] = (torch.dot(a, b) / (a.norm() * b.norm())).item()
+    res = dict(trainable_tensors=len(ref), same_names=sorted(ref) == sorted(got), worst_cosine=min(cos.values()), worst_name=min(cos, key=cos.get),
+               stock_fwd_bwd_ms=ms_stock, installed_fwd_bwd_ms=ms_ours)
+    assert res["same_names"] and res["worst_cosine"] > 0.99, res
+    return res
+
+
 # widths of BASELINE.json configs[2] / configs[1]; 3 layers (MoT, plain, MoT), reduced token count
 WAN_14B_3L = dict(synth.WAN_14B, num_layers=3, block_idx_with_mot_ref=[0, 2])
 COG_5B_3L = dict(synth.COG_5B, num_layers=3, block_idx_with_mot_ref=[0, 1])
@@ -198,6 +241,9 @@ CHECKS = {
     # CogVideoX-5B widths; the learned positional embedding of the 5B-I2V config pins the latent grid to 13 x 60 x 90
     "ref_cog5b_blocks": lambda: check_blocks("cog", COG_5B_3L, (13, 60, 90)),
     "ref_cog5b_denoise": lambda: check_cog_denoise(COG_5B_3L, (13, 60, 90)),
+    # block-level trainer seam: gradients of the expert's parameters, stock autograd vs fused forward + recomputed backward
+    "ref_wan14b_train_block": lambda: check_train_block_level("wan", WAN_14B_3L, (3, 60, 104)),
+    "ref_cog5b_train_block": lambda: check_train_block_level("cog", dict(synth.COG_5B, num_layers=2, block_idx_with_mot_ref=[0, 1]), (13, 60, 90)),
     # BASELINE.json configs[2] itself: all 40 MoT blocks, 49 frames 480x832 (J = 40 560), one forward + the 4-step guided denoise
     "ref_wan14b_full_cfg3": lambda: check_wan_full(),
 }

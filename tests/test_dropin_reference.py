@@ -78,9 +78,12 @@ def test_install_on_the_reference_model_matches_the_reference(family):
         assert res["block_rope_swapped"] and res["processor_rope_swapped"], res
 
 
-def _train_worker(family, q):
-    """The trainer's contract at the SDPA seam (finetrainers/trainer/sft_trainer/trainer.py:154-164, 674-714): only parameters with
-    "_mot_ref" in their name train; the loss back-propagates through the reference's own block code and OUR attention."""
+def _train_worker(family, q, mode="sdpa"):
+    """mode "sdpa": the trainer's contract at the SDPA seam (finetrainers/trainer/sft_trainer/trainer.py:154-164, 674-714): only parameters with
+    "_mot_ref" in their name train; the loss back-propagates through the reference's own block code and OUR attention.
+    mode "block": install(level="block", trainable=True) — the fused forward as the first pass of activation checkpointing, the reference's block
+    code recomputed in the backward (video-as-prompt_b200/training.py); also under torch.utils.checkpoint, as the trainer calls the blocks when
+    gradient checkpointing is on (positional arguments), and without gradient tracking (plain fused forward)."""
     try:
         sys.path.insert(0, ROOT)
         sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -111,10 +114,22 @@ def _train_worker(family, q):
             return {n: p.grad.float().clone() for n, p in model.named_parameters() if p.grad is not None}
 
         ref = grads()
-        vap.install(model, level="sdpa")
-        got = grads()
-        vap.uninstall(model)
-        res = {"n_ref": len(ref), "n_got": len(got), "same_names": sorted(ref) == sorted(got)}
+        res = {}
+        if mode == "sdpa":
+            vap.install(model, level="sdpa")
+            got = grads()
+            vap.uninstall(model)
+        else:
+            with torch.no_grad():
+                out_ref = model(**inp, return_dict=False)[0].float()
+            vap.install(model, level="block", trainable=True)
+            got = grads()
+            with torch.no_grad():  # no gradient tracking: the wrapper is the fused forward itself
+                out = model(**inp, return_dict=False)[0].float()
+            res["forward_err"] = ((out - out_ref).abs().max() / out_ref.abs().max()).item()
+            res["sdpa_slot_restored"] = torch.nn.functional.scaled_dot_product_attention is not vap.sdpa.joint_sdpa
+            vap.uninstall(model)
+        res.update({"n_ref": len(ref), "n_got": len(got), "same_names": sorted(ref) == sorted(got)})
         # cosine per parameter (bf16 training noise makes max-abs a poor gate for gradients), worst case over all trainable tensors
         cos = {}
         for n in ref:
@@ -128,6 +143,22 @@ def _train_worker(family, q):
     except Exception:  # noqa: BLE001
         import traceback
         q.put({"error": traceback.format_exc()[-3000:]})
+
+
+@pytest.mark.parametrize("family", ["wan", "cog"])
+def test_fused_block_forward_with_recompute_backward_trains_the_reference_model(family):
+    """install(level="block", trainable=True): every trainable tensor gets a gradient whose cosine with the stock reference's is > 0.99 (the
+    gradients are the reference block's own, evaluated at the saved inputs; the inputs of later blocks differ by the fused path's bf16 noise)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    p = ctx.Process(target=_train_worker, args=(family, q, "block"))
+    p.start()
+    res = q.get(timeout=600)
+    p.join(60)
+    assert "error" not in res, res.get("error")
+    assert res["same_names"] and res["n_got"] > 0 and res["attn_grads_present"], res
+    assert res["worst_cosine"] > 0.99, res
+    assert res["forward_err"] < 2e-2 and res["sdpa_slot_restored"], res
 
 
 @pytest.mark.parametrize("family", ["wan", "cog"])

@@ -333,3 +333,22 @@ def test_bench_flop_accounting_matches_the_survey():
         got_total, got_attn = bench.wan_flops(w[name]["cfg"], S, S)
         assert abs(got_total / total - 1) < 1e-3 and abs(got_attn / attn - 1) < 1e-3, (name, got_total, got_attn)
     assert [i for i in w["wan14b_d20"]["cfg"]["block_idx_with_mot_ref"]] == list(range(0, 40, 2))
+
+
+def test_dual_stream_schedule_is_off_for_cpu_tensors_and_automatic_by_row_count(monkeypatch):
+    """streams.dual(): None for CPU tensors (the gloo / stand-in tests run both token streams in issue order on one queue); in the default
+    "auto" mode the two-stream schedule is chosen by the rows per stream (measured: +6.6 % at the 2 535 rows a rank owns under 8-way Ulysses,
+    neutral at the full 20 280); dual_streams(True / False / None) forces / restores it."""
+    st = vap.streams
+    assert st.dual(torch.device("cpu"), 100) is None
+    created = []
+    monkeypatch.setattr(st, "DualStream", lambda dev: created.append(dev) or object())
+    monkeypatch.setattr(st, "_PER_DEVICE", {})
+    with vap.dual_streams(None):
+        assert st.dual(torch.device("cuda", 0), 2535) is not None and st.dual(torch.device("cuda", 0), 20280) is None
+        assert st.dual(torch.device("cuda", 0), st.AUTO_MAX_ROWS) is not None
+    with vap.dual_streams(True):
+        assert st.dual(torch.device("cuda", 0), 20280) is not None
+    with vap.dual_streams(False):
+        assert st.dual(torch.device("cuda", 0), 100) is None
+    assert created == [torch.device("cuda", 0)]  # one DualStream per device, cached

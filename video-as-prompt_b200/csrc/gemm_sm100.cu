@@ -75,15 +75,35 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
 
 // Epilogue of one accumulator row: thread `lane` of the warp that owns TMEM lane quarter q reads its row (BN fp32 columns at
 // `taddr`, 32 at a time), applies bias / GELU / gated residual with the reference's bf16 rounding points and stores 16-byte vectors.
-template <int BN>
-__device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t taddr, int row, int nb) {
+template <int BN, bool kRes>
+__device__ __forceinline__ void epilogue_rows_impl(const GemmParams& p, uint32_t taddr, int row, int nb) {
     const bool row_ok = row < p.M;
     const float* gate = nullptr;
     if (p.gate) gate = p.gate + (p.rows_per_batch > 0 ? (row_ok ? row / p.rows_per_batch : 0) : 0) * p.gate_stride;
     __nv_bfloat16* crow = p.C + static_cast<int64_t>(row) * p.ldc;
     const __nv_bfloat16* rrow = p.R ? p.R + static_cast<int64_t>(row) * p.ldr : nullptr;
+    constexpr bool has_res = kRes;  // two instantiations: the bias / GELU epilogues keep their short loop body (a shared body cost the GELU epilogue 25 % at K = 3072)
+    // The residual row is read one 32-column chunk AHEAD of the accumulator (a thread's 64 bytes per chunk are two full sectors of its own row, but
+    // 32 different rows per warp instruction: latency-bound).  Read right before use, the eight chunks of a residual epilogue took longer than the
+    // main loop of the next tile at K = 5120 (ncu launch list, Wan O-projection 20 280 x 5120 x 5120: 820 us against 687 us for the same GEMM
+    // with the bias-only epilogue); one chunk ahead, the loads fly during the tcgen05.ld + arithmetic + stores of the chunk before.
+    uint4 rnext[4];
+    auto load_res = [&](int c0) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int n = nb * BN + c0 + 8 * g;
+            if (row_ok && n < p.N) rnext[g] = *reinterpret_cast<const uint4*>(rrow + n);
+        }
+    };
+    if (has_res) load_res(0);
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint4 rcur[4];
+        if (has_res) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) rcur[g] = rnext[g];
+            if (c0 + 32 < BN) load_res(c0 + 32);
+        }
         uint32_t v[32];
         tmem_ld_x32(taddr + c0, v);
         tmem_ld_wait();
@@ -106,15 +126,14 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t tadd
                             y[2 * j + 1] += f.y;
                         }
                     }
-                    if (p.epilogue != kEpiBias) {
+                    if (kRes || p.epilogue != kEpiBias) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) y[j] = bf16_round(y[j]);
-                        if (p.epilogue == kEpiBiasGelu) {
+                        if (!kRes) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) y[j] = gelu_tanh_f(y[j]);
                         } else {
-                            const uint4 rr = *reinterpret_cast<const uint4*>(rrow + n);
-                            const uint32_t* ru = reinterpret_cast<const uint32_t*>(&rr);
+                            const uint32_t* ru = reinterpret_cast<const uint32_t*>(&rcur[g]);
                             float r[8];
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
@@ -149,6 +168,12 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t tadd
             }
         }
     }
+}
+
+template <int BN>
+__device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t taddr, int row, int nb) {
+    if (p.epilogue >= kEpiGateResF32) epilogue_rows_impl<BN, true>(p, taddr, row, nb);
+    else epilogue_rows_impl<BN, false>(p, taddr, row, nb);
 }
 
 // CL = 2: the kernel runs as clusters of two CTAs that work on vertically adjacent M-blocks of the SAME N-block: each CTA fetches

@@ -16,7 +16,7 @@ import types
 
 import torch.nn as nn
 
-from . import cogvideox, rope, sdpa, wan
+from . import cogvideox, rope, sdpa, training, wan
 
 _WAN_PROC = {"WanAttnMOTProcessor2_0": wan.WanAttnMOTProcessor2_0, "WanAttnCrossMOTProcessor2_0": wan.WanAttnCrossMOTProcessor2_0,
              "WanAttnProcessor2_0": wan.WanAttnProcessor2_0}
@@ -55,18 +55,25 @@ def _restore_wan_rope(model: nn.Module) -> None:
             del mod.forward
 
 
-def install(model: nn.Module, level: str = "block", strict: bool = True) -> nn.Module:
+def install(model: nn.Module, level: str = "block", strict: bool = True, trainable: bool = False) -> nn.Module:
     """strict=False (levels "processor" / "sdpa"): SDPA calls outside the kernel's envelope — a VAE's or text encoder's attention under the
-    global patch — fall through to the original torch function instead of raising (sdpa.patch_scaled_dot_product_attention)."""
+    global patch — fall through to the original torch function instead of raising (sdpa.patch_scaled_dot_product_attention).
+    trainable=True (level "block", the reference's own block classes): the fused forward becomes the first pass of activation checkpointing —
+    the backward pass re-runs the block's original forward under autograd with the attention kernels' backward in the SDPA slot (training.py)."""
     family, blocks = _blocks(model)
+    if trainable and level != "block":
+        raise ValueError("trainable=True applies to level='block' (levels 'processor' / 'sdpa' keep torch autograd for everything but the attention)")
     if level == "block":
         fwd = wan.wan_block_forward if family == "wan" else cogvideox.cog_block_forward
         for blk in blocks:
             if not hasattr(blk, "with_mot_ref"):
                 raise TypeError(f"{type(blk).__name__} is not a MoT block (no `with_mot_ref`)")
+            if trainable and getattr(type(blk).forward, "__wrapped__", type(blk).forward) in (wan.wan_block_forward, cogvideox.cog_block_forward):
+                raise TypeError("trainable=True needs a block whose own forward is differentiable torch code (the reference's classes); "
+                                "this package's stand-alone shell has none — train it with install(level='sdpa') on the reference model")
             blk.__dict__["_vap_original_forward"] = blk.forward
-            blk.forward = types.MethodType(fwd, blk)
-        if family == "wan":
+            blk.forward = types.MethodType(training.checkpointed_block_forward(fwd, blk.forward) if trainable else fwd, blk)
+        if family == "wan" and not trainable:  # the recomputed reference forward needs the shell's own complex freqs
             _swap_wan_rope(model)
     elif level == "processor":
         table = _WAN_PROC if family == "wan" else _COG_PROC
