@@ -32,7 +32,14 @@ enum GemmEpilogue : int {
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;
-constexpr int kGemmThreads = 256;
+// Epilogue warps per CTA: 4 (one per TMEM lane quarter, a thread drains a whole accumulator row) or 8 (two per quarter, each draining half of the
+// row's columns): the epilogue of a tile overlaps the main loop of the next one, and at K <= 5120 a four-warp residual / GELU epilogue is the longer of the two.
+#ifndef VAP_GEMM_EPI_WARPS
+#define VAP_GEMM_EPI_WARPS 8
+#endif
+constexpr int kEpiWarps = VAP_GEMM_EPI_WARPS;
+static_assert(kEpiWarps == 4 || kEpiWarps == 8, "VAP_GEMM_EPI_WARPS");
+constexpr int kGemmThreads = 128 + 32 * kEpiWarps;
 #ifndef VAP_GEMM_GROUP_M
 #define VAP_GEMM_GROUP_M 16
 #endif
@@ -76,7 +83,7 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
 // Epilogue of one accumulator row: thread `lane` of the warp that owns TMEM lane quarter q reads its row (BN fp32 columns at
 // `taddr`, 32 at a time), applies bias / GELU / gated residual with the reference's bf16 rounding points and stores 16-byte vectors.
 template <int BN, bool kRes>
-__device__ __forceinline__ void epilogue_rows_impl(const GemmParams& p, uint32_t taddr, int row, int nb) {
+__device__ __forceinline__ void epilogue_rows_impl(const GemmParams& p, uint32_t taddr, int row, int nb, int c_begin, int c_end) {
     const bool row_ok = row < p.M;
     const float* gate = nullptr;
     if (p.gate) gate = p.gate + (p.rows_per_batch > 0 ? (row_ok ? row / p.rows_per_batch : 0) : 0) * p.gate_stride;
@@ -95,14 +102,14 @@ __device__ __forceinline__ void epilogue_rows_impl(const GemmParams& p, uint32_t
             if (row_ok && n < p.N) rnext[g] = *reinterpret_cast<const uint4*>(rrow + n);
         }
     };
-    if (has_res) load_res(0);
+    if (has_res) load_res(c_begin);
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int c0 = c_begin; c0 < c_end; c0 += 32) {
         uint4 rcur[4];
         if (has_res) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) rcur[g] = rnext[g];
-            if (c0 + 32 < BN) load_res(c0 + 32);
+            if (c0 + 32 < c_end) load_res(c0 + 32);
         }
         uint32_t v[32];
         tmem_ld_x32(taddr + c0, v);
@@ -170,10 +177,13 @@ __device__ __forceinline__ void epilogue_rows_impl(const GemmParams& p, uint32_t
     }
 }
 
+// `part` = (warp - 4) / 4: which share of the row's columns this warp drains (kEpiWarps / 4 shares)
 template <int BN>
-__device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t taddr, int row, int nb) {
-    if (p.epilogue >= kEpiGateResF32) epilogue_rows_impl<BN, true>(p, taddr, row, nb);
-    else epilogue_rows_impl<BN, false>(p, taddr, row, nb);
+__device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t taddr, int row, int nb, int part) {
+    constexpr int kCols = BN / (kEpiWarps / 4);
+    static_assert(kCols % 32 == 0, "column share of an epilogue warp");
+    if (p.epilogue >= kEpiGateResF32) epilogue_rows_impl<BN, true>(p, taddr, row, nb, part * kCols, (part + 1) * kCols);
+    else epilogue_rows_impl<BN, false>(p, taddr, row, nb, part * kCols, (part + 1) * kCols);
 }
 
 // CL = 2: the kernel runs as clusters of two CTAs that work on vertically adjacent M-blocks of the SAME N-block: each CTA fetches
@@ -216,7 +226,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(tfull_bar(s), 1);
-            mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
+            mbar_init(tempty_bar(s), kEpiWarps);  // one arrive per epilogue warp
         }
         fence_mbar_init();
     }
@@ -310,7 +320,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tc_fence_after();
 #pragma unroll 1
             for (int mt = 0; mt < MT; ++mt)
-                epilogue_rows<BN>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * (MT * BN) + mt * BN, (mb * MT + mt) * kBM + q * 32 + lane, nb);
+                epilogue_rows<BN>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * (MT * BN) + mt * BN, (mb * MT + mt) * kBM + q * 32 + lane, nb, (warp - 4) >> 2);
             // all TMEM reads of this accumulator stage are complete (tmem_ld_wait) -> release it
             tc_fence_before();
             __syncwarp();
@@ -340,7 +350,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 //             its transaction bytes there (cp.async.bulk.tensor.cta_group::2)
 //   empty[s]  per CTA; the leader's tcgen05.commit.cta_group::2 arrives on both (multicast)
 //   tfull[a]  per CTA; committed by the leader on both -> each CTA's epilogue warps read their own 128 accumulator rows
-//   tempty[a] lives in the leader, 8 arrivals: the four epilogue warps of BOTH CTAs (the peer's arrive remotely)
+//   tempty[a] lives in the leader, 2 x kEpiWarps arrivals: the epilogue warps of BOTH CTAs (the peer's arrive remotely)
 // ------------------------------------------------------------------------------------------------------------------------
 struct GemmPairCfg {
     static constexpr int BN = 256;
@@ -386,7 +396,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(tfull_bar(s), 1);
-            mbar_init(tempty_bar(s), 8);  // four epilogue warps of each CTA; unused in the peer
+            mbar_init(tempty_bar(s), 2 * kEpiWarps);  // the epilogue warps of each CTA; unused in the peer
         }
         fence_mbar_init();
     }
@@ -469,7 +479,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             tile_coords(tile, m_units, p.n_blocks, mu, nb);
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
-            epilogue_rows<BN>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN, (2 * mu + cta_rank) * kBM + q * 32 + lane, nb);
+            epilogue_rows<BN>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN, (2 * mu + cta_rank) * kBM + q * 32 + lane, nb, (warp - 4) >> 2);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(tempty_bar(acc), 0);

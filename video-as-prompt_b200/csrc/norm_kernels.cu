@@ -309,7 +309,10 @@ static int staged_ctas_per_batch(int64_t rows, int64_t rows_per_batch, int64_t* 
     if (*nbatch > 64 || rows < 16 * kStagedWarps * 8) return 0;  // few rows: the per-CTA staging of the vectors would not amortise
     int per = static_cast<int>(sm_count() / *nbatch);
     if (per < 1) per = 1;
-    const int64_t max_useful = (rpb + kStagedWarps * 4 - 1) / (kStagedWarps * 4);  // at least ~4 rows per warp
+    // developer switch, read per call (tools/norm_rows_ab.py): minimum rows per warp before another CTA is worth staging the vectors again
+    const char* env = getenv("VAP_NORM_STAGED_ROWS_PER_WARP");
+    const int rows_per_warp = (env && atoi(env) > 0) ? atoi(env) : 4;
+    const int64_t max_useful = (rpb + kStagedWarps * rows_per_warp - 1) / (kStagedWarps * rows_per_warp);
     if (per > max_useful) per = static_cast<int>(max_useful);
     return per;
 }
