@@ -55,7 +55,14 @@ def _worker(rank, world, port, family, ret):
             sp = vap.ulysses.enable(mode="nccl")  # the collective transport (gloo here); "p2p" needs NVLink peer memory
             assert vap.ulysses.current() is sp
             out = model(**inp, return_dict=False)[0].float()
-            if family == "wan":  # the context cache is rank-local host logic: same sharded forward, bit for bit, hit or miss
+            if family == "wan":
+                # the cross-attention context K / V are computed on one rank each and all-gathered (wan._shard_context_kv): the replicated
+                # computation gives the same forward bit for bit, and no module keeps its hand-over after the forward
+                model.shard_context_projections = False
+                assert torch.equal(model(**inp, return_dict=False)[0].float(), out)
+                model.shard_context_projections = True
+                assert not any("_vap_ctx_prefill" in m.__dict__ for m in model.modules())
+                # the context cache is rank-local host logic: same sharded forward, bit for bit, hit or miss
                 with vap.wan.context_cache():
                     c1 = model(**inp, return_dict=False)[0].float()
                     c2 = model(**inp, return_dict=False)[0].float()

@@ -311,7 +311,9 @@ static int staged_ctas_per_batch(int64_t rows, int64_t rows_per_batch, int64_t* 
     if (per < 1) per = 1;
     // developer switch, read per call (tools/norm_rows_ab.py): minimum rows per warp before another CTA is worth staging the vectors again
     const char* env = getenv("VAP_NORM_STAGED_ROWS_PER_WARP");
-    const int rows_per_warp = (env && atoi(env) > 0) ? atoi(env) : 4;
+    // 2: measured on a B200 (profiles/r02_norm_rows_ab.json): at the 2 535 rows of one rank of 8-way Ulysses the q/k-norm + RoPE takes 50.6 us with
+    // 2 rows per warp against 65.5 with 4 and 104 with 8; from 5 070 rows up the choice makes no difference
+    const int rows_per_warp = (env && atoi(env) > 0) ? atoi(env) : 2;
     const int64_t max_useful = (rpb + kStagedWarps * rows_per_warp - 1) / (kStagedWarps * rows_per_warp);
     if (per > max_useful) per = static_cast<int>(max_useful);
     return per;

@@ -21,6 +21,7 @@ import weakref
 from typing import Any, Dict, List, Optional, Tuple, Union
 
 import torch
+import torch.distributed as dist
 import torch.nn as nn
 import torch.nn.functional as F
 
@@ -209,46 +210,106 @@ def _split_qkv(qkv: torch.Tensor, heads: int):
     return (_heads_view(qkv[..., :inner], heads), _heads_view(qkv[..., inner:2 * inner], heads), _heads_view(qkv[..., 2 * inner:], heads))
 
 
+def _context_split(attn: nn.Module, ctx: torch.Tensor, num_mot_ref: int = 1) -> int:
+    """Number of leading image tokens of a cross-attention context.  The reference splits off the image tokens only when the module has the
+    added projections (:47-52, :127-129); a text-only block attends over the whole context, whatever its length."""
+    img_len = ctx.shape[1] - TEXT_CONTEXT_LEN * num_mot_ref if getattr(attn, "add_k_proj", None) is not None else 0
+    if img_len < 0:
+        raise ValueError(f"context of {ctx.shape[1]} tokens is shorter than the {TEXT_CONTEXT_LEN * num_mot_ref} text tokens the I2V cross-attention expects")
+    return img_len
+
+
+def _context_kv(attn: nn.Module, ctx: torch.Tensor, which: str, out: Optional[torch.Tensor] = None, num_mot_ref: int = 1) -> torch.Tensor:
+    """K / V of the cross-attention context (:131-147): which = "text": [norm_k(to_k(text)) | to_v(text)], "image": [norm_added_k(add_k_proj(img)) |
+    add_v_proj(img)], as one [B, tokens, 2 * inner] tensor (written into `out` if given).  Depends on the context and the module's weights only."""
+    img_len = _context_split(attn, ctx, num_mot_ref)
+    heads = attn.heads
+    inner = attn.to_q.weight.shape[0]
+    if which == "text":
+        W, b = _packed(attn, "kv", [attn.to_k, attn.to_v])
+        src, norm = ctx[:, img_len:], attn.norm_k
+    else:
+        W, b = _packed(attn, "kv_img", [attn.add_k_proj, attn.add_v_proj])
+        src, norm = ctx[:, :img_len], attn.norm_added_k
+    kv = ops.linear(src, W, b, out=out)
+    ops.qk_norm_rope_(kv[..., :inner], None, heads=heads, head_dim=inner // heads, wq=_f32(norm, "w", norm.weight), rows_per_batch=kv.shape[1],
+                      eps=attn.norm_q.eps, mode=ops.QK_WAN)
+    return kv
+
+
 def _cross_attn(attn: nn.Module, x: torch.Tensor, ctx: torch.Tensor, num_mot_ref: int = 1) -> torch.Tensor:
     """WanAttnCrossMOTProcessor2_0 arithmetic (:115-186) up to (and excluding) to_out: returns o_text + o_image [B, L, d]."""
     if num_mot_ref != 1:
         raise NotImplementedError("num_mot_ref > 1 is rejected by the reference block itself (transformer_wan_mot.py:611)")
     heads = attn.heads
-    # the reference splits off the image tokens only when the module has the added projections (:47-52, :127-129); a text-only block
-    # attends over the whole context, whatever its length
-    img_len = ctx.shape[1] - TEXT_CONTEXT_LEN * num_mot_ref if getattr(attn, "add_k_proj", None) is not None else 0
-    if img_len < 0:
-        raise ValueError(f"context of {ctx.shape[1]} tokens is shorter than the {TEXT_CONTEXT_LEN * num_mot_ref} text tokens the I2V cross-attention expects")
-    ctx_img, ctx_txt = ctx[:, :img_len], ctx[:, img_len:]
+    img_len = _context_split(attn, ctx, num_mot_ref)
     inner = attn.to_q.weight.shape[0]
     hd = inner // heads
-    eps = attn.norm_q.eps
     q = _linear(attn.to_q, x)
-    ops.qk_norm_rope_(q, None, heads=heads, head_dim=hd, wq=_f32(attn.norm_q, "w", attn.norm_q.weight), rows_per_batch=q.shape[1], eps=eps,
+    ops.qk_norm_rope_(q, None, heads=heads, head_dim=hd, wq=_f32(attn.norm_q, "w", attn.norm_q.weight), rows_per_batch=q.shape[1], eps=attn.norm_q.eps,
                       mode=ops.QK_WAN)
-
-    def text_kv():
-        Wkv, bkv = _packed(attn, "kv", [attn.to_k, attn.to_v])
-        kv = ops.linear(ctx_txt, Wkv, bkv)
-        ops.qk_norm_rope_(kv[..., :inner], None, heads=heads, head_dim=hd, wq=_f32(attn.norm_k, "w", attn.norm_k.weight),
-                          rows_per_batch=kv.shape[1], eps=eps, mode=ops.QK_WAN)
-        return kv
-
-    def image_kv():
-        Wi, bi = _packed(attn, "kv_img", [attn.add_k_proj, attn.add_v_proj])
-        kvi = ops.linear(ctx_img, Wi, bi)
-        ops.qk_norm_rope_(kvi[..., :inner], None, heads=heads, head_dim=hd, wq=_f32(attn.norm_added_k, "w", attn.norm_added_k.weight),
-                          rows_per_batch=kvi.shape[1], eps=eps, mode=ops.QK_WAN)
-        return kvi
-
-    kv = _cached(attn, "kv", (ctx,), text_kv)  # keyed on the whole context tensor: ctx_txt / ctx_img are fresh views of it
+    # K / V of the context: handed over by the shell when it sharded these projections over the sequence-parallel ranks (_shard_context_kv),
+    # else computed here — once per denoise loop while context_cache() is on (keyed on the whole context tensor: its slices are fresh views)
+    pre = attn.__dict__.get("_vap_ctx_prefill")
+    if pre is not None and pre[0] != _tensor_key(ctx):
+        pre = None
+    kv = _cached(attn, "kv", (ctx,), (lambda: pre[1]) if pre is not None else (lambda: _context_kv(attn, ctx, "text", num_mot_ref=num_mot_ref)))
     qh = _heads_view(q, heads)
     o = ops.attention(qh, _heads_view(kv[..., :inner], heads), _heads_view(kv[..., inner:], heads))
     if img_len > 0:
-        kvi = _cached(attn, "kv_img", (ctx,), image_kv)
+        kvi = _cached(attn, "kv_img", (ctx,), (lambda: pre[2]) if pre is not None else (lambda: _context_kv(attn, ctx, "image", num_mot_ref=num_mot_ref)))
         # two independent softmaxes summed as bf16 tensors (:186): the second launch's epilogue adds to the first one's output
         ops.attention(qh, _heads_view(kvi[..., :inner], heads), _heads_view(kvi[..., inner:], heads), out=o, accumulate=True)
     return _token_major(o)
+
+
+def _cache_holds(owner: nn.Module, slot: str, inputs) -> bool:
+    """True if context_cache() is on and already holds the entry `_cached(owner, slot, inputs, ...)` would return."""
+    if not _CTX_CACHE_ON[0]:
+        return False
+    key = _tensor_key(*inputs)
+    return any(k == key and all(r is None or r() is not None for r in refs) for k, refs, _ in owner.__dict__.get("_vap_ctx_cache", {}).get(slot, []))
+
+
+def _shard_context_kv(blocks, ctx: torch.Tensor, ctx_r: Optional[torch.Tensor], sp) -> list:
+    """Sequence parallelism: the K / V projections of the cross-attention context (:131-147) depend on the context and the weights only, so
+    every rank of a token-sharded forward would repeat all of them — 2 x 769 x 5120 x 10240 FLOP per stream and block, ~8 ms of a 286 ms step
+    at 8 ranks (14B, 480p).  Instead rank r computes them for every P-th cross-attention module (whole GEMMs: same tile efficiency), ONE
+    all-gather hands every rank all of them, and the blocks pick theirs up (`_vap_ctx_prefill`).  Same kernels on the same operands as the
+    replicated computation: bit-identical.  Returns the modules that were prefilled (the caller clears them after the forward)."""
+    items = []
+    for blk in blocks:
+        items.append((blk.attn2, ctx))
+        if blk.with_mot_ref:
+            items.append((blk.attn2_mot_ref, ctx_r))
+    if not items or any(c is None or c.shape != ctx.shape for _, c in items):
+        return []
+    if _cache_holds(items[0][0], "kv", (items[0][1],)):
+        return []  # a denoise loop's later forwards: every module finds its K / V in the context cache
+    img_len = _context_split(items[0][0], ctx)
+    if any(_context_split(a, c) != img_len or a.to_q.weight.shape != items[0][0].to_q.weight.shape for a, c in items):
+        return []
+    P, r = sp.world, sp.rank
+    n_loc = (len(items) + P - 1) // P
+    B, Lc, _ = ctx.shape
+    width = 2 * items[0][0].to_q.weight.shape[0]
+    local = torch.empty((n_loc, B, Lc, width), dtype=torch.bfloat16, device=ctx.device)
+    for slot in range(n_loc):
+        i = slot * P + r
+        if i >= len(items):
+            local[slot].zero_()
+            continue
+        attn, c = items[i]
+        for b in range(B):  # rows of one batch element are uniformly strided inside the slot
+            _context_kv(attn, c[b:b + 1], "text", out=local[slot, b:b + 1, img_len:])
+            if img_len > 0:
+                _context_kv(attn, c[b:b + 1], "image", out=local[slot, b:b + 1, :img_len])
+    gathered = torch.empty((P * n_loc,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)  # rank-major: slot s of rank q at q * n_loc + s
+    dist.all_gather_into_tensor(gathered, local, group=sp.group)
+    for i, (attn, c) in enumerate(items):
+        g = gathered[(i % P) * n_loc + i // P]
+        attn.__dict__["_vap_ctx_prefill"] = (_tensor_key(c), g[:, img_len:], g[:, :img_len] if img_len > 0 else None)
+    return [a for a, _ in items]
 
 
 def _joint_attention(qkv: torch.Tensor, heads: int) -> torch.Tensor:
@@ -553,6 +614,9 @@ class WanTransformer3DMOTModel(nn.Module):
         # expert-side query rows / O-projection / cross-attention / FFN (same model output, ~1 % less work at 40/40 MoT blocks).
         # Off by default: the benchmark step and the per-block parity checks run the reference's full arithmetic.
         self.skip_dead_reference_work = False
+        # Under Ulysses sequence parallelism: compute every cross-attention's context K / V on ONE rank and all-gather them instead of repeating
+        # them on every rank (_shard_context_kv; bit-identical).  No effect on one GPU.
+        self.shard_context_projections = True
         self.scale_shift_table = nn.Parameter(torch.randn(1, 2, inner) / inner ** 0.5)
 
     def forward(self, hidden_states: torch.Tensor, timestep: torch.Tensor, encoder_hidden_states: torch.Tensor,
@@ -584,10 +648,15 @@ class WanTransformer3DMOTModel(nn.Module):
         proj_r = proj_r.unflatten(1, (6, -1))
 
         last_mot = max((i for i, b in enumerate(self.blocks) if b.with_mot_ref), default=-1)
-        for i, block in enumerate(self.blocks):
-            block.__dict__["_vap_ref_output_unused"] = bool(self.skip_dead_reference_work) and i == last_mot
-            x, xr = block(hidden_states=x, encoder_hidden_states=ctx, temb=proj, rotary_emb=rope, hidden_states_mot_ref=xr,
-                          encoder_hidden_states_mot_ref=ctx_r, temb_mot_ref=proj_r, rotary_emb_mot_ref=rope_r, num_mot_ref=num_mot_ref)
+        prefilled = _shard_context_kv(self.blocks, ctx, ctx_r, sp) if (sp is not None and self.shard_context_projections) else []
+        try:
+            for i, block in enumerate(self.blocks):
+                block.__dict__["_vap_ref_output_unused"] = bool(self.skip_dead_reference_work) and i == last_mot
+                x, xr = block(hidden_states=x, encoder_hidden_states=ctx, temb=proj, rotary_emb=rope, hidden_states_mot_ref=xr,
+                              encoder_hidden_states_mot_ref=ctx_r, temb_mot_ref=proj_r, rotary_emb_mot_ref=rope_r, num_mot_ref=num_mot_ref)
+        finally:
+            for m in prefilled:
+                m.__dict__.pop("_vap_ctx_prefill", None)
 
         shift, scale = (self.scale_shift_table + temb.unsqueeze(1)).chunk(2, dim=1)  # :952 (model dtype)
         x = ops.adaln_layernorm(x, eps=cfg["eps"], rounding=ops.ROUND_WAN, scale1p=(1 + scale).float(), shift=shift.float())
