@@ -219,14 +219,24 @@ def check_train_block_level(family: str, cfg: dict, latent):
         got, ms_ours = grads()
     finally:
         vap.uninstall(model)
-    cos = {}
+    # Per-tensor cosine for every tensor that carries a real gradient (norm >= 1 % of the largest one), and the relative error of the whole
+    # gradient.  Tensors below that floor are rounding noise in BOTH runs — e.g. the cross-attention key bias, to which a softmax is invariant
+    # up to the RMSNorm that follows it: its cosine flips sign from run to run — and are only required to stay small.
+    norms = {n: ref[n].double().norm().item() for n in ref}
+    floor = 1e-2 * max(norms.values())
+    cos, small = {}, {}
     for n in ref:
         a, b = ref[n].double().flatten(), got[n].double().flatten()
-        if a.norm() > 0:
+        if norms[n] >= floor:
             cos[n] = (torch.dot(a, b) / (a.norm() * b.norm())).item()
-    res = dict(trainable_tensors=len(ref), same_names=sorted(ref) == sorted(got), worst_cosine=min(cos.values()), worst_name=min(cos, key=cos.get),
+        else:
+            small[n] = b.norm().item()
+    num = sum((got[n].double() - ref[n].double()).pow(2).sum().item() for n in ref) ** 0.5
+    den = sum(ref[n].double().pow(2).sum().item() for n in ref) ** 0.5
+    res = dict(trainable_tensors=len(ref), compared_by_cosine=len(cos), same_names=sorted(ref) == sorted(got), worst_cosine=min(cos.values()),
+               worst_name=min(cos, key=cos.get), whole_gradient_rel_err=num / den, noise_level_tensors_stay_small=all(v < 2 * floor for v in small.values()),
                stock_fwd_bwd_ms=ms_stock, installed_fwd_bwd_ms=ms_ours)
-    assert res["same_names"] and res["worst_cosine"] > 0.99, res
+    assert res["same_names"] and res["worst_cosine"] > 0.99 and res["whole_gradient_rel_err"] < 0.1 and res["noise_level_tensors_stay_small"], res
     return res
 
 

@@ -132,9 +132,10 @@ def _train_worker(family, q, mode="sdpa"):
         res.update({"n_ref": len(ref), "n_got": len(got), "same_names": sorted(ref) == sorted(got)})
         # cosine per parameter (bf16 training noise makes max-abs a poor gate for gradients), worst case over all trainable tensors
         cos = {}
+        floor = 1e-2 * max(g.double().norm().item() for g in ref.values())  # below it a gradient is rounding noise in both runs (e.g. the key biases)
         for n in ref:
             a, b = ref[n].double().flatten(), got[n].double().flatten()
-            if a.norm() > 0:
+            if a.norm() >= floor:
                 cos[n] = (torch.dot(a, b) / (a.norm() * b.norm())).item()
         res["worst_cosine"] = min(cos.values())
         res["worst_name"] = min(cos, key=cos.get)

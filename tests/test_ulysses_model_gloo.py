@@ -1,7 +1,7 @@
 """CPU, gloo, world_size 2 and 4: the N > 1 HOST path of both transformer shells under Ulysses sequence parallelism (token sharding of
 both streams — CogVideoX: of each stream's [text | video] sequence, so ranks end up with different text / video row counts, some
 with none — RoPE table sharding, the two all-to-alls around the joint attention, zero-row guards, the final all-gather, the
-per-sample loop for the B = 2 CFG batch).  The kernels are replaced by torch stand-ins (tests/cpu_standin_ops.py) in these worker
+B = 2 CFG batch of the CogVideoX pipeline and of wan_denoise(batch_cfg=True) through the sharded path).  The kernels are replaced by torch stand-ins (tests/cpu_standin_ops.py) in these worker
 processes only; the assertion is that the N-rank forward equals the 1-rank forward of the same model.  A single-process case pins
 the stand-ins + host logic to the reference's golden fixtures first."""
 import importlib
@@ -69,7 +69,15 @@ def _worker(rank, world, port, family, ret):
                 vap.wan.clear_context_cache(model)
                 assert torch.equal(c1, out) and torch.equal(c2, out)
             vap.ulysses.disable()
-        ret[rank] = ((out - ref).abs().max() / ref.abs().max()).item()
+            err = ((out - ref).abs().max() / ref.abs().max()).item()
+            if family == "wan":  # a B = 2 batch ([conditional | unconditional] of wan_denoise(batch_cfg=True)) through the sharded forward
+                inp2 = vap.synth.wan_inputs(cfg, 2, 8, 4 * world, seed=3, batch=2)
+                ref2 = model(**inp2, return_dict=False)[0].float()
+                vap.ulysses.enable(mode="nccl")
+                out2 = model(**inp2, return_dict=False)[0].float()
+                vap.ulysses.disable()
+                err = max(err, ((out2 - ref2).abs().max() / ref2.abs().max()).item())
+        ret[rank] = err
     finally:
         dist.destroy_process_group()
 

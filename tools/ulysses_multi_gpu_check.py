@@ -38,6 +38,14 @@ with torch.no_grad():
         vap.ulysses.disable()
         err = max(((o - ref).abs().max() / ref.abs().max()).item() for o in outs)
         res[mode] = err
+    if a.family == "wan":  # a B = 2 batch (wan_denoise(batch_cfg=True)): one exchange and one attention launch for both samples in "p2p" mode
+        inp2 = vap.synth.wan_inputs(cfg, a.frames, 16, 8 * world, seed=3, device=dev, batch=2)
+        ref2 = model(**inp2, return_dict=False)[0].float()
+        for mode in ("p2p", "nccl"):
+            vap.ulysses.enable(mode=mode)
+            outs = [model(**inp2, return_dict=False)[0].float() for _ in range(2)]
+            vap.ulysses.disable()
+            res[mode + "_batch2"] = max(((o - ref2).abs().max() / ref2.abs().max()).item() for o in outs)
 ok = all(e < 2e-2 for e in res.values())
 t = torch.tensor([0 if ok else 1], device=dev); dist.all_reduce(t)
 if rank == 0:

@@ -67,7 +67,7 @@ def _qkv(attn: nn.Module, h: torch.Tensor, T: int, tables: Optional[Tables], out
                      cos=tables[0] if tables else None, sin=tables[1] if tables else None, rows_per_batch=h.shape[0], rope_row0=T,
                      eps=attn.norm_q.eps, mode=ops.QK_COG)
     if scatter is not None:
-        scatter[0].dispatch(out, scatter[1], **norm_rope)
+        scatter[0].dispatch(out, scatter[1], batch_index=scatter[2] if len(scatter) > 2 else 0, **norm_rope)
     else:
         ops.qk_norm_rope_(out[:, :inner], out[:, inner:2 * inner], heads=heads, head_dim=inner // heads, **norm_rope)
 
@@ -129,7 +129,7 @@ def cog_block_forward(self: nn.Module, hidden_states: torch.Tensor, encoder_hidd
     # shards them: rank 0 holds the text rows, st.T may be 0 elsewhere); the joint attention then does the two exchanges.
     J = sum(st.T + st.S for st in streams)
     qkv = torch.empty((B, J, 3 * inner), dtype=torch.bfloat16, device=dev)
-    px = _sp_p2p(hidden_states, J, heads, hd)  # PeerExchange in peer-memory mode (B == 1), else None
+    px = _sp_p2p(hidden_states, J, heads, hd)  # PeerExchange (for the whole batch) in peer-memory mode, else None
     row0 = [0, streams[0].T + streams[0].S]    # first joint row of each stream
     # the expert's stream is issued on a side CUDA stream between the joint attentions (streams.py); None: CPU tensors / plain block / switched off
     ds = stream_pair.dual(dev, max(st.T + st.S for st in streams)) if len(streams) > 1 else None
@@ -144,7 +144,7 @@ def cog_block_forward(self: nn.Module, hidden_states: torch.Tensor, encoder_hidd
                 _ln_zero(st.norm1, st.e[b], m, True, st.se, h[:st.T])
             if st.S:
                 _ln_zero(st.norm1, st.v[b], m, False, st.sv, h[st.T:])
-            _qkv(st.attn, h, st.T, st.tables, qkv[b, row0[si]:row0[si] + L], scatter=(px, row0[si]) if px is not None else None)
+            _qkv(st.attn, h, st.T, st.tables, qkv[b, row0[si]:row0[si] + L], scatter=(px, row0[si], b) if px is not None else None)
 
     if ds is not None:
         ds.fork()
@@ -157,7 +157,7 @@ def cog_block_forward(self: nn.Module, hidden_states: torch.Tensor, encoder_hidd
 
     # ---- joint attention ---------------------------------------------------------------------------------------
     if px is not None:
-        o = px.attention().unsqueeze(0)     # exchanges fused into the kernels over NVLink peer memory
+        o = px.attention()                  # [B, J, inner]: exchanges fused into the kernels over NVLink peer memory
     else:
         o = _joint_attention(qkv, heads)    # [B, J, inner]; NCCL all-to-alls around the kernel when Ulysses runs in "nccl" mode
 
@@ -388,19 +388,6 @@ class CogVideoXTransformer3DMOTModel(nn.Module):
         assert hidden_states_mot_ref.shape[1] // Fr == num_mot_ref, f"hidden_states_mot_ref.shape[1]: {hidden_states_mot_ref.shape}"
 
         sp = ulysses.current()
-        if sp is not None and B > 1:
-            # classifier-free guidance hands the shell one B = 2 batch (pipeline_cogvideox_image2video_mot.py:972-1001); the exchange
-            # buffers are per sequence, so under sequence parallelism the batch elements run one after the other
-            outs = []
-            for b in range(B):
-                pick = lambda t: t[b:b + 1] if torch.is_tensor(t) and t.dim() > 0 and t.shape[0] == B else t  # noqa: E731
-                outs.append(self.forward(pick(hidden_states), pick(encoder_hidden_states), pick(timestep), timestep_cond, ofs, image_rotary_emb,
-                                         attention_kwargs, False, num_mot_ref, pick(hidden_states_mot_ref), pick(encoder_hidden_states_mot_ref),
-                                         image_rotary_emb_mot_ref, effect_types, reference_train_mode,
-                                         None if timestep_list_mot_ref is None else [pick(t) for t in timestep_list_mot_ref])[0])
-            out = torch.cat(outs, dim=0)
-            return (out,) if not return_dict else _Output(sample=out)
-
         h = self.patch_embed(encoder_hidden_states, hidden_states)
         vs, es = [], []
         for i in range(num_mot_ref):

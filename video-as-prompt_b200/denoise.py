@@ -54,9 +54,6 @@ def wan_denoise(model, latents: torch.Tensor, condition: torch.Tensor, latents_r
     from . import wan
     x_ref = torch.cat([latents_ref, condition_ref], dim=1).to(dtype)
     ts_ref = torch.ones((1, latents.shape[0]), dtype=torch.float32, device=dev)  # reference video is clean: timestep 1 (:812-813)
-    from . import ulysses
-    if ulysses.current() is not None:
-        batch_cfg = False  # the Ulysses exchange buffers are per sequence (one B = 1 forward per guidance pass, as in the Wan pipeline)
     if batch_cfg and uncond_kwargs is not None:
         # the B = 2 conditioning is concatenated ONCE, so the context cache sees the same tensors at every step
         cond_kwargs = {k: (torch.cat([v, uncond_kwargs[k]], dim=0) if torch.is_tensor(v) else v) for k, v in cond_kwargs.items()}

@@ -133,29 +133,32 @@ def exchange_out(o: torch.Tensor, sp: SequenceParallel, unpack: Callable = _unpa
 class PeerExchange:
     """Symmetric (peer-mapped) buffers of one joint-attention shape, shared by all MoT blocks.
 
-      recv[f] [P, rows, 3, (H/P)*D]   slot s = what rank s dispatched to this rank (its local rows of both streams, q|k|v of this
-                                      rank's heads); rows = local joint rows.  Viewed as [1, P*rows, 3, H/P, D] it is the
-                                      rank-major joint sequence the attention kernel reads through strided TMA descriptors.
-      out[f]  [rows, H*D]             this rank's rows of O for ALL heads; rank r's attention kernel fills columns
-                                      [r*(H/P)*D, (r+1)*(H/P)*D).
+      recv[f] [B, P, rows, 3, (H/P)*D]  slot s = what rank s dispatched to this rank (its local rows of both streams, q|k|v of this
+                                        rank's heads); rows = local joint rows.  Viewed as [B, P*rows, 3, H/P, D] it is the
+                                        rank-major joint sequence the attention kernel reads through strided TMA descriptors.
+      out[f]  [B, rows, H*D]            this rank's rows of O for ALL heads; rank r's attention kernel fills columns
+                                        [r*(H/P)*D, (r+1)*(H/P)*D).
+    B = the batch of the forward (1 per guidance pass in the Wan pipeline, 2 = [conditional | unconditional] in the CogVideoX pipeline,
+    pipeline_cogvideox_image2video_mot.py:972-1001): one exchange and ONE attention launch serve the whole batch.
 
     f alternates per block.  Why two sets suffice: block b writes set b%2 on the peers; a peer's last read of that set (block b-2's
     attention for recv, block b-2's output projections for out) is stream-ordered before the barrier that peer entered in
     block b-1, which this rank has passed before it launches block b's kernels."""
 
-    def __init__(self, sp: SequenceParallel, rows: int, heads: int, head_dim: int, device: torch.device):
+    def __init__(self, sp: SequenceParallel, rows: int, heads: int, head_dim: int, device: torch.device, batch: int = 1):
         import torch.distributed._symmetric_memory as symm
         P = sp.world
-        self.sp, self.rows, self.heads, self.head_dim = sp, rows, heads, head_dim
+        self.sp, self.rows, self.heads, self.head_dim, self.batch = sp, rows, heads, head_dim, batch
         self.hp = heads // P * head_dim
+        self.recv_batch_bytes = P * rows * 3 * self.hp * 2  # one batch element of a receive buffer
         group = sp.group if sp.group is not None else dist.group.WORLD
         self.recv, self.out, self.recv_ptrs, self.out_ptrs = [], [], [], []
         self._handles = []
         for _ in range(2):
-            r = symm.empty((P, rows, 3, self.hp), dtype=torch.bfloat16, device=device)
+            r = symm.empty((batch, P, rows, 3, self.hp), dtype=torch.bfloat16, device=device)
             h = symm.rendezvous(r, group)
             self.recv.append(r), self.recv_ptrs.append([int(p) for p in h.buffer_ptrs]), self._handles.append(h)
-            o = symm.empty((rows, heads * head_dim), dtype=torch.bfloat16, device=device)
+            o = symm.empty((batch, rows, heads * head_dim), dtype=torch.bfloat16, device=device)
             h = symm.rendezvous(o, group)
             # every rank writes its own head columns of the owner's rows
             self.out.append(o), self.out_ptrs.append([int(p) + sp.rank * self.hp * 2 for p in h.buffer_ptrs]), self._handles.append(h)
@@ -167,28 +170,32 @@ class PeerExchange:
     def barrier(self) -> None:
         self._handles[0].barrier(channel=0)  # stream-ordered: signals every peer and waits for every peer
 
-    def dispatch(self, qkv: torch.Tensor, row0: int, **norm_rope) -> None:
-        """Exchange #1 for one stream: qkv [L, 3*H*D] = this rank's rows of the stream's QKV projection (pre-norm)."""
+    def dispatch(self, qkv: torch.Tensor, row0: int, batch_index: int = 0, **norm_rope) -> None:
+        """Exchange #1 for one stream of one batch element: qkv [L, 3*H*D] = this rank's rows of the stream's QKV projection (pre-norm)."""
         inner = qkv.shape[-1] // 3
+        if not 0 <= batch_index < self.batch:
+            raise IndexError(f"batch element {batch_index} of a PeerExchange made for batch {self.batch}")
+        ptrs = self.recv_ptrs[self.flip] if batch_index == 0 else [p + batch_index * self.recv_batch_bytes for p in self.recv_ptrs[self.flip]]
         ops.qkv_scatter(qkv[:, :inner], qkv[:, inner:2 * inner], qkv[:, 2 * inner:], heads=self.heads, head_dim=self.head_dim,
-                        dst_ptrs=self.recv_ptrs[self.flip], dst_slot=self.sp.rank, slot_rows=self.rows, dst_row0=row0, **norm_rope)
+                        dst_ptrs=ptrs, dst_slot=self.sp.rank, slot_rows=self.rows, dst_row0=row0, **norm_rope)
 
     def attention(self) -> torch.Tensor:
         """barrier -> joint attention of this rank's heads over the full sequence, O rows stored to their owners -> barrier.
-        Returns this rank's rows of O for all heads, [rows, H*D]."""
+        Returns this rank's rows of O for all heads, [B, rows, H*D]."""
         P, hp, D = self.sp.world, self.hp, self.head_dim
         self.barrier()
-        joint = self.recv[self.flip].view(1, P * self.rows, 3, self.heads // P, D)
+        joint = self.recv[self.flip].view(self.batch, P * self.rows, 3, self.heads // P, D)
         q, k, v = (joint[:, :, w].transpose(1, 2) for w in range(3))
-        ops.attention_scatter(q, k, v, o_ptrs=self.out_ptrs[self.flip], rows_per_peer=self.rows, o_strides=(0, D, self.heads * D))
+        ops.attention_scatter(q, k, v, o_ptrs=self.out_ptrs[self.flip], rows_per_peer=self.rows,
+                              o_strides=(self.rows * self.heads * D, D, self.heads * D))
         self.barrier()
         return self.out[self.flip]
 
 
-def peer_exchange(sp: SequenceParallel, rows: int, heads: int, head_dim: int, device: torch.device) -> PeerExchange:
+def peer_exchange(sp: SequenceParallel, rows: int, heads: int, head_dim: int, device: torch.device, batch: int = 1) -> PeerExchange:
     """The (cached) PeerExchange of this shape.  Creating one is collective: every rank must get here in the same order."""
-    key = (rows, heads, head_dim)
+    key = (rows, heads, head_dim, batch)
     if key not in sp._exchanges:
         check_divisible(rows * sp.world, heads, sp.world)
-        sp._exchanges[key] = PeerExchange(sp, rows, heads, head_dim, device)
+        sp._exchanges[key] = PeerExchange(sp, rows, heads, head_dim, device, batch)
     return sp._exchanges[key]

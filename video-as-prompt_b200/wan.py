@@ -199,7 +199,7 @@ def _self_attn_qkv(attn: nn.Module, x: torch.Tensor, tables: Optional[Tables], o
     for b in range(B):  # rows of one batch are uniformly strided inside the joint buffer
         ops.linear(x[b], W, bvec, out=out[b])
         if scatter is not None:
-            scatter[0].dispatch(out[b], scatter[1], **norm_rope)
+            scatter[0].dispatch(out[b], scatter[1], batch_index=b, **norm_rope)
         else:
             ops.qk_norm_rope_(out[b, :, :inner], out[b, :, inner:2 * inner], heads=heads, head_dim=inner // heads, **norm_rope)
     return out
@@ -323,11 +323,12 @@ def _joint_attention(qkv: torch.Tensor, heads: int) -> torch.Tensor:
     if sp is None:
         q, k, v = _split_qkv(qkv, heads)
         return _token_major(ops.attention(q, k, v))
-    if qkv.shape[0] != 1:
-        raise NotImplementedError("Ulysses sequence parallelism expects batch 1 per forward (the Wan pipeline's CFG passes are B=1)")
-    q, k, v = ulysses.exchange_qkv(qkv[0], heads, sp)
-    o = _token_major(ops.attention(q, k, v))[0]  # [P*L_loc, (H/P)*D]
-    return ulysses.exchange_out(o, sp).unsqueeze(0)
+    outs = []
+    for b in range(qkv.shape[0]):  # the collective transport exchanges one sequence at a time (the baseline; "p2p" serves the batch in one launch)
+        q, k, v = ulysses.exchange_qkv(qkv[b], heads, sp)
+        o = _token_major(ops.attention(q, k, v))[0]  # [P*L_loc, (H/P)*D]
+        outs.append(ulysses.exchange_out(o, sp))
+    return outs[0].unsqueeze(0) if len(outs) == 1 else torch.stack(outs, dim=0)
 
 
 def _sp_p2p(x: torch.Tensor, rows: int, heads: int, head_dim: int):
@@ -335,9 +336,7 @@ def _sp_p2p(x: torch.Tensor, rows: int, heads: int, head_dim: int):
     sp = ulysses.current()
     if sp is None or sp.mode != "p2p":
         return None
-    if x.shape[0] != 1:
-        raise NotImplementedError("Ulysses sequence parallelism expects batch 1 per forward (the Wan pipeline's CFG passes are B=1)")
-    px = ulysses.peer_exchange(sp, rows, heads, head_dim, x.device)
+    px = ulysses.peer_exchange(sp, rows, heads, head_dim, x.device, batch=x.shape[0])
     px.next_block()
     return px
 
@@ -388,7 +387,7 @@ def wan_block_forward(self: nn.Module, hidden_states: torch.Tensor, encoder_hidd
         px = _sp_p2p(x, x.shape[1], heads, hd)
         if px is not None:
             _self_attn_qkv(attn1, xn, tables, scatter=(px, 0))
-            o = px.attention().unsqueeze(0)
+            o = px.attention()
         else:
             o = _joint_attention(_self_attn_qkv(attn1, xn, tables), heads)
         x = _linear(attn1.to_out[0], o, epilogue=ops.EPI_GATE_RES_F32, residual=x, gate=gate)
@@ -421,7 +420,7 @@ def wan_block_forward(self: nn.Module, hidden_states: torch.Tensor, encoder_hidd
     if ds is not None:
         ds.join()
     if px is not None:
-        o = px.attention().unsqueeze(0)
+        o = px.attention()
     else:
         if self.__dict__.get("_vap_ref_output_unused", False) and ulysses.current() is None:
             # Last MoT block of a shell whose output head reads the target stream only (:951-987): the expert stream's output is dead,
