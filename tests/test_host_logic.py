@@ -352,3 +352,12 @@ def test_dual_stream_schedule_is_off_for_cpu_tensors_and_automatic_by_row_count(
     with vap.dual_streams(False):
         assert st.dual(torch.device("cuda", 0), 100) is None
     assert created == [torch.device("cuda", 0)]  # one DualStream per device, cached
+
+
+def test_rows_view_accepts_an_empty_batched_tensor():
+    """A sequence-parallel CogVideoX rank may hold text rows only: its video tensor is [B, 0, d] (B = 2 under CFG), whose batch stride cannot
+    'continue the row pitch' — there is nothing to address, the wrappers must see 0 rows instead of raising."""
+    t = torch.empty((2, 280, 512), dtype=torch.bfloat16)[:, 140:140]
+    assert vap.ops._rows_view(t, "x")[0] == 0
+    with pytest.raises(ValueError):  # a non-empty slice whose batch stride breaks the row pitch is still refused
+        vap.ops._rows_view(torch.empty((2, 3, 512))[:, 1:3], "x")

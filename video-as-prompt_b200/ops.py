@@ -73,6 +73,8 @@ def _rows_view(t: torch.Tensor, name: str) -> Tuple[int, int, int]:
     d = t.shape[-1]
     if t.dim() == 1:
         return 1, d, d
+    if t.numel() == 0:  # no rows (a sequence-parallel rank holding text rows only): nothing to address, any pitch will do
+        return 0, d, max(d, 1)
     rs = t.stride(-2)
     rows = t.shape[-2]
     for i in range(t.dim() - 3, -1, -1):  # leading dims must continue the same row pitch
