@@ -1,17 +1,16 @@
 """CUDA-graph replay of a transformer forward (fixed shapes): the whole step — every kernel of the 40 blocks, the Ulysses peer
 barriers, the final all-gather — is captured once and replayed with one launch call.
 
-Why: at 8 GPUs a Wan-14B 480p step is ~3 900 kernel launches of ~70 us each; the Python / ctypes launch path (~50 us per launch)
-is then slower than the GPU and the step is CPU-bound (measured: faster kernels did not move the 8-GPU step time).  The reference
-has no counterpart (eager PyTorch); SURVEY.md §8(f) rank 2 lists graph capture of the step as the next shell-level item.
+Why: at 8 GPUs a Wan-14B 480p step is ~5 400 kernel launches of ~50 us each; round 1 suspected the Python / ctypes launch path of being the
+bound there.  The reference has no counterpart (eager PyTorch); SURVEY.md §8(f) rank 2 lists graph capture of the step as a shell-level item.
 
     graphed = GraphedForward(model, example_kwargs)      # 2 eager warm-up forwards on a side stream, then capture
     out = graphed(**kwargs)[0]                           # copies tensor inputs into the captured buffers, replays
 
-Status (round 1): single GPU: parity of replay vs eager, no speed-up (the step is GPU-bound: 2100 vs 2092 ms).  2 GPUs: capture and
-replay work with the peer-memory Ulysses exchange and the final all-gather inside the graph (1069 vs 1072 ms), but the processes
-did not exit cleanly afterwards (torchrun had to kill them) — so `bench.py --graph on` is opt-in and the 8-GPU case, where the
-launch path is the bound, is not measured yet.
+Status (round 2, B200s): capture (including the fork / join of the blocks' side stream, streams.py, the peer-memory exchange, the all-gather of the
+sharded context projections and the final all-gather), replay and process exit are clean at 1, 2 and 8 GPUs.  The gain is what the launch path
+costs: none on one GPU (GPU-bound), 1014.2 -> 1012.9 ms at 2 GPUs, 268.5 -> 266.0 ms at 8 (profiles/r02_bench_n8_v2.json) — the 8-GPU step is
+GPU-bound too, so replay stays opt-in (`bench.py --graph on`).
 """
 from __future__ import annotations
 
