@@ -288,6 +288,26 @@ def check_attention_variants():
     return res
 
 
+def check_attention_short_and_long():
+    """The short-KV kernel (one Q tile per CTA, two CTAs per SM; chosen by itself up to 8 KV tiles) and the two-tile ping-pong kernel, each FORCED
+    on the shapes the other one gets by default (VAP_ATTN_SHORT is read per call): cross-attention shapes through the long kernel, multi-tile /
+    peaky / accumulate / split-KV / peer-store / D = 64 shapes through the short one."""
+    res = {}
+    on, off = {"VAP_ATTN_SHORT": "1"}, {"VAP_ATTN_SHORT": "0"}
+    res["long_cross_257"] = _with_env(off, check_attention, B=1, H=2, Lq=600, Lkv=257, D=128, joint_layout=False)["err"]
+    res["long_cross_512"] = _with_env(off, check_attention, B=1, H=2, Lq=300, Lkv=512, D=128, joint_layout=False)["err"]
+    res["long_one_tile"] = _with_env(off, check_attention, B=1, H=1, Lq=64, Lkv=100, D=128, joint_layout=False)["err"]
+    res["long_accumulate"] = _with_env(off, check_attention_accumulate)["err"]
+    res["short_multi_tile"] = _with_env(on, check_attention, B=1, H=3, Lq=1000, Lkv=1000, D=128)["err"]
+    res["short_17_tiles"] = _with_env(on, check_attention, B=1, H=2, Lq=300, Lkv=2100, D=128, joint_layout=False)["err"]
+    res["short_d64"] = _with_env(on, check_attention, B=2, H=4, Lq=452, Lkv=900, D=64, joint_layout=False)["err"]
+    res["short_peaky"] = _with_env(on, check_attention_peaky)["err"]
+    res["short_accumulate_d64"] = _with_env(on, check_attention_accumulate, D=64, H=2, Lq=300, kv=(100, 226))["err"]
+    res["short_splitkv"] = _with_env(on, check_attention_splitkv, B=1, H=2, Lq=300, Lkv=1000, D=128, splits=2)["err"]
+    res["short_p2p_emulated"] = _with_env(on, check_ulysses_p2p_emulated, P=4, L=96, H=8, D=128, mode=0)["err"]
+    return res
+
+
 def check_attention_peaky(D=128):
     """Scores with a large dynamic range (exercises the lazy O-rescale path: the running max keeps growing by > 2^8)."""
     H, L = 2, 1024
@@ -804,6 +824,7 @@ CHECKS = {
     "attn_one_tile": lambda: check_attention(1, 1, 64, 100, 128, joint_layout=False),
     "attn_peaky": lambda: check_attention_peaky(),
     "attn_variants_row_pair": check_attention_variants,
+    "attn_short_and_long_forced": check_attention_short_and_long,
     "attn_accumulate": lambda: check_attention_accumulate(),
     "attn_accumulate_d64": lambda: check_attention_accumulate(D=64, H=2, Lq=300, kv=(100, 226)),
     "attn_splitkv_2": lambda: check_attention_splitkv(1, 2, 300, 1000, 128, 2),

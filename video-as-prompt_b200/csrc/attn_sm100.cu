@@ -75,16 +75,19 @@ constexpr float kSumTrigger = 256.0f;  // 2^kRescaleThreshold
 #define VAP_ATTN_TRACE 0  // 1: clock64() stamps of CTA (0,0,0) when a trace buffer is installed (tools/attn_trace.py)
 #endif
 
-template <int D>
+// T = Q tiles per CTA: 2 (the ping-pong kernels: 256 query rows, all 512 TMEM columns, one CTA per SM) or 1 (the short-KV kernel: 128 query rows,
+// 256 TMEM columns, a two-slot K / V ring, so that TWO CTAs share an SM).
+template <int D, int T = 2>
 struct AttnCfg {
+    static constexpr int kQTiles = T;
     static constexpr int kTileBytes = 128 * D * 2;   // one Q / K / V tile
     static constexpr int kHalfBytes = 128 * 64 * 2;  // one 64-column (128-byte) swizzle slab
     static constexpr int kHalves = D / 64;
-    static constexpr int kKvStages = (D == 128) ? 5 : 8;
+    static constexpr int kKvStages = (T == 2) ? ((D == 128) ? 5 : 8) : ((D == 128) ? 2 : 4);
     static constexpr int kBarBytes = 512;
-    static constexpr int kSmemBytes = 2 * kTileBytes + kKvStages * kTileBytes + kBarBytes + 1024;
-    static constexpr int kTmemCols = 512;
-    static constexpr int kColS0 = 0, kColS1 = 128, kColO0 = 256, kColO1 = 256 + D;
+    static constexpr int kSmemBytes = T * kTileBytes + kKvStages * kTileBytes + kBarBytes + 1024;
+    static constexpr int kTmemCols = (T == 2) ? 512 : 256;
+    static constexpr int kColS0 = 0, kColS1 = 128, kColO0 = (T == 2) ? 256 : 128, kColO1 = 256 + D;
 };
 
 // bf16(float(a) + float(b)) per element of a packed pair: what a bf16 tensor add computes
@@ -94,12 +97,12 @@ __device__ __forceinline__ uint32_t add_bf16x2_as_tensors(uint32_t a, uint32_t b
 }
 
 // Shared-memory map of one CTA: Q tiles | K/V ring | mbarriers.
-template <int D>
+template <int D, int T = 2>
 struct AttnSmem {
-    using Cfg = AttnCfg<D>;
+    using Cfg = AttnCfg<D, T>;
     uint32_t q_smem, kv_smem, bar_base;
     __device__ __forceinline__ explicit AttnSmem(uint32_t smem_base)
-        : q_smem(smem_base), kv_smem(smem_base + 2 * Cfg::kTileBytes), bar_base(smem_base + 2 * Cfg::kTileBytes + Cfg::kKvStages * Cfg::kTileBytes) {}
+        : q_smem(smem_base), kv_smem(smem_base + T * Cfg::kTileBytes), bar_base(smem_base + T * Cfg::kTileBytes + Cfg::kKvStages * Cfg::kTileBytes) {}
     __device__ __forceinline__ uint32_t kv_full(int s) const { return bar_base + 8u * s; }
     __device__ __forceinline__ uint32_t kv_empty(int s) const { return bar_base + 8u * (Cfg::kKvStages + s); }
     __device__ __forceinline__ uint32_t q_full() const { return bar_base + 8u * (2 * Cfg::kKvStages); }
@@ -136,13 +139,13 @@ struct AttnSmem {
 // CL = 2: clusters of two CTAs (adjacent 256-row query blocks of the same head) share every K / V tile: each CTA fetches half of
 // the tile's rows and TMA multicasts them into both CTAs' shared memory, so K / V cross the L2 -> SM fabric once per 512 query
 // rows; a ring slot is reusable when BOTH CTAs' MMAs have read it (multicast tcgen05.commit on the empty barriers).
-template <int D, int CL>
-__device__ __forceinline__ void attn_producer_warp(const AttnSmem<D>& sm, const CUtensorMap* tmQ, const CUtensorMap* tmK, const CUtensorMap* tmV, int q0, int head,
+template <int D, int CL, int T = 2>
+__device__ __forceinline__ void attn_producer_warp(const AttnSmem<D, T>& sm, const CUtensorMap* tmQ, const CUtensorMap* tmK, const CUtensorMap* tmV, int q0, int head,
                                                    int batch, int j0, int n_kv, int cta_rank) {
-    using Cfg = AttnCfg<D>;
+    using Cfg = AttnCfg<D, T>;
     if (elect_one()) {
-        mbar_arrive_expect_tx(sm.q_full(), 2 * Cfg::kTileBytes);
-        for (int t = 0; t < 2; ++t)
+        mbar_arrive_expect_tx(sm.q_full(), T * Cfg::kTileBytes);
+        for (int t = 0; t < T; ++t)
             for (int h = 0; h < Cfg::kHalves; ++h)
                 tma_load_4d(sm.q_smem + t * Cfg::kTileBytes + h * Cfg::kHalfBytes, tmQ, sm.q_full(), h * 64, q0 + t * kBlockM, head, batch);
     }
@@ -353,8 +356,8 @@ __device__ __forceinline__ void attn_mma_warp(const AttnSmem<D>& sm, uint32_t tm
 struct AttnWork {
     int q0, head, batch, j0, n_kv;
     unsigned split;
-    __device__ __forceinline__ explicit AttnWork(const AttnParams& p) {
-        q0 = blockIdx.x * (2 * kBlockM);
+    __device__ __forceinline__ explicit AttnWork(const AttnParams& p, int q_tiles = 2) {
+        q0 = blockIdx.x * (q_tiles * kBlockM);
         head = blockIdx.y;
         batch = static_cast<int>(blockIdx.z) / p.kv_splits;
         split = blockIdx.z - static_cast<unsigned>(batch * p.kv_splits);
@@ -368,8 +371,8 @@ struct AttnWork {
 // (kRemoteP: P is published on the LEADER CTA's barriers, where the pair's only MMA issuer waits).
 template <int D, bool kRemoteP, typename Smem>
 __device__ __forceinline__ void attn_softmax_lane16(const Smem& sm, const AttnParams& p, const AttnWork& wk, uint32_t tmem_base, int warp, int lane) {
-    using Cfg = AttnCfg<D>;
-    constexpr bool kP3 = (VAP_ATTN_P3 != 0) && !kRemoteP;  // three-stage publish of P (the CTA-pair kernel keeps two)
+    using Cfg = typename Smem::Cfg;  // TMEM column map of the kernel this runs in (two Q tiles, or one in the short-KV kernel)
+    constexpr bool kP3 = (VAP_ATTN_P3 != 0) && !kRemoteP && Cfg::kQTiles == 2;  // three-stage publish of P (the CTA-pair and short-KV kernels keep two)
     static_assert(VAP_ATTN_P3_PAIRS == 8 || VAP_ATTN_P3_PAIRS == 12, "VAP_ATTN_P3_PAIRS");
     constexpr int kPolyPairs = (D == 128) ? VAP_ATTN_POLY_PAIRS_D128 : VAP_ATTN_POLY_PAIRS_D64;
     const int q0 = wk.q0, head = wk.head, batch = wk.batch, j0 = wk.j0, n_kv = wk.n_kv;
@@ -680,6 +683,137 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
 
 // ------------------------------------------------------------------------------------------------------------------------
+// SHORT-KV kernel: ONE 128-row Q tile per CTA, TWO CTAs per SM.
+// The Wan cross-attention (Lkv = 512 text / 257 image tokens, transformer_wan_mot.py:163-179) gives a CTA 3-4 KV tiles of work: with one CTA
+// per SM its prologue (TMEM allocation, barrier init, Q + first K load) and its epilogue (O -> global) are fully exposed — the ncu launch list
+// shows 324 / 367 us per launch at 20 280 query rows, ~460 TFLOP/s, 2.8 % of a denoise step for 1.1 % of its FLOPs.  Here a CTA owns 128 query
+// rows, half of the TMEM (S | O = 256 columns), a Q tile and a TWO-slot K / V ring (96 KB of shared memory at D = 128), ten warps (producer,
+// MMA issuer, the eight softmax warps of the 16-lane organisation above — same code), so two CTAs are resident per SM and one's prologue /
+// epilogue / load bubbles overlap the other's tile steps.  Ring protocol with two slots: K_j and V_j alternate between them; the issuer waits
+// for V_j before the PV MMAs and for K_{j+1} only right before QK^T(j+1), releases V_j's slot behind QK^T(j+1) and K_{j+1}'s slot behind it too
+// (the commit covers every earlier MMA), so the producer refills a slot while the softmax of the next step runs.
+// ------------------------------------------------------------------------------------------------------------------------
+constexpr int kShortThreads = (kFirstSoftmaxWarp + kSoftmaxWarps / 2) * 32;  // 10 warps
+
+template <int D>
+__device__ __forceinline__ void attn_mma_warp_short(const AttnSmem<D, 1>& sm, uint32_t tmem_base, int n_kv) {
+    using Cfg = AttnCfg<D, 1>;
+    constexpr uint32_t idesc_qk = make_idesc_bf16(kBlockM, kBlockN, 0, 0);
+    constexpr uint32_t idesc_pv = make_idesc_bf16(kBlockM, D, 0, 1);
+    const uint32_t col_s = tmem_base + Cfg::kColS0, col_o = tmem_base + Cfg::kColO0;
+    const uint32_t q_addr = sm.q_smem, kv_smem = sm.kv_smem;
+    auto issue_qk = [&](uint32_t k_addr) {
+        if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < D / 16; ++k) {
+                const uint32_t off = (k >> 2) * Cfg::kHalfBytes + (k & 3) * 32;
+                umma_ss(col_s, make_smem_desc(q_addr + off, 0, 1024, kLayoutSw128), make_smem_desc(k_addr + off, 0, 1024, kLayoutSw128), idesc_qk, k != 0 ? 1u : 0u);
+            }
+        }
+        __syncwarp();
+    };
+    auto issue_pv_half = [&](int c, uint32_t v_addr, uint32_t accumulate) {
+        if (elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < kBlockN / 32; ++kk) {
+                const int k = 4 * c + kk;
+                umma_ts(col_o, col_s + 8 * k, make_smem_desc(v_addr + k * 2048, Cfg::kHalfBytes, 1024, kLayoutSw128), idesc_pv, k != 0 ? 1u : accumulate);
+            }
+        }
+        __syncwarp();
+    };
+    auto commit = [&](uint32_t bar) {
+        if (elect_one()) umma_commit(bar);
+        __syncwarp();
+    };
+    int stage = 0;
+    uint32_t phase = 0;
+    auto advance = [&]() {
+        if (++stage == Cfg::kKvStages) {
+            stage = 0;
+            phase ^= 1;
+        }
+    };
+    mbar_wait(sm.q_full(), 0);
+    mbar_wait(sm.kv_full(stage), phase);  // K_0
+    tc_fence_after();
+    issue_qk(kv_smem + stage * Cfg::kTileBytes);
+    commit(sm.s_full(0));
+    commit(sm.kv_empty(stage));
+    advance();
+    for (int j = 0; j < n_kv; ++j) {
+        const uint32_t par = j & 1;
+        const bool has_next = (j + 1 < n_kv);
+        const int v_stage = stage;
+        mbar_wait(sm.kv_full(stage), phase);  // V_j
+        advance();
+        mbar_wait(sm.p_full(0, 0), par);
+        tc_fence_after();
+        issue_pv_half(0, kv_smem + v_stage * Cfg::kTileBytes, j > 0 ? 1u : 0u);
+        commit(sm.pv_half(0));
+        mbar_wait(sm.p_full(0, 1), par);
+        tc_fence_after();
+        issue_pv_half(1, kv_smem + v_stage * Cfg::kTileBytes, 1u);
+        if (has_next) {
+            const int k_stage = stage;
+            mbar_wait(sm.kv_full(stage), phase);  // K_{j+1}: its slot was released behind QK^T(j), it has had a whole softmax pass to arrive
+            advance();
+            tc_fence_after();
+            issue_qk(kv_smem + k_stage * Cfg::kTileBytes);
+            commit(sm.s_full(0));  // also covers PV(j): O is quiescent when the softmax sees S(j+1)
+            commit(sm.kv_empty(v_stage));
+            commit(sm.kv_empty(k_stage));
+        } else {
+            commit(sm.o_done(0));
+            commit(sm.kv_empty(v_stage));
+        }
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(kShortThreads, 2)
+attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+    using Cfg = AttnCfg<D, 1>;
+    extern __shared__ uint8_t smem_raw[];
+    const AttnSmem<D, 1> sm((smem_u32(smem_raw) + 1023u) & ~1023u);
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const AttnWork wk(p, 1);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmK);
+        tma_prefetch_desc(&tmV);
+    }
+    if (warp == 1 && lane == 0) sm.init_barriers(1, kSoftmaxWarps / 2);
+    if (warp == 0) {
+        tmem_alloc(sm.tmem_ptr_addr(), Cfg::kTmemCols);  // half of the SM's TMEM: the co-resident CTA allocates the other half
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(sm.tmem_ptr_addr()));
+
+    if (warp == 0) {
+        attn_producer_warp<D, 1, 1>(sm, &tmQ, &tmK, &tmV, wk.q0, wk.head, wk.batch, wk.j0, wk.n_kv, 0);
+    } else if (warp == 1) {
+        attn_mma_warp_short<D>(sm, tmem_base, wk.n_kv);
+    } else {
+        attn_softmax_lane16<D, false>(sm, p, wk, tmem_base, warp, lane);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------------
 // "row" organisation of the softmax: ONE THREAD PER QUERY ROW, four warps per Q tile, 12 warps per CTA.
 //   warp 0: TMEM allocator + TMA producer, warp 1: MMA issuer (both shared with the kernel above), warps 2-3: idle (they only give their
 //   registers away), warps 4-7: softmax of Q tile 0, warps 8-11: softmax of Q tile 1.
@@ -924,6 +1058,7 @@ attn_fwd_row_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 // multicasts to both CTAs' s_full / pv_half / o_done / kv_empty.
 // ------------------------------------------------------------------------------------------------------------------------
 struct AttnPairSmem {
+    using Cfg = AttnCfg<128>;                          // TMEM column map: the one-CTA layout S0 | S1 | O0 | O1
     static constexpr int kTileBytes = 128 * 128 * 2;  // one Q tile
     static constexpr int kSlabBytes = 128 * 64 * 2;   // Q: 128 rows x 64 columns (one 128-byte swizzle slab)
     static constexpr int kStageBytes = 64 * 128 * 2;  // half a K tile (64 rows x 128 cols = two 8 KB slabs) or half a V tile (128 rows x 64 cols)
@@ -1196,6 +1331,24 @@ static int launch_attn_d(const CUtensorMap& tmQ, const CUtensorMap& tmK, const C
     return 0;
 }
 
+// Short-KV launches (see attn_fwd_short_kernel): chosen when a CTA would see at most kShortMaxKvTiles KV tiles.  VAP_ATTN_SHORT=0 / 1 forces it off / on.
+constexpr int kShortMaxKvTiles = 8;  // measured (tools/attn_short_ab.py, profiles/r02_attn_short_ab.json): ahead up to 1024 KV rows, behind from 2048
+static int attn_short_mode() {
+    const char* e = getenv("VAP_ATTN_SHORT");
+    return (e && *e) ? (e[0] == '1' ? 1 : 0) : -1;
+}
+template <int D>
+static int launch_attn_short(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const AttnParams& p, cudaStream_t stream) {
+    using Cfg = AttnCfg<D, 1>;
+    static_assert(2 * (Cfg::kSmemBytes + 1024) <= 233472, "two CTAs per SM");
+    static bool opted_in[64] = {};
+    if (int rc = smem_opt_in(attn_fwd_short_kernel<D>, Cfg::kSmemBytes, opted_in)) return rc;
+    const dim3 grid(static_cast<unsigned>((p.Lq + kBlockM - 1) / kBlockM), p.H, p.B * p.kv_splits);
+    attn_fwd_short_kernel<D><<<grid, kShortThreads, Cfg::kSmemBytes, stream>>>(tmQ, tmK, tmV, p);
+    VAP_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 static int launch_attn_pair(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const AttnParams& p, cudaStream_t stream) {
     static_assert(AttnPairSmem::kSmemBytes <= 232448, "shared memory budget");
     static bool opted_in[64] = {};
@@ -1254,6 +1407,10 @@ int launch_attention_fwd(const AttnTensor& q, const AttnTensor& k, const AttnTen
     if (make_attn_tmap(&tmK, k, p.B, p.H, p.Lkv, D, cluster ? kBlockN / 2 : kBlockN, "k")) return -3;
     if (make_attn_tmap(&tmV, v, p.B, p.H, p.Lkv, D, cluster ? kBlockN / 2 : kBlockN, "v")) return -3;
     const bool row = attn_row_mode();
+    const int kv_tiles_per_cta = ((p.Lkv + kBlockN - 1) / kBlockN + p.kv_splits - 1) / p.kv_splits;
+    const int short_mode = attn_short_mode();
+    if (!cluster && !row && (short_mode == 1 || (short_mode == -1 && kv_tiles_per_cta <= kShortMaxKvTiles)))
+        return D == 128 ? launch_attn_short<128>(tmQ, tmK, tmV, p, stream) : launch_attn_short<64>(tmQ, tmK, tmV, p, stream);
     return D == 128 ? launch_attn_variant<128>(cluster, row, tmQ, tmK, tmV, p, stream) : launch_attn_variant<64>(cluster, row, tmQ, tmK, tmV, p, stream);
 }
 
