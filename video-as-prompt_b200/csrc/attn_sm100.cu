@@ -588,8 +588,14 @@ __device__ __forceinline__ void attn_softmax_lane16(const Smem& sm, const AttnPa
             l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
             l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
         }
+#if VAP_ATTN_TRACE
+        if (tr && i == 0) tr[1024 + 14] = clock64();  // last P published
+#endif
         mbar_wait(sm.o_done(i), 0);
         tc_fence_after();
+#if VAP_ATTN_TRACE
+        if (tr && i == 0) tr[1024 + 15] = clock64();  // O complete
+#endif
         const float inv_l[2] = {1.f / l[0], 1.f / l[1]};
         const int row[2] = {q0 + i * kBlockM + row0_in_tile, q0 + i * kBlockM + row0_in_tile + 8};
         // plain mode: one output tensor; peer mode (Ulysses exchange #2 fused into the epilogue): the query rows of rank r are
@@ -690,8 +696,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 // rows, half of the TMEM (S | O = 256 columns), a Q tile and a TWO-slot K / V ring (96 KB of shared memory at D = 128), ten warps (producer,
 // MMA issuer, the eight softmax warps of the 16-lane organisation above — same code), so two CTAs are resident per SM and one's prologue /
 // epilogue / load bubbles overlap the other's tile steps.  Ring protocol with two slots: K_j and V_j alternate between them; the issuer waits
-// for V_j before the PV MMAs and for K_{j+1} only right before QK^T(j+1), releases V_j's slot behind QK^T(j+1) and K_{j+1}'s slot behind it too
-// (the commit covers every earlier MMA), so the producer refills a slot while the softmax of the next step runs.
+// for V_j before the PV MMAs and for K_{j+1} only right before QK^T(j+1), releases V_j's slot behind PV(j) and K_{j+1}'s slot behind QK^T(j+1)
+// (a commit covers every earlier MMA), so the producer refills a slot while the softmax of the next step runs.
 // ------------------------------------------------------------------------------------------------------------------------
 constexpr int kShortThreads = (kFirstSoftmaxWarp + kSoftmaxWarps / 2) * 32;  // 10 warps
 
@@ -754,6 +760,7 @@ __device__ __forceinline__ void attn_mma_warp_short(const AttnSmem<D, 1>& sm, ui
         mbar_wait(sm.p_full(0, 1), par);
         tc_fence_after();
         issue_pv_half(1, kv_smem + v_stage * Cfg::kTileBytes, 1u);
+        commit(sm.kv_empty(v_stage));  // V_j's slot is free as soon as PV(j) has read it: V_{j+1} gets QK^T(j+1) + half a softmax pass to arrive
         if (has_next) {
             const int k_stage = stage;
             mbar_wait(sm.kv_full(stage), phase);  // K_{j+1}: its slot was released behind QK^T(j), it has had a whole softmax pass to arrive
@@ -761,11 +768,9 @@ __device__ __forceinline__ void attn_mma_warp_short(const AttnSmem<D, 1>& sm, ui
             tc_fence_after();
             issue_qk(kv_smem + k_stage * Cfg::kTileBytes);
             commit(sm.s_full(0));  // also covers PV(j): O is quiescent when the softmax sees S(j+1)
-            commit(sm.kv_empty(v_stage));
             commit(sm.kv_empty(k_stage));
         } else {
             commit(sm.o_done(0));
-            commit(sm.kv_empty(v_stage));
         }
     }
 }
@@ -779,6 +784,12 @@ attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const AttnWork wk(p, 1);
+#if VAP_ATTN_TRACE
+    // kernel-level stamps of CTA (0,0,0) in the unused columns 6 / 7 of the issuer's rows (tools/attn_short_trace.py): [1024 + 6] entry, [+ 7] set-up
+    // done, [+ 14] last P published, [+ 15] O complete (both by the softmax code), [+ 22] O stored, [+ 23] exit
+    long long* trk = (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == kFirstSoftmaxWarp && lane == 0) ? p.trace + 1024 : nullptr;
+    if (trk) trk[6] = clock64();
+#endif
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQ);
@@ -795,6 +806,9 @@ attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(sm.tmem_ptr_addr()));
+#if VAP_ATTN_TRACE
+    if (trk) trk[7] = clock64();
+#endif
 
     if (warp == 0) {
         attn_producer_warp<D, 1, 1>(sm, &tmQ, &tmK, &tmV, wk.q0, wk.head, wk.batch, wk.j0, wk.n_kv, 0);
@@ -803,6 +817,9 @@ attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     } else {
         attn_softmax_lane16<D, false>(sm, p, wk, tmem_base, warp, lane);
     }
+#if VAP_ATTN_TRACE
+    if (trk) trk[22] = clock64();
+#endif
 
     tc_fence_before();
     __syncthreads();
@@ -810,6 +827,9 @@ attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         tc_fence_after();
         tmem_dealloc(tmem_base, Cfg::kTmemCols);
     }
+#if VAP_ATTN_TRACE
+    if (trk) trk[23] = clock64();
+#endif
 }
 
 

@@ -153,6 +153,13 @@ def _packed(owner: nn.Module, name: str, linears: List[nn.Linear]) -> Tuple[torc
             return cache[name]
         W = torch.cat([l.weight.detach() for l in linears], dim=0).contiguous()
         bvec = torch.cat([l.bias.detach() for l in linears], dim=0).contiguous() if has_bias else None
+        if W.is_cuda:
+            # Re-pointing the parameters below FREES their old storages.  The caching allocator hands such a block straight back to the stream it
+            # was allocated on, while the copies above may still be queued on ANOTHER stream — the expert's modules are packed on the side stream of
+            # the two-stream block schedule (streams.py), their weights were allocated on the default stream: a main-stream allocation could then
+            # overwrite a weight before it has been copied (seen on a B200 as garbage in the expert stream of one block).  Packing happens once
+            # per module: wait for the copies.
+            torch.cuda.current_stream(W.device).synchronize()
         r = 0
         for l in linears:
             n = l.weight.shape[0]
