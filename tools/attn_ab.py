@@ -59,7 +59,7 @@ def main():
         libs = {k: v for k, v in libs.items() if k in a.only.split(",")}
     variants = []
     for name in libs:
-        modes = ["row"] if name.startswith("row") else ["lane16"] if name.startswith("l16") else ["pair"] if name.startswith("pair") else ["lane16", "pair", "row"]
+        modes = ["row"] if name.startswith("row") else ["lane16"] if name.startswith("l16") else ["pair"] if name.startswith("pair") else ["lane16", "short", "pair", "row"]
         for m in modes:
             if a.modes and m not in a.modes.split(","):
                 continue
@@ -90,6 +90,7 @@ def main():
             use_lib(libs[name])
             os.environ["VAP_ATTN_SOFTMAX"] = "row" if mode == "row" else "lane16"
             os.environ["VAP_ATTN_PAIR"] = "1" if mode == "pair" else "0"  # CTA-pair kernel (cta_group::2), D = 128 only
+            os.environ["VAP_ATTN_SHORT"] = "1" if mode == "short" else "0"  # one Q tile per CTA, two CTAs per SM (the short-KV kernel) forced on
             os.environ["VAP_ATTN_CLUSTER"] = cl
             for sh, (q, k, v, ref, tail, flop) in data.items():
                 key = f"{sh}/{name}/{mode}/cl{cl}"
@@ -115,6 +116,7 @@ def main():
         print(json.dumps({"round": rnd, **{k: v for k, v in res.items()}}), flush=True)
     os.environ.pop("VAP_ATTN_SOFTMAX", None)
     os.environ.pop("VAP_ATTN_PAIR", None)
+    os.environ.pop("VAP_ATTN_SHORT", None)
     os.environ.pop("VAP_ATTN_CLUSTER", None)
     best = {}
     for key, r in res.items():
