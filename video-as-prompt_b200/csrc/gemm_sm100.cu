@@ -13,8 +13,9 @@
 //   warp 0   : TMA producer  (A tile 128x64, W tile BNx64 per stage, SWIZZLE_128B, kStages-deep mbarrier ring)
 //   warp 1   : MMA issuer    (one elected thread, tcgen05.mma cta_group::1 kind::f16, M=128 N=BN K=16)
 //   warp 2   : TMEM allocator (2 accumulator stages x BN fp32 columns)
-//   warps 4-7: epilogue      (tcgen05.ld -> bias / GELU / gated residual with the reference's bf16 rounding
-//                             points -> 16-byte global stores), overlapped with the next tile's main loop.
+//   warps 4-11: epilogue     (tcgen05.ld -> bias / GELU / gated residual with the reference's bf16 rounding
+//                             points -> 16-byte global stores), overlapped with the next tile's main loop; two warps per
+//                             TMEM lane quarter, each draining half of the row's columns (VAP_GEMM_EPI_WARPS = 8)
 #include <cstdlib>
 #include <cstring>
 #include "vap_kernels.cuh"
